@@ -1,0 +1,216 @@
+/*
+ * cumind_b200.h — C ABI of the B200-native CuMind search hot path.
+ *
+ * The reference (carletonai/CuMind v0.1.7) has no FFI of its own: its boundary is the
+ * Python surface Agent.select_action -> MCTS.search -> CuMindNetwork.{initial,recurrent}_inference
+ * (src/cumind/agent/agent.py:61-89, src/cumind/core/mcts.py:115-222,
+ * src/cumind/core/network.py:288-315).  Each entry point below names the reference
+ * function it replaces.  Everything is `extern "C"`, plain pointers and sizes; no torch
+ * or jax types.  INTEGRATION.md shows the ctypes and jax.ffi bindings.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; cumind_last_error()
+ *     returns a thread-local, NUL-terminated description of the last failure.
+ *   - pointers named d_* are DEVICE pointers owned by the caller (torch / XLA buffers);
+ *     pointers named h_* are HOST pointers.  Nothing is allocated after *_create.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all
+ *     device entry points are asynchronous with respect to the host.
+ *   - one host thread per device.
+ */
+#ifndef CUMIND_B200_H
+#define CUMIND_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUMIND_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------------------------
+ * Network descriptor + flat parameter blob.
+ *
+ * Mirrors the constructor of CuMindNetwork (network.py:272-286).  The parameter blob is one
+ * contiguous fp32 array holding the reference's parameter tree in this
+ * order (all kernels row-major exactly as flax stores them, [in,out] / [kh,kw,cin,cout]):
+ *
+ *   representation_network/encoder
+ *     vector obs (obs_ndim==1):  for i in 0..L-1:  layers/i/kernel[in_i,H], layers/i/bias[H]
+ *                                (in_0 = obs_shape[0], in_i = H)
+ *     image  obs (obs_ndim==3):  initial_conv/kernel[3,3,C,Cc], initial_conv/bias[Cc]
+ *                                for i in 0..L-1: conv1/kernel[3,3,Cc,Cc], conv1/bias[Cc],
+ *                                   bn1/{scale,bias,mean,var}[Cc], conv2/kernel, conv2/bias,
+ *                                   bn2/{scale,bias,mean,var}[Cc]
+ *                                final_dense/kernel[Cc,H], final_dense/bias[H]
+ *                                (C = obs_shape[2]: the LAST axis is channels, network.py:127)
+ *   dynamics_network:   action_embedding/embedding[A,H]; for l in 0..L-1: layers/l/kernel[H,H],
+ *                       layers/l/bias[H]; reward_head/kernel[H,1], reward_head/bias[1]
+ *   prediction_network: policy_head/kernel[H,A], policy_head/bias[A];
+ *                       value_head/kernel[H,1], value_head/bias[1]
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cumind_net_desc {
+    int32_t obs_ndim;          /* 1 (vector) or 3 (image, NHWC)                       */
+    int32_t obs_shape[3];      /* (D,0,0) or (height, width, channels)                */
+    int32_t hidden_dim;        /* H   (config.hidden_dim)                             */
+    int32_t num_blocks;        /* L   (config.num_blocks)                             */
+    int32_t action_space_size; /* A   (logits of the policy head / embedding rows)    */
+    int32_t conv_channels;     /* Cc  (config.conv_channels; ignored for vector obs)  */
+} cumind_net_desc;
+
+/* Arithmetic mode of the network kernels. */
+enum {
+    CUMIND_NET_FP32_EXACT = 0, /* pinned-order fp32 SIMT: bit-identical to oracle/ (parity mode) */
+    CUMIND_NET_BF16_TC    = 1  /* bf16 operands, fp32 accumulate on tcgen05 tensor cores          */
+};
+
+/* Tree-policy mode. */
+enum {
+    CUMIND_TREE_REFERENCE = 0  /* exactly mcts.py: +inf for n==0, no min-max Q, undiscounted
+                                  backup of parents only, root backed up twice (mcts.py:51-65,
+                                  157-203).                                                   */
+};
+
+typedef struct cumind_search_cfg {
+    int32_t num_simulations;      /* S        config.num_simulations          (mcts.py:139) */
+    int32_t action_space_size;    /* A_cfg    config.action_space_size; children per node =
+                                              min(A_cfg, net A) (zip truncation, mcts.py:88) */
+    double  c_puct;               /*          config.c_puct                   (mcts.py:169) */
+    double  exploration_fraction; /* f        config.exploration_fraction     (mcts.py:222) */
+    double  dirichlet_alpha;      /* alpha    config.dirichlet_alpha          (mcts.py:218) */
+    int32_t noise_mode;           /* 0 none (add_noise=False); 1 explicit d_noise[B,A_tree] f64;
+                                     2 on-device Philox Dirichlet(alpha) from (seed, tree index) */
+    int32_t net_mode;             /* CUMIND_NET_*                                            */
+    int32_t tree_mode;            /* CUMIND_TREE_*                                           */
+    int32_t lanes_per_tree;       /* 0 = auto; else 2,4,8,16,32 (tuning knob, no effect on results) */
+    uint64_t seed;                /* Philox key for noise_mode 2                             */
+    uint64_t tree_index_base;     /* global index of local tree 0 (multi-GPU sharding: results
+                                     do not depend on the GPU count)                         */
+} cumind_search_cfg;
+
+typedef struct cumind_net  cumind_net;   /* opaque: packed parameters on one device  */
+typedef struct cumind_tree cumind_tree;  /* opaque: view over a caller-owned SoA slab */
+
+const char* cumind_last_error(void);
+int         cumind_abi_version(void);
+
+/* Number of fp32 values in the parameter blob for `desc` (0 on invalid desc). */
+size_t cumind_param_count(const cumind_net_desc* desc);
+
+/* Replaces CuMindNetwork.__init__ + nnx.update (network.py:272-286, agent.py:109-121):
+ * copies the host blob to the current device and builds the kernel-side layouts
+ * (bf16 copies for the tensor-core mode).  h_params has cumind_param_count(desc) floats. */
+int cumind_net_create(const cumind_net_desc* desc, const float* h_params, size_t n_params,
+                      cumind_net** out);
+int cumind_net_update_params(cumind_net* net, const float* h_params, size_t n_params, void* stream);
+int cumind_net_destroy(cumind_net* net);
+
+/* CuMindNetwork.initial_inference (network.py:288-300).
+ * d_obs [B, *obs_shape] fp32 -> d_hidden [B,H], d_logits [B,A] (may be NULL), d_value [B] (may be NULL). */
+int cumind_initial_inference(const cumind_net* net, const float* d_obs, int32_t B,
+                             float* d_hidden, float* d_logits, float* d_value,
+                             int32_t net_mode, void* stream);
+
+/* CuMindNetwork.recurrent_inference (network.py:302-315) = DynamicsNetwork.__call__ (217-236)
+ * followed by PredictionNetwork.__call__ (254-266).
+ * d_hidden [B,H], d_action [B] int32 -> d_next [B,H], d_reward [B], d_logits [B,A], d_value [B]
+ * (any output may be NULL). */
+int cumind_recurrent_inference(const cumind_net* net, const float* d_hidden, const int32_t* d_action,
+                               int32_t B, float* d_next, float* d_reward, float* d_logits,
+                               float* d_value, int32_t net_mode, void* stream);
+
+/* PredictionNetwork.__call__ alone (network.py:254-266; called directly at mcts.py:127,190). */
+int cumind_prediction(const cumind_net* net, const float* d_hidden, int32_t B,
+                      float* d_logits, float* d_value, int32_t net_mode, void* stream);
+
+/* jax.nn.softmax over the last axis with the pinned exp (mcts.py:128,191). d_logits/d_probs [B,A]. */
+int cumind_softmax(const float* d_logits, int32_t B, int32_t A, float* d_probs, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Tree storage: B independent trees as structure-of-arrays in one caller-owned device slab.
+ * Replaces the Python `Node` object graph (mcts.py:18-98).  Node slots per tree:
+ *   N = 1 + A_tree*(S_max+1); slot 0 is the root; the e-th expansion (e=0 is the root) owns
+ *   child slots 1+e*A_tree .. 1+(e+1)*A_tree-1 and hidden-state row e.
+ * ------------------------------------------------------------------------------------------ */
+size_t cumind_tree_bytes(int32_t B, int32_t S_max, int32_t A_tree, int32_t H);
+int cumind_tree_create(int32_t B, int32_t S_max, int32_t A_tree, int32_t H,
+                       void* d_slab, size_t slab_bytes, cumind_tree** out);
+int cumind_tree_destroy(cumind_tree* tree);
+
+/* Device pointers of the SoA arrays inside the slab (for parity dumps / zero-copy readers). */
+typedef struct cumind_tree_view {
+    int32_t B, S_max, A, H, N;
+    int32_t* visit;        /* [B,N]        Node.visit_count                                  */
+    double*  value_sum;    /* [B,N]        Node.value_sum (float64, mcts.py:29)              */
+    float*   prior;        /* [B,N]        Node.prior as produced by the fp32 softmax        */
+    double*  root_prior;   /* [B,A]        root children priors after noise mixing (float64) */
+    int32_t* child_eidx;   /* [B,N]        -1 if not expanded, else expansion index e        */
+    int32_t* exp_node;     /* [B,S_max+1]  slot of the e-th expanded node                    */
+    float*   hidden;       /* [B,S_max+1,H] Node.hidden_state of the e-th expanded node      */
+    int32_t* path;         /* [B,S_max+2]  scratch: parents on the current path (step API)   */
+    int32_t* path_len;     /* [B]                                                            */
+    int32_t* leaf;         /* [B]          scratch: slot of the selected leaf                */
+    int32_t* n_expanded;   /* [B]          expansions so far (root included)                 */
+    int64_t* depth_sum;    /* [B]          sum of path lengths over all simulations          */
+} cumind_tree_view;
+int cumind_tree_get_view(const cumind_tree* tree, cumind_tree_view* out);
+
+/* MCTS.search (mcts.py:115-155) for B trees in lockstep, all on device, one fused launch:
+ * root prediction + softmax + root expand + optional noise + S x (select, dynamics, prediction,
+ * expand, backup) + visit-count normalisation.
+ *   d_root_hidden [B,H] fp32            (output of initial_inference)
+ *   d_noise       [B,A_tree] f64 or NULL (noise_mode 1)
+ *   d_out_visits  [B,A_cfg] int32       root.children[a].visit_count
+ *   d_out_probs   [B,A_cfg] f64         visits/sum, uniform if sum==0 (mcts.py:143-153)
+ *   d_out_root_value [B] f64 or NULL    root.value_sum / root.visit_count
+ * The full trees stay in `tree` for inspection. */
+int cumind_search(cumind_tree* tree, const cumind_net* net, const float* d_root_hidden,
+                  const cumind_search_cfg* cfg, const double* d_noise,
+                  int32_t* d_out_visits, double* d_out_probs, double* d_out_root_value,
+                  void* stream);
+
+/* Same search issued as separate kernels per phase (the fine-grained entry points below);
+ * used by the tests to cross-check the fused kernel and by ncu to attribute time per phase. */
+int cumind_search_stepwise(cumind_tree* tree, const cumind_net* net, const float* d_root_hidden,
+                           const cumind_search_cfg* cfg, const double* d_noise,
+                           int32_t* d_out_visits, double* d_out_probs, double* d_out_root_value,
+                           void* stream);
+
+/* Agent.select_action for a batch (agent.py:61-89, training=False argmax path; the sampling
+ * draw of training=True stays on the host): HOST observations in, HOST results out.
+ * h_obs [B,*obs_shape] fp32 (pinned or pageable) -> h_actions [B] int32 (first arg-max of
+ * probs), h_probs [B,A_cfg] f64.  Performs H2D, initial_inference, search, D2H and
+ * synchronises `stream`.  d_work is a caller-owned device scratch of
+ * cumind_select_actions_work_bytes() bytes. */
+size_t cumind_select_actions_work_bytes(const cumind_net_desc* desc, int32_t B, int32_t A_cfg);
+int cumind_select_actions_host(cumind_tree* tree, const cumind_net* net, const float* h_obs,
+                               const cumind_search_cfg* cfg, const double* h_noise,
+                               int32_t* h_actions, double* h_probs, void* d_work, size_t work_bytes,
+                               void* stream);
+
+/* Fine-grained phases (one launch each).  Reference anchors:
+ *   cumind_tree_init_root : mcts.py:126-136  (root prediction softmax, expand, noise)
+ *   cumind_select         : mcts.py:165-171  (Node.select_child / ucb_score, 51-76)
+ *   cumind_expand         : mcts.py:181-196  (dynamics, prediction, softmax, Node.expand 78-89)
+ *   cumind_backup         : mcts.py:199-203  (Node.backup 91-98; root twice)
+ *   cumind_finalize       : mcts.py:143-155
+ *   cumind_dirichlet      : mcts.py:218      (np.random.dirichlet; Philox4x32-10 here)        */
+int cumind_tree_init_root(cumind_tree* tree, const cumind_net* net, const float* d_root_hidden,
+                          const cumind_search_cfg* cfg, const double* d_noise, void* stream);
+int cumind_select(cumind_tree* tree, const cumind_search_cfg* cfg, void* stream);
+int cumind_expand(cumind_tree* tree, const cumind_net* net, const cumind_search_cfg* cfg,
+                  float* d_leaf_value, void* stream);
+int cumind_backup(cumind_tree* tree, const float* d_leaf_value, void* stream);
+int cumind_finalize(cumind_tree* tree, const cumind_search_cfg* cfg, int32_t* d_out_visits,
+                    double* d_out_probs, double* d_out_root_value, void* stream);
+int cumind_dirichlet(double* d_noise, int32_t B, int32_t A, double alpha, uint64_t seed,
+                     uint64_t tree_index_base, void* stream);
+
+/* Counters: kernels launched by this library since load (bench.py reports the delta). */
+uint64_t cumind_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUMIND_B200_H */
