@@ -1,0 +1,131 @@
+"""Agent with the reference's surface (src/cumind/agent/agent.py:20-121) driving the B200 search.
+
+  Agent(config, existing_state=None)              agent.py:23-59
+  select_action(observation, training=False)      agent.py:61-89   (one environment)
+  select_actions(observations[B,...], training)   batched extension: B environments, one fused search
+  update_target_network / save_state / load_state agent.py:91-121
+The optimiser is carried as hyper-parameters + AdamW moment arrays so checkpoints round-trip; the
+training step itself is outside this round's hot path.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native, params as P
+from .config import Config
+from .mcts import MCTS
+from .network import CuMindNetwork, _stream_ptr
+from .prng import Rngs, key
+
+
+class AdamW:
+    """Hyper-parameters of optax.adamw(learning_rate, weight_decay) (agent.py:48)."""
+
+    def __init__(self, learning_rate: float, weight_decay: float, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8):
+        self.learning_rate, self.weight_decay, self.b1, self.b2, self.eps = learning_rate, weight_decay, b1, b2, eps
+
+    def init(self, blob: np.ndarray) -> Dict[str, Any]:
+        return {"count": 0, "mu": np.zeros_like(blob), "nu": np.zeros_like(blob)}
+
+
+class Agent:
+    def __init__(self, config: Config, existing_state: Optional[Dict[str, Any]] = None):
+        self.config = config
+        if not torch.cuda.is_available():
+            raise _native.CuMindNativeError("cumind_b200 needs a CUDA device (there is no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        key.seed(config.seed)
+        rngs = Rngs(params=key())
+        self.network = CuMindNetwork(observation_shape=config.observation_shape, action_space_size=config.action_space_size,
+                                     hidden_dim=config.hidden_dim, num_blocks=config.num_blocks,
+                                     conv_channels=config.conv_channels, rngs=rngs, device=self.device)
+        self.target_network = self.network.clone()
+        self.optimizer = AdamW(config.learning_rate, config.weight_decay)
+        if existing_state:
+            self.load_state(existing_state)
+        else:
+            self.optimizer_state = self.optimizer.init(self.network.blob)
+        self.mcts = MCTS(self.network, config)
+        self._rng = np.random.default_rng(key())
+        self._work: Optional[torch.Tensor] = None
+        self._pinned: Dict[str, torch.Tensor] = {}
+
+    # ---- action selection ------------------------------------------------------------------------
+    def select_action(self, observation: np.ndarray, training: bool = False) -> Tuple[int, np.ndarray]:
+        """encode -> search -> argmax (eval) or sample (training)  — agent.py:61-89."""
+        obs = np.asarray(observation, dtype=np.float32)[None]
+        hidden, _, _ = self.network.initial_inference(obs)
+        action_probs = self.mcts.search(root_hidden_state=hidden[0], add_noise=training)
+        if training:
+            action_idx = int(self._rng.choice(len(action_probs), p=action_probs))
+        else:
+            action_idx = int(np.argmax(action_probs))
+        return action_idx, action_probs
+
+    def select_actions(self, observations: np.ndarray, training: bool = False, noise: Optional[np.ndarray] = None,
+                       philox_seed: Optional[int] = None, tree_index_base: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+        """Batched select_action through ONE C-ABI call with host buffers (cumind_select_actions_host):
+        H2D of the observations, initial_inference, fused search, first-arg-max, D2H of actions+probs.
+        training=True draws root noise on the device (Philox) unless `noise` [B,A] is given, and
+        samples the actions on the host from the returned probabilities."""
+        net, lib = self.network, self.mcts._lib
+        obs = np.ascontiguousarray(observations, dtype=np.float32)
+        B = obs.shape[0]
+        if tuple(obs.shape[1:]) != tuple(net.observation_shape):
+            raise ValueError(f"expected observations of shape (B, {net.observation_shape}), got {obs.shape}")
+        A_cfg = int(self.config.action_space_size)
+        A = min(A_cfg, net.action_space_size)
+        tree = self.mcts._tree(B, int(self.config.num_simulations), A)
+        mode = 0
+        if noise is not None:
+            mode = 1
+        elif training or philox_seed is not None:
+            mode = 2
+            if philox_seed is None:
+                philox_seed = int(self._rng.integers(0, 2**63 - 1))
+        cfg = self.mcts._cfg(mode, philox_seed or 0, tree_index_base)
+        need = int(lib.cumind_select_actions_work_bytes(C.byref(net._desc), B, A_cfg))
+        if self._work is None or self._work.numel() < need + 256:
+            self._work = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+        wbase = self._work.data_ptr() + ((-self._work.data_ptr()) % 256)
+        pin = self._pinned
+        if "obs" not in pin or pin["obs"].shape != obs.shape:
+            pin["obs"] = torch.empty(obs.shape, dtype=torch.float32).pin_memory()
+            pin["actions"] = torch.empty((B,), dtype=torch.int32).pin_memory()
+            pin["probs"] = torch.empty((B, A_cfg), dtype=torch.float64).pin_memory()
+            pin["noise"] = torch.empty((B, A), dtype=torch.float64).pin_memory()
+        pin["obs"].numpy()[...] = obs
+        h_noise = None
+        if noise is not None:
+            pin["noise"].numpy()[...] = np.asarray(noise, dtype=np.float64)
+            h_noise = pin["noise"]
+        with torch.cuda.device(self.device):
+            _native.check(lib.cumind_select_actions_host(
+                tree.handle, net._handle, C.c_void_p(pin["obs"].data_ptr()), C.byref(cfg),
+                C.c_void_p(h_noise.data_ptr() if h_noise is not None else 0), C.c_void_p(pin["actions"].data_ptr()),
+                C.c_void_p(pin["probs"].data_ptr()), C.c_void_p(wbase), need, _stream_ptr()))
+        probs = pin["probs"].numpy().copy()
+        if training:
+            cdf = np.cumsum(probs, axis=1)
+            u = self._rng.random(B)[:, None] * cdf[:, -1:]
+            actions = np.minimum((u >= cdf).sum(axis=1), A_cfg - 1).astype(np.int32)
+        else:
+            actions = pin["actions"].numpy().copy()
+        return actions, probs
+
+    # ---- state -----------------------------------------------------------------------------------
+    def update_target_network(self) -> None:
+        self.target_network.load_state(self.network.state())
+
+    def save_state(self) -> Dict[str, Any]:
+        return {"network_state": self.network.state(), "optimizer_state": self.optimizer_state}
+
+    def load_state(self, state: Dict[str, Any]) -> None:
+        self.network.load_state(state["network_state"])
+        self.optimizer_state = state["optimizer_state"]
+        self.update_target_network()

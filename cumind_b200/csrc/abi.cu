@@ -1,0 +1,581 @@
+// abi.cu — the C ABI of include/cumind_b200.h: handles, validation, kernel selection.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace cm;
+
+// ------------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------------
+struct cumind_net {
+    cumind_net_desc desc;
+    int device;
+    int sm_count;
+    size_t n_params;
+    float* d_blob;
+    float* d_pack;
+    BlobLayout lo;
+    PackLayout pk;
+    float* d_work;        // activation workspace of the image encoder (lazily sized, grow-only)
+    size_t work_bytes;
+    std::vector<float> h_pack;
+};
+
+struct cumind_tree {
+    TreeView tv;
+    float* leaf_value;  // [B] scratch of the stepwise path
+    size_t bytes;
+};
+
+static thread_local std::string g_err;
+static std::atomic<unsigned long long> g_launches{0};
+
+static int fail(const std::string& msg) {
+    g_err = msg;
+    return 1;
+}
+static int fail_cuda(const char* what, cudaError_t e) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return 2;
+}
+#define CM_CUDA(call)                                         \
+    do {                                                      \
+        cudaError_t _e = (call);                              \
+        if (_e != cudaSuccess) return fail_cuda(#call, _e);   \
+    } while (0)
+
+extern "C" const char* cumind_last_error(void) { return g_err.c_str(); }
+extern "C" int cumind_abi_version(void) { return CUMIND_ABI_VERSION; }
+extern "C" uint64_t cumind_launch_count(void) { return g_launches.load(); }
+
+extern "C" size_t cumind_param_count(const cumind_net_desc* desc) {
+    if (!desc_valid(desc)) return 0;
+    return make_blob_layout(desc).total;
+}
+
+static NetView view_of(const cumind_net* n) {
+    NetView v;
+    v.desc = n->desc;
+    v.blob = n->d_blob;
+    v.lo = n->lo;
+    v.pack = n->d_pack;
+    v.pk = n->pk;
+    return v;
+}
+
+// canonical blob -> PackLayout (emb | layers | heads [H][HP] | head biases)
+static void build_pack(const cumind_net* n, const float* blob, std::vector<float>& pack) {
+    const PackLayout& pk = n->pk;
+    const BlobLayout& lo = n->lo;
+    const int H = pk.H, L = pk.L, A = pk.A, HP = pk.HP;
+    pack.assign(pk.total, 0.0f);
+    memcpy(&pack[pk.emb], blob + lo.emb, sizeof(float) * (size_t)A * H);
+    memcpy(&pack[pk.layers], blob + lo.dyn, sizeof(float) * (size_t)L * ((size_t)H * H + H));
+    for (int k = 0; k < H; ++k) {
+        for (int a = 0; a < A; ++a) pack[pk.heads_w + (size_t)k * HP + a] = blob[lo.pol_k + (size_t)k * A + a];
+        pack[pk.heads_w + (size_t)k * HP + A] = blob[lo.val_k + k];
+        pack[pk.heads_w + (size_t)k * HP + A + 1] = blob[lo.rew_k + k];
+    }
+    for (int a = 0; a < A; ++a) pack[pk.heads_b + a] = blob[lo.pol_b + a];
+    pack[pk.heads_b + A] = blob[lo.val_b];
+    pack[pk.heads_b + A + 1] = blob[lo.rew_b];
+}
+
+extern "C" int cumind_net_create(const cumind_net_desc* desc, const float* h_params, size_t n_params, cumind_net** out) {
+    if (!out) return fail("cumind_net_create: out is NULL");
+    *out = nullptr;
+    if (!desc_valid(desc)) {
+        if (desc && desc->obs_ndim != 1 && desc->obs_ndim != 3)
+            return fail("Unsupported observation shape: observation must be 1-D or 3-D");  // network.py:179-180
+        return fail("cumind_net_create: invalid descriptor");
+    }
+    const BlobLayout lo = make_blob_layout(desc);
+    if (n_params != lo.total || !h_params) return fail("cumind_net_create: parameter blob has the wrong size");
+    cumind_net* n = new (std::nothrow) cumind_net();
+    if (!n) return fail("cumind_net_create: out of host memory");
+    n->desc = *desc;
+    n->lo = lo;
+    n->pk = make_pack_layout(desc->hidden_dim, desc->num_blocks, desc->action_space_size);
+    n->n_params = n_params;
+    n->d_blob = n->d_pack = n->d_work = nullptr;
+    n->work_bytes = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&n->device)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&n->sm_count, cudaDevAttrMultiProcessorCount, n->device)) != cudaSuccess ||
+        (e = cudaMalloc(&n->d_blob, sizeof(float) * lo.total)) != cudaSuccess ||
+        (e = cudaMalloc(&n->d_pack, sizeof(float) * n->pk.total)) != cudaSuccess) {
+        cudaFree(n->d_blob); cudaFree(n->d_pack);
+        delete n;
+        return fail_cuda("cumind_net_create", e);
+    }
+    *out = n;
+    int rc = cumind_net_update_params(n, h_params, n_params, nullptr);
+    if (rc != 0) { cumind_net_destroy(n); *out = nullptr; return rc; }
+    CM_CUDA(cudaStreamSynchronize(nullptr));
+    return 0;
+}
+
+extern "C" int cumind_net_update_params(cumind_net* n, const float* h_params, size_t n_params, void* stream) {
+    if (!n || !h_params) return fail("cumind_net_update_params: NULL argument");
+    if (n_params != n->n_params) return fail("cumind_net_update_params: parameter blob has the wrong size");
+    cudaStream_t st = (cudaStream_t)stream;
+    build_pack(n, h_params, n->h_pack);
+    CM_CUDA(cudaMemcpyAsync(n->d_blob, h_params, sizeof(float) * n_params, cudaMemcpyHostToDevice, st));
+    CM_CUDA(cudaMemcpyAsync(n->d_pack, n->h_pack.data(), sizeof(float) * n->pk.total, cudaMemcpyHostToDevice, st));
+    CM_CUDA(cudaStreamSynchronize(st));  // h_pack is reused by the next update
+    return 0;
+}
+
+extern "C" int cumind_net_destroy(cumind_net* n) {
+    if (!n) return 0;
+    cudaFree(n->d_blob);
+    cudaFree(n->d_pack);
+    cudaFree(n->d_work);
+    delete n;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// network entry points
+// ------------------------------------------------------------------------------------------------
+static int check_mode(int net_mode) {
+    if (net_mode == CUMIND_NET_FP32_EXACT) return 0;
+    return fail("net_mode not available in this build (only CUMIND_NET_FP32_EXACT)");
+}
+
+extern "C" int cumind_prediction(const cumind_net* n, const float* d_hidden, int32_t B, float* d_logits, float* d_value,
+                                 int32_t net_mode, void* stream) {
+    if (!n || !d_hidden || B < 0) return fail("cumind_prediction: bad argument");
+    if (check_mode(net_mode)) return 1;
+    if (B == 0) return 0;
+    CM_CUDA(launch_prediction(view_of(n), d_hidden, B, d_logits, d_value, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+extern "C" int cumind_initial_inference(const cumind_net* cn, const float* d_obs, int32_t B, float* d_hidden, float* d_logits,
+                                        float* d_value, int32_t net_mode, void* stream) {
+    cumind_net* n = const_cast<cumind_net*>(cn);
+    if (!n || !d_obs || !d_hidden || B < 0) return fail("cumind_initial_inference: bad argument");
+    if (check_mode(net_mode)) return 1;
+    if (B == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const NetView nv = view_of(n);
+    if (n->desc.obs_ndim == 1) {
+        CM_CUDA(launch_vector_encoder(nv, d_obs, B, d_hidden, st));
+        g_launches += 1;
+    } else {
+        if ((n->desc.conv_channels & 3) != 0) return fail("image encoder needs conv_channels % 4 == 0");
+        const int chunk = B < 128 ? B : 128;
+        const size_t need = conv_encoder_work_bytes(n->desc, chunk);
+        if (need > n->work_bytes) {
+            CM_CUDA(cudaStreamSynchronize(st));
+            cudaFree(n->d_work);
+            n->d_work = nullptr;
+            n->work_bytes = 0;
+            CM_CUDA(cudaMalloc(&n->d_work, need));
+            n->work_bytes = need;
+        }
+        CM_CUDA(launch_conv_encoder(nv, d_obs, B, d_hidden, n->d_work, chunk, st));
+        g_launches += (unsigned long long)((B + chunk - 1) / chunk) * (2 + 2 * n->desc.num_blocks);
+    }
+    if (d_logits || d_value) {
+        CM_CUDA(launch_prediction(nv, d_hidden, B, d_logits, d_value, st));
+        g_launches += 1;
+    }
+    return 0;
+}
+
+extern "C" int cumind_recurrent_inference(const cumind_net* n, const float* d_hidden, const int32_t* d_action, int32_t B,
+                                          float* d_next, float* d_reward, float* d_logits, float* d_value, int32_t net_mode,
+                                          void* stream) {
+    if (!n || !d_hidden || !d_action || B < 0) return fail("cumind_recurrent_inference: bad argument");
+    if (check_mode(net_mode)) return 1;
+    if (B == 0) return 0;
+    CM_CUDA(launch_recurrent(view_of(n), d_hidden, d_action, B, d_next, d_reward, d_logits, d_value, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+extern "C" int cumind_softmax(const float* d_logits, int32_t B, int32_t A, float* d_probs, void* stream) {
+    if (!d_logits || !d_probs || B < 0 || A <= 0) return fail("cumind_softmax: bad argument");
+    if (B == 0) return 0;
+    CM_CUDA(launch_softmax(d_logits, B, A, d_probs, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tree slab
+// ------------------------------------------------------------------------------------------------
+struct SlabOffsets {
+    size_t nodes, eidx, rprior, exp_node, hidden, path, path_len, leaf, n_exp, depth, leaf_value, total;
+};
+static SlabOffsets slab_offsets(int64_t B, int64_t S, int64_t A, int64_t H) {
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t N = 1 + A * (S + 1);
+    SlabOffsets o;
+    size_t p = 0;
+    o.nodes = p;      p = al(p + B * N * sizeof(Node));
+    o.eidx = p;       p = al(p + B * N * sizeof(int32_t));
+    o.rprior = p;     p = al(p + B * A * sizeof(double));
+    o.exp_node = p;   p = al(p + B * (S + 1) * sizeof(int32_t));
+    o.hidden = p;     p = al(p + B * (S + 1) * H * sizeof(float));
+    o.path = p;       p = al(p + B * (S + 2) * sizeof(int32_t));
+    o.path_len = p;   p = al(p + B * sizeof(int32_t));
+    o.leaf = p;       p = al(p + B * sizeof(int32_t));
+    o.n_exp = p;      p = al(p + B * sizeof(int32_t));
+    o.depth = p;      p = al(p + B * sizeof(long long));
+    o.leaf_value = p; p = al(p + B * sizeof(float));
+    o.total = p;
+    return o;
+}
+
+extern "C" size_t cumind_tree_bytes(int32_t B, int32_t S_max, int32_t A_tree, int32_t H) {
+    if (B <= 0 || S_max <= 0 || A_tree <= 0 || H <= 0) return 0;
+    return slab_offsets(B, S_max, A_tree, H).total;
+}
+
+extern "C" int cumind_tree_create(int32_t B, int32_t S_max, int32_t A_tree, int32_t H, void* d_slab, size_t slab_bytes,
+                                  cumind_tree** out) {
+    if (!out) return fail("cumind_tree_create: out is NULL");
+    *out = nullptr;
+    if (B <= 0 || S_max <= 0 || A_tree <= 0 || H <= 0) return fail("cumind_tree_create: sizes must be positive");
+    const SlabOffsets o = slab_offsets(B, S_max, A_tree, H);
+    if (!d_slab || slab_bytes < o.total) return fail("cumind_tree_create: slab too small (see cumind_tree_bytes)");
+    if (((uintptr_t)d_slab & 255) != 0) return fail("cumind_tree_create: slab must be 256-byte aligned");
+    if ((int64_t)1 + (int64_t)A_tree * (S_max + 1) > 0x7fffffff) return fail("cumind_tree_create: tree too large");
+    cumind_tree* t = new (std::nothrow) cumind_tree();
+    if (!t) return fail("cumind_tree_create: out of host memory");
+    unsigned char* b = (unsigned char*)d_slab;
+    t->tv.B = B; t->tv.S_max = S_max; t->tv.A = A_tree; t->tv.H = H; t->tv.N = 1 + A_tree * (S_max + 1);
+    t->tv.nodes = (Node*)(b + o.nodes);
+    t->tv.child_eidx = (int32_t*)(b + o.eidx);
+    t->tv.root_prior = (double*)(b + o.rprior);
+    t->tv.exp_node = (int32_t*)(b + o.exp_node);
+    t->tv.hidden = (float*)(b + o.hidden);
+    t->tv.path = (int32_t*)(b + o.path);
+    t->tv.path_len = (int32_t*)(b + o.path_len);
+    t->tv.leaf = (int32_t*)(b + o.leaf);
+    t->tv.n_expanded = (int32_t*)(b + o.n_exp);
+    t->tv.depth_sum = (long long*)(b + o.depth);
+    t->leaf_value = (float*)(b + o.leaf_value);
+    t->bytes = o.total;
+    *out = t;
+    return 0;
+}
+
+extern "C" int cumind_tree_destroy(cumind_tree* t) {
+    delete t;
+    return 0;
+}
+
+extern "C" int cumind_tree_get_view(const cumind_tree* t, cumind_tree_view* out) {
+    if (!t || !out) return fail("cumind_tree_get_view: NULL argument");
+    out->B = t->tv.B; out->S_max = t->tv.S_max; out->A = t->tv.A; out->H = t->tv.H; out->N = t->tv.N;
+    out->nodes = (cumind_node*)t->tv.nodes;
+    out->child_eidx = t->tv.child_eidx;
+    out->root_prior = t->tv.root_prior;
+    out->exp_node = t->tv.exp_node;
+    out->hidden = t->tv.hidden;
+    out->path = t->tv.path;
+    out->path_len = t->tv.path_len;
+    out->leaf = t->tv.leaf;
+    out->n_expanded = t->tv.n_expanded;
+    out->depth_sum = (int64_t*)t->tv.depth_sum;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// search
+// ------------------------------------------------------------------------------------------------
+static int check_search(const char* fn, const cumind_tree* t, const cumind_net* n, const cumind_search_cfg* c, const double* d_noise) {
+    if (!t || !n || !c) return fail(std::string(fn) + ": NULL argument");
+    if (c->num_simulations <= 0) return fail("num_simulations must be positive");      // config.py:160-162
+    if (c->action_space_size <= 0) return fail("action_space_size must be positive");  // config.py:143-145
+    if (c->num_simulations > t->tv.S_max) return fail(std::string(fn) + ": num_simulations exceeds the tree's S_max");
+    const int A_tree = c->action_space_size < n->desc.action_space_size ? c->action_space_size : n->desc.action_space_size;
+    if (A_tree != t->tv.A) return fail(std::string(fn) + ": tree was created for a different action count");
+    if (n->desc.hidden_dim != t->tv.H) return fail(std::string(fn) + ": tree was created for a different hidden_dim");
+    if (c->noise_mode < 0 || c->noise_mode > 2) return fail("noise_mode must be 0, 1 or 2");
+    if (c->noise_mode == 1 && !d_noise) return fail("noise_mode 1 needs d_noise");
+    if (c->tree_mode != CUMIND_TREE_REFERENCE) return fail("tree_mode not available in this build");
+    if (c->net_mode != CUMIND_NET_FP32_EXACT) return fail("net_mode not available in this build (only CUMIND_NET_FP32_EXACT)");
+    return 0;
+}
+
+static StepParams step_params(const cumind_tree* t, const cumind_net* n, const cumind_search_cfg* c) {
+    StepParams p;
+    p.tv = t->tv;
+    p.pack = n->d_pack;
+    p.pk = n->pk;
+    p.S = c->num_simulations;
+    p.A_cfg = c->action_space_size;
+    p.A_net = n->desc.action_space_size;
+    p.c_puct = c->c_puct;
+    p.frac = c->exploration_fraction;
+    p.one_minus_frac = 1.0 - c->exploration_fraction;  // (1 - f) in float64, mcts.py:222
+    p.alpha = c->dirichlet_alpha;
+    p.noise_mode = c->noise_mode;
+    p.seed = c->seed;
+    p.tree_base = c->tree_index_base;
+    return p;
+}
+
+// choose (G, R): R = H / G outputs per lane; valid pairs are H == G*R with R in {2,4,8,16}, or
+// H <= G with R == 1.
+static bool pick_lanes(int H, int want_G, int& G, int& R) {
+    const int cand[4] = {4, 8, 16, 32};
+    int best = -1, best_d = 1 << 30;
+    for (int i = 0; i < 4; ++i) {
+        const int g = cand[i];
+        bool ok = false;
+        if (H % g == 0) { const int r = H / g; ok = (r == 2 || r == 4 || r == 8 || r == 16); }
+        if (!ok && H <= g && (i == 0 || H > cand[i - 1])) ok = true;  // smallest G >= H, R = 1
+        if (!ok) continue;
+        int d = g > want_G ? g / want_G : want_G / g;
+        if (d < best_d) { best_d = d; best = g; }
+    }
+    if (best < 0) return false;
+    G = best;
+    R = H <= best ? 1 : H / best;
+    if (H == best) R = 1;
+    return true;
+}
+
+struct FusedPlan { int G, R, grid, block; size_t smem; FusedParams p; };
+
+static int plan_fused(const cumind_tree* t, const cumind_net* n, const cumind_search_cfg* c, FusedPlan& pl, std::string& why) {
+    const int H = n->desc.hidden_dim, B = t->tv.B;
+    const int sm = n->sm_count;
+    int want = c->lanes_per_tree;
+    if (want <= 0) {
+        const int tps = (B + sm - 1) / sm;
+        want = 256 / (tps > 0 ? tps : 1);
+        want = want < 4 ? 4 : (want > 32 ? 32 : want);
+        int p2 = 4; while (p2 * 2 <= want) p2 *= 2; want = p2;
+    }
+    if (!pick_lanes(H, want, pl.G, pl.R)) { why = "hidden_dim has no lane mapping"; return 1; }
+    const int G = pl.G;
+    const PackLayout& pk = n->pk;
+    const size_t pack_bytes = pk.total * sizeof(float);
+    const int n_sqrt = 2 * t->tv.S_max + 2;
+    const size_t off_sqrt = (pack_bytes + 15) & ~(size_t)15;
+    const size_t off_slots = (off_sqrt + (size_t)n_sqrt * sizeof(double) + 15) & ~(size_t)15;
+    const size_t slot_base = ((size_t)(2 * (H + 4) + 2 * pk.HP) * sizeof(float) + 15) & ~(size_t)15;
+    const size_t path_bytes = ((size_t)(t->tv.S_max + 2) * sizeof(int) + 15) & ~(size_t)15;
+    const size_t kMax = 227 * 1024;
+    // trees per block: one CTA per SM when the whole batch fits, else 512 threads per CTA
+    int tps = (B + sm - 1) / sm;
+    int tpb = tps * G <= 512 ? tps : 512 / G;
+    const int gran = 32 / G;  // trees per warp
+    tpb = ((tpb + gran - 1) / gran) * gran;
+    if (tpb * G > 512) tpb = 512 / G;
+    int path_in_smem = 1;
+    size_t slot = slot_base + path_bytes;
+    auto total = [&](int tpb_, size_t slot_) { return off_slots + (size_t)tpb_ * slot_ + 16; };
+    if (total(tpb, slot) > kMax) { path_in_smem = 0; slot = slot_base; }
+    while (tpb > gran && total(tpb, slot) > kMax) tpb -= gran;
+    if (total(tpb, slot) > kMax) { why = "recurrent-path parameters do not fit in shared memory"; return 1; }
+    pl.block = tpb * G;
+    pl.smem = total(tpb, slot);
+    int blocks = (B + tpb - 1) / tpb;
+    int per_sm = (int)(kMax / pl.smem);
+    if (per_sm < 1) per_sm = 1;
+    const int by_threads = 2048 / pl.block;
+    if (per_sm > by_threads) per_sm = by_threads < 1 ? 1 : by_threads;
+    if (per_sm > 1 && pl.block > 256) per_sm = 1;  // __launch_bounds__(512,1) register budget
+    const int cap = sm * per_sm;
+    pl.grid = blocks < cap ? blocks : cap;
+    FusedParams& p = pl.p;
+    p.tv = t->tv;
+    p.pack = n->d_pack;
+    p.pk = pk;
+    p.S = c->num_simulations;
+    p.A_cfg = c->action_space_size;
+    p.A_net = n->desc.action_space_size;
+    p.c_puct = c->c_puct;
+    p.frac = c->exploration_fraction;
+    p.one_minus_frac = 1.0 - c->exploration_fraction;
+    p.alpha = c->dirichlet_alpha;
+    p.noise_mode = c->noise_mode;
+    p.seed = c->seed;
+    p.tree_base = c->tree_index_base;
+    p.path_in_smem = path_in_smem;
+    p.off_sqrt = (unsigned)off_sqrt;
+    p.off_slots = (unsigned)off_slots;
+    p.slot_bytes = (unsigned)slot;
+    p.off_bar = (unsigned)(off_slots + (size_t)tpb * slot);
+    p.off_bar = (p.off_bar + 7u) & ~7u;
+    p.n_sqrt = n_sqrt;
+    return 0;
+}
+
+extern "C" int cumind_search_stepwise(cumind_tree* t, const cumind_net* n, const float* d_root_hidden, const cumind_search_cfg* c,
+                                      const double* d_noise, int32_t* d_out_visits, double* d_out_probs, double* d_out_root_value,
+                                      void* stream) {
+    if (check_search("cumind_search_stepwise", t, n, c, d_noise)) return 1;
+    if (!d_root_hidden) return fail("cumind_search_stepwise: d_root_hidden is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    const StepParams p = step_params(t, n, c);
+    CM_CUDA(launch_init_root(p, d_root_hidden, d_noise, st));
+    for (int s = 0; s < c->num_simulations; ++s) {
+        CM_CUDA(launch_select(p, st));
+        CM_CUDA(launch_expand(p, t->leaf_value, st));
+        CM_CUDA(launch_backup(p, t->leaf_value, st));
+    }
+    CM_CUDA(launch_finalize(p, d_out_visits, d_out_probs, d_out_root_value, st));
+    g_launches += 2 + 3ull * c->num_simulations;
+    return 0;
+}
+
+extern "C" int cumind_search(cumind_tree* t, const cumind_net* n, const float* d_root_hidden, const cumind_search_cfg* c,
+                             const double* d_noise, int32_t* d_out_visits, double* d_out_probs, double* d_out_root_value,
+                             void* stream) {
+    if (check_search("cumind_search", t, n, c, d_noise)) return 1;
+    if (!d_root_hidden || !d_out_visits || !d_out_probs) return fail("cumind_search: NULL device pointer");
+    FusedPlan pl;
+    std::string why;
+    if (plan_fused(t, n, c, pl, why) != 0)
+        return cumind_search_stepwise(t, n, d_root_hidden, c, d_noise, d_out_visits, d_out_probs, d_out_root_value, stream);
+    pl.p.root_hidden = d_root_hidden;
+    pl.p.noise = d_noise;
+    pl.p.out_visits = d_out_visits;
+    pl.p.out_probs = d_out_probs;
+    pl.p.out_root_value = d_out_root_value;
+    CM_CUDA(launch_search_fused(pl.G, pl.R, pl.p, pl.grid, pl.block, pl.smem, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+// introspection for tests / bench: the launch configuration cumind_search would use
+extern "C" int cumind_search_plan(const cumind_tree* t, const cumind_net* n, const cumind_search_cfg* c, int32_t* out /*[6]*/) {
+    if (!t || !n || !c || !out) return fail("cumind_search_plan: NULL argument");
+    FusedPlan pl;
+    std::string why;
+    if (plan_fused(t, n, c, pl, why) != 0) { out[0] = 0; return 0; }
+    out[0] = 1; out[1] = pl.G; out[2] = pl.R; out[3] = pl.grid; out[4] = pl.block; out[5] = (int32_t)pl.smem;
+    return 0;
+}
+
+// ---- fine-grained phases ------------------------------------------------------------------------
+static cumind_search_cfg cfg_for_tree(const cumind_tree* t, const cumind_search_cfg* c) { (void)t; return *c; }
+
+extern "C" int cumind_tree_init_root(cumind_tree* t, const cumind_net* n, const float* d_root_hidden, const cumind_search_cfg* c,
+                                     const double* d_noise, void* stream) {
+    if (check_search("cumind_tree_init_root", t, n, c, d_noise)) return 1;
+    if (!d_root_hidden) return fail("cumind_tree_init_root: d_root_hidden is NULL");
+    CM_CUDA(launch_init_root(step_params(t, n, c), d_root_hidden, d_noise, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+extern "C" int cumind_select(cumind_tree* t, const cumind_search_cfg* c, void* stream) {
+    if (!t || !c) return fail("cumind_select: NULL argument");
+    StepParams p{};
+    p.tv = t->tv;
+    p.c_puct = c->c_puct;
+    CM_CUDA(launch_select(p, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+extern "C" int cumind_expand(cumind_tree* t, const cumind_net* n, const cumind_search_cfg* c, float* d_leaf_value, void* stream) {
+    if (!t || !n || !c || !d_leaf_value) return fail("cumind_expand: NULL argument");
+    if (n->desc.hidden_dim != t->tv.H) return fail("cumind_expand: tree was created for a different hidden_dim");
+    const cumind_search_cfg cc = cfg_for_tree(t, c);
+    CM_CUDA(launch_expand(step_params(t, n, &cc), d_leaf_value, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+extern "C" int cumind_backup(cumind_tree* t, const float* d_leaf_value, void* stream) {
+    if (!t || !d_leaf_value) return fail("cumind_backup: NULL argument");
+    StepParams p{};
+    p.tv = t->tv;
+    CM_CUDA(launch_backup(p, d_leaf_value, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+extern "C" int cumind_finalize(cumind_tree* t, const cumind_search_cfg* c, int32_t* d_out_visits, double* d_out_probs,
+                               double* d_out_root_value, void* stream) {
+    if (!t || !c) return fail("cumind_finalize: NULL argument");
+    StepParams p{};
+    p.tv = t->tv;
+    p.A_cfg = c->action_space_size;
+    CM_CUDA(launch_finalize(p, d_out_visits, d_out_probs, d_out_root_value, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+extern "C" int cumind_dirichlet(double* d_noise, int32_t B, int32_t A, double alpha, uint64_t seed, uint64_t tree_index_base,
+                                void* stream) {
+    if (!d_noise || B <= 0 || A <= 0 || !(alpha > 0.0)) return fail("cumind_dirichlet: bad argument");
+    CM_CUDA(launch_dirichlet(d_noise, B, A, alpha, seed, tree_index_base, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Agent.select_action for a batch, host buffers in / out (agent.py:61-89)
+// ------------------------------------------------------------------------------------------------
+struct WorkOffsets { size_t obs, hidden, noise, visits, probs, actions, total; };
+static WorkOffsets work_offsets(const cumind_net_desc* d, int64_t B, int64_t A_cfg) {
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t osz = d->obs_ndim == 1 ? (size_t)d->obs_shape[0] : (size_t)d->obs_shape[0] * d->obs_shape[1] * d->obs_shape[2];
+    WorkOffsets o;
+    size_t p = 0;
+    o.obs = p;     p = al(p + B * osz * sizeof(float));
+    o.hidden = p;  p = al(p + B * d->hidden_dim * sizeof(float));
+    o.noise = p;   p = al(p + B * d->action_space_size * sizeof(double));
+    o.visits = p;  p = al(p + B * A_cfg * sizeof(int32_t));
+    o.probs = p;   p = al(p + B * A_cfg * sizeof(double));
+    o.actions = p; p = al(p + B * sizeof(int32_t));
+    o.total = p;
+    return o;
+}
+
+extern "C" size_t cumind_select_actions_work_bytes(const cumind_net_desc* desc, int32_t B, int32_t A_cfg) {
+    if (!desc_valid(desc) || B <= 0 || A_cfg <= 0) return 0;
+    return work_offsets(desc, B, A_cfg).total;
+}
+
+extern "C" int cumind_select_actions_host(cumind_tree* t, const cumind_net* n, const float* h_obs, const cumind_search_cfg* c,
+                                          const double* h_noise, int32_t* h_actions, double* h_probs, void* d_work,
+                                          size_t work_bytes, void* stream) {
+    if (!t || !n || !c || !h_obs || !h_actions || !h_probs || !d_work) return fail("cumind_select_actions_host: NULL argument");
+    const int B = t->tv.B, A_cfg = c->action_space_size;
+    const WorkOffsets o = work_offsets(&n->desc, B, A_cfg);
+    if (work_bytes < o.total) return fail("cumind_select_actions_host: work buffer too small");
+    if (c->noise_mode == 1 && !h_noise) return fail("noise_mode 1 needs h_noise");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* w = (unsigned char*)d_work;
+    float* d_obs = (float*)(w + o.obs);
+    float* d_hidden = (float*)(w + o.hidden);
+    double* d_noise = (double*)(w + o.noise);
+    int32_t* d_visits = (int32_t*)(w + o.visits);
+    double* d_probs = (double*)(w + o.probs);
+    int32_t* d_actions = (int32_t*)(w + o.actions);
+    const size_t osz = n->desc.obs_ndim == 1 ? (size_t)n->desc.obs_shape[0]
+                                             : (size_t)n->desc.obs_shape[0] * n->desc.obs_shape[1] * n->desc.obs_shape[2];
+    CM_CUDA(cudaMemcpyAsync(d_obs, h_obs, (size_t)B * osz * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (c->noise_mode == 1)
+        CM_CUDA(cudaMemcpyAsync(d_noise, h_noise, (size_t)B * t->tv.A * sizeof(double), cudaMemcpyHostToDevice, st));
+    int rc = cumind_initial_inference(n, d_obs, B, d_hidden, nullptr, nullptr, c->net_mode, stream);
+    if (rc) return rc;
+    rc = cumind_search(t, n, d_hidden, c, c->noise_mode == 1 ? d_noise : nullptr, d_visits, d_probs, nullptr, stream);
+    if (rc) return rc;
+    CM_CUDA(launch_argmax_first(d_probs, B, A_cfg, d_actions, st));
+    g_launches += 1;
+    CM_CUDA(cudaMemcpyAsync(h_actions, d_actions, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CM_CUDA(cudaMemcpyAsync(h_probs, d_probs, (size_t)B * A_cfg * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CM_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}

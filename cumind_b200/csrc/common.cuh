@@ -1,0 +1,160 @@
+// common.cuh — shared declarations of the CuMind-B200 kernels (sm_100a).
+//
+// Canonical numerics: every value that feeds the bit-exactness gate is produced with
+// explicitly rounded intrinsics (__fmul_rn/__fadd_rn/__dmul_rn/__dadd_rn/__ddiv_rn/__dsqrt_rn),
+// which nvcc never contracts into FMAs, in the operation order of the reference
+// (src/cumind/core/mcts.py:51-65, 91-98, 222) and of the pinned network arithmetic.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cumind_b200.h"
+
+#define CM_HOST_DEVICE __host__ __device__ __forceinline__
+#define CM_DEVICE __device__ __forceinline__
+
+namespace cm {
+
+// ------------------------------------------------------------------------------------------------
+// parameter blob layout (include/cumind_b200.h) and the packed "search" layout kept on device
+// ------------------------------------------------------------------------------------------------
+struct BlobLayout {
+    size_t enc, emb, dyn, rew_k, rew_b, pol_k, pol_b, val_k, val_b, total;
+};
+
+inline bool desc_valid(const cumind_net_desc* d) {
+    if (!d) return false;
+    if (d->hidden_dim <= 0 || d->num_blocks <= 0 || d->action_space_size <= 0) return false;
+    if (d->obs_ndim == 1) return d->obs_shape[0] > 0;
+    if (d->obs_ndim == 3)
+        return d->obs_shape[0] > 0 && d->obs_shape[1] > 0 && d->obs_shape[2] > 0 && d->conv_channels > 0;
+    return false;
+}
+
+inline size_t encoder_count(const cumind_net_desc* d) {
+    size_t H = d->hidden_dim, L = d->num_blocks;
+    if (d->obs_ndim == 1) {
+        size_t D = d->obs_shape[0];
+        return D * H + H + (L - 1) * (H * H + H);
+    }
+    size_t C = d->obs_shape[2], Cc = d->conv_channels;
+    return (9 * C * Cc + Cc) + L * (2 * (9 * Cc * Cc + Cc) + 8 * Cc) + (Cc * H + H);
+}
+
+inline BlobLayout make_blob_layout(const cumind_net_desc* d) {
+    size_t H = d->hidden_dim, L = d->num_blocks, A = d->action_space_size;
+    BlobLayout lo;
+    size_t o = 0;
+    lo.enc = o;   o += encoder_count(d);
+    lo.emb = o;   o += A * H;
+    lo.dyn = o;   o += L * (H * H + H);
+    lo.rew_k = o; o += H;
+    lo.rew_b = o; o += 1;
+    lo.pol_k = o; o += H * A;
+    lo.pol_b = o; o += A;
+    lo.val_k = o; o += H;
+    lo.val_b = o; o += 1;
+    lo.total = o;
+    return lo;
+}
+
+// Packed recurrent-path parameters ("pack"): one 16-byte-aligned fp32 buffer the search kernel
+// bulk-copies into shared memory:
+//   emb [A][H] | L x ( K_l [H][H] | b_l [H] ) | Wh [H][HP] | bh [HP]
+// Head columns: 0..A-1 policy, A value, A+1 reward; HP = round_up(A+2, 4).
+struct PackLayout {
+    int H, L, A, HP;
+    size_t emb, layers, heads_w, heads_b, total;  // float offsets
+    CM_HOST_DEVICE size_t layer_k(int l) const { return layers + (size_t)l * ((size_t)H * H + H); }
+    CM_HOST_DEVICE size_t layer_b(int l) const { return layer_k(l) + (size_t)H * H; }
+};
+
+inline PackLayout make_pack_layout(int H, int L, int A) {
+    PackLayout p;
+    p.H = H; p.L = L; p.A = A;
+    p.HP = (A + 2 + 3) & ~3;
+    size_t o = 0;
+    auto al = [](size_t x) { return (x + 3) & ~(size_t)3; };
+    p.emb = o;     o = al(o + (size_t)A * H);
+    p.layers = o;  o = al(o + (size_t)L * ((size_t)H * H + H));
+    p.heads_w = o; o = al(o + (size_t)H * p.HP);
+    p.heads_b = o; o = al(o + (size_t)p.HP);
+    p.total = o;
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tree storage
+// ------------------------------------------------------------------------------------------------
+// One 16-byte record per node: a node's A children are contiguous, so one 32-byte sector serves
+// two children (all of them when A == 2) and one LDG.128 fetches everything ucb_score needs.
+struct __align__(16) Node {
+    double value_sum;  // Node.value_sum  (float64, mcts.py:29)
+    int32_t visit;     // Node.visit_count
+    float prior;       // Node.prior as the fp32 softmax produced it (root children: see root_prior)
+};
+static_assert(sizeof(Node) == 16, "Node record must be 16 bytes");
+
+struct TreeView {
+    int32_t B, S_max, A, H, N;
+    Node* nodes;          // [B][N]
+    int32_t* child_eidx;  // [B][N]   -1 = not expanded, else expansion index e
+    double* root_prior;   // [B][A]   root children priors after noise mixing (float64)
+    int32_t* exp_node;    // [B][S_max+1]
+    float* hidden;        // [B][S_max+1][H]
+    int32_t* path;        // [B][S_max+2]
+    int32_t* path_len;    // [B]
+    int32_t* leaf;        // [B]
+    int32_t* n_expanded;  // [B]
+    long long* depth_sum; // [B]
+};
+
+struct NetView {
+    cumind_net_desc desc;
+    const float* blob;   // canonical fp32 blob (device)
+    BlobLayout lo;
+    const float* pack;   // packed recurrent-path parameters (device, 16B aligned)
+    PackLayout pk;
+};
+
+// ------------------------------------------------------------------------------------------------
+// pinned scalar numerics (device)
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+CM_DEVICE float fmul(float a, float b) { return __fmul_rn(a, b); }
+CM_DEVICE float fadd(float a, float b) { return __fadd_rn(a, b); }
+CM_DEVICE float frelu(float v) { return v > 0.0f ? v : 0.0f; }
+
+// exp(d), d <= 0, float64, mul/add only — the same operation sequence as cmo_pexp (oracle) so the
+// fp32-rounded result is bit-identical on CPU and GPU.
+CM_DEVICE double pexp(double d) {
+    if (d != d) return d;
+    if (!(d >= -200.0)) return 0.0;
+    if (d > 0.0) d = 0.0;
+    const double LOG2E = 1.4426950408889634;
+    const double LN2_HI = 6.93147180369123816490e-01;
+    const double LN2_LO = 1.90821492927058770002e-10;
+    double kf = rint(__dmul_rn(d, LOG2E));
+    double r = __dsub_rn(__dsub_rn(d, __dmul_rn(kf, LN2_HI)), __dmul_rn(kf, LN2_LO));
+    const double C[14] = {1.0, 1.0, 0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0,
+                          1.0 / 40320.0, 1.0 / 362880.0, 1.0 / 3628800.0, 1.0 / 39916800.0,
+                          1.0 / 479001600.0, 1.0 / 6227020800.0};
+    double p = C[13];
+#pragma unroll
+    for (int i = 12; i >= 0; --i) p = __dadd_rn(__dmul_rn(p, r), C[i]);
+    long long k = (long long)kf;
+    double scale = __longlong_as_double((k + 1023) << 52);
+    return __dmul_rn(p, scale);
+}
+
+// Node.ucb_score (mcts.py:51-65): inf if n == 0 else W/n + ((c*p)*sqrt(N))/(1+n), float64.
+// `sqrtN` is __dsqrt_rn((double)N_parent) (correctly rounded, same as math.sqrt).
+CM_DEVICE double ucb_score(int32_t n, double W, double prior, double sqrtN, double c_puct) {
+    if (n == 0) return __longlong_as_double(0x7FF0000000000000LL);
+    double explo = __ddiv_rn(__dmul_rn(__dmul_rn(c_puct, prior), sqrtN), (double)(1 + n));
+    return __dadd_rn(__ddiv_rn(W, (double)n), explo);
+}
+#endif
+
+}  // namespace cm

@@ -1,0 +1,61 @@
+// kernels.h — host-visible launchers of the CUDA kernels (implemented in the .cu files of this dir).
+#pragma once
+
+#include "common.cuh"
+
+namespace cm {
+
+struct FusedParams {
+    TreeView tv;
+    const float* pack;      // device, PackLayout order
+    PackLayout pk;
+    const float* root_hidden;  // [B][H]
+    const double* noise;       // [B][A] or nullptr
+    int32_t* out_visits;       // [B][A_cfg]
+    double* out_probs;         // [B][A_cfg]
+    double* out_root_value;    // [B] or nullptr
+    int S, A_cfg, A_net;
+    double c_puct, frac, one_minus_frac, alpha;
+    int noise_mode;
+    unsigned long long seed, tree_base;
+    int path_in_smem;
+    // shared-memory carve-up (bytes)
+    unsigned off_sqrt, off_slots, slot_bytes, off_bar;
+    int n_sqrt;
+};
+
+// search_fused.cu
+cudaError_t launch_search_fused(int G, int R, const FusedParams& p, int grid, int block, size_t smem, cudaStream_t st);
+
+// tree_steps.cu — one launch per phase (warp per tree, any H / A)
+struct StepParams {
+    TreeView tv;
+    const float* pack;
+    PackLayout pk;
+    int S, A_cfg, A_net;
+    double c_puct, frac, one_minus_frac, alpha;
+    int noise_mode;
+    unsigned long long seed, tree_base;
+};
+cudaError_t launch_init_root(const StepParams& p, const float* root_hidden, const double* noise, cudaStream_t st);
+cudaError_t launch_select(const StepParams& p, cudaStream_t st);
+cudaError_t launch_expand(const StepParams& p, float* leaf_value, cudaStream_t st);
+cudaError_t launch_backup(const StepParams& p, const float* leaf_value, cudaStream_t st);
+cudaError_t launch_finalize(const StepParams& p, int32_t* out_visits, double* out_probs, double* out_root_value, cudaStream_t st);
+cudaError_t launch_dirichlet(double* noise, int B, int A, double alpha, unsigned long long seed,
+                             unsigned long long tree_base, cudaStream_t st);
+cudaError_t launch_argmax_first(const double* probs, int B, int A, int32_t* actions, cudaStream_t st);
+
+// network_fp32.cu — batched fp32-exact network entry points (warp per row)
+cudaError_t launch_vector_encoder(const NetView& nv, const float* obs, int B, float* hidden, cudaStream_t st);
+cudaError_t launch_recurrent(const NetView& nv, const float* hidden, const int32_t* action, int B, float* next,
+                             float* reward, float* logits, float* value, cudaStream_t st);
+cudaError_t launch_prediction(const NetView& nv, const float* hidden, int B, float* logits, float* value, cudaStream_t st);
+cudaError_t launch_softmax(const float* logits, int B, int A, float* probs, cudaStream_t st);
+
+// conv_fp32.cu — image encoder, fp32-exact (ConvEncoder, network.py:111-147)
+size_t conv_encoder_work_bytes(const cumind_net_desc& d, int chunk);
+cudaError_t launch_conv_encoder(const NetView& nv, const float* obs, int B, float* hidden, float* work, int chunk,
+                                cudaStream_t st);
+
+}  // namespace cm

@@ -1,0 +1,232 @@
+// tree_steps.cu — the search as one launch per phase (warp per tree, any hidden_dim / action count).
+//
+// These are the fine-grained C-ABI entry points (cumind_tree_init_root / _select / _expand /
+// _backup / _finalize / _dirichlet): the tests cross-check the fused kernel against them, ncu
+// attributes time per phase with them, and cumind_search falls back to them when the parameters
+// do not fit the fused kernel's shared-memory staging.  Reference anchors are in search_core.cuh.
+#include "kernels.h"
+#include "search_core.cuh"
+
+namespace cm {
+
+static constexpr int kWarpsPerBlock = 4;
+
+CM_DEVICE int warp_tree_index() { return blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); }
+
+// generic-H layer: lane computes outputs j = lane, lane+32, ... (sequential k, unfused)
+CM_DEVICE void dyn_layer_any(const float* __restrict__ K, const float* __restrict__ b, const float* __restrict__ xin,
+                             float* __restrict__ xout, int H, int lane) {
+    for (int j = lane; j < H; j += 32) {
+        float acc = 0.0f;
+        for (int k = 0; k < H; ++k) acc = fadd(acc, fmul(xin[k], K[(size_t)k * H + j]));
+        xout[j] = fadd(frelu(fadd(acc, b[j])), xin[j]);
+    }
+}
+
+// ---- root: prediction -> softmax -> expand -> noise (mcts.py:126-136) ----------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) init_root_kernel(const StepParams p, const float* __restrict__ root_hidden,
+                                                                       const double* __restrict__ noise) {
+    extern __shared__ __align__(16) float sm[];
+    const int H = p.pk.H, HP = p.pk.HP, A = p.tv.A, A_net = p.A_net;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float* x = sm + (size_t)w * (H + 2 * HP);
+    float* lg = x + H;
+    float* eb = lg + HP;
+    const int t = warp_tree_index();
+    const bool active = t < p.tv.B;
+    const size_t tt = active ? (size_t)t : 0;
+    Node* nodes = p.tv.nodes + tt * p.tv.N;
+    int32_t* eidx = p.tv.child_eidx + tt * p.tv.N;
+    double* rprior = p.tv.root_prior + tt * A;
+    float* hidden = p.tv.hidden + tt * (size_t)(p.tv.S_max + 1) * H;
+    if (active)
+        for (int j = lane; j < H; j += 32) { const float v = root_hidden[tt * H + j]; x[j] = v; hidden[j] = v; }
+    __syncwarp();
+    if (active) heads<32>(p.pack + p.pk.heads_w, p.pack + p.pk.heads_b, x, H, HP, A_net, lg, lane);
+    if (active && p.noise_mode == 2 && lane == 0) dirichlet_row(rprior, A, p.alpha, p.seed, p.tree_base + (unsigned long long)t);
+    __syncwarp();
+    const float ssum = softmax_prepare<32>(lg, eb, A_net, lane, active);
+    if (active) {
+        for (int a = lane; a < A; a += 32) {
+            const float p32 = __fdiv_rn(eb[a], ssum);
+            double pd = (double)p32;
+            if (p.noise_mode == 1) pd = __dadd_rn(__dmul_rn(pd, p.one_minus_frac), __dmul_rn(noise[tt * A + a], p.frac));
+            else if (p.noise_mode == 2) pd = __dadd_rn(__dmul_rn(pd, p.one_minus_frac), __dmul_rn(rprior[a], p.frac));
+            rprior[a] = pd;
+            store_node(nodes + 1 + a, 0.0, 0, p32);
+            eidx[1 + a] = -1;
+        }
+        if (lane == 0) {
+            store_node(nodes, 0.0, 0, 1.0f);
+            eidx[0] = 0;
+            p.tv.exp_node[tt * (p.tv.S_max + 1)] = 0;
+            p.tv.n_expanded[t] = 1;
+            p.tv.depth_sum[t] = 0;
+            p.tv.path_len[t] = 0;
+            p.tv.leaf[t] = 0;
+        }
+    }
+}
+
+// ---- selection (mcts.py:165-171) ----------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) select_kernel(const StepParams p, int n_sqrt) {
+    extern __shared__ __align__(16) double sq_s[];
+    for (int i = threadIdx.x; i < n_sqrt; i += blockDim.x) sq_s[i] = __dsqrt_rn((double)i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int t = warp_tree_index();
+    const bool active = t < p.tv.B;
+    const size_t tt = active ? (size_t)t : 0;
+    const Node* nodes = p.tv.nodes + tt * p.tv.N;
+    const int32_t* eidx = p.tv.child_eidx + tt * p.tv.N;
+    int* path = p.tv.path + tt * (p.tv.S_max + 2);
+    const int root_visits = load_node(nodes).visit;
+    int plen, parent_e, action;
+    const int leaf = select_leaf<32>(nodes, eidx, p.tv.root_prior + tt * p.tv.A, sq_s, p.tv.A, p.c_puct, root_visits, path,
+                                     lane, active, plen, parent_e, action);
+    if (active && lane == 0) {
+        p.tv.path_len[t] = plen;
+        p.tv.leaf[t] = leaf;
+        p.tv.depth_sum[t] += plen;
+    }
+}
+
+// ---- expansion + evaluation (mcts.py:181-196) ---------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) expand_kernel(const StepParams p, float* __restrict__ leaf_value) {
+    extern __shared__ __align__(16) float sm[];
+    const int H = p.pk.H, L = p.pk.L, HP = p.pk.HP, A = p.tv.A, A_net = p.A_net;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float* x0 = sm + (size_t)w * (2 * H + 2 * HP);
+    float* x1 = x0 + H;
+    float* lg = x1 + H;
+    float* eb = lg + HP;
+    const int t = warp_tree_index();
+    const bool active = t < p.tv.B;
+    const size_t tt = active ? (size_t)t : 0;
+    Node* nodes = p.tv.nodes + tt * p.tv.N;
+    int32_t* eidx = p.tv.child_eidx + tt * p.tv.N;
+    float* hidden = p.tv.hidden + tt * (size_t)(p.tv.S_max + 1) * H;
+    const int leaf = p.tv.leaf[tt];
+    const int k = p.tv.n_expanded[tt];
+    const int parent_e = (leaf - 1) / A, action = (leaf - 1) % A;
+    if (active) {
+        const float* h = hidden + (size_t)parent_e * H;
+        const float* emb = p.pack + p.pk.emb + (size_t)action * H;
+        for (int j = lane; j < H; j += 32) x0[j] = fadd(h[j], emb[j]);
+    }
+    __syncwarp();
+    float* cur = x0;
+    float* nxt = x1;
+    for (int l = 0; l < L; ++l) {
+        if (active) dyn_layer_any(p.pack + p.pk.layer_k(l), p.pack + p.pk.layer_b(l), cur, nxt, H, lane);
+        __syncwarp();
+        float* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    if (active) {
+        for (int j = lane; j < H; j += 32) hidden[(size_t)k * H + j] = cur[j];
+        heads<32>(p.pack + p.pk.heads_w, p.pack + p.pk.heads_b, cur, H, HP, A_net + 1, lg, lane);
+    }
+    __syncwarp();
+    const float ssum = softmax_prepare<32>(lg, eb, A_net, lane, active);
+    if (active) {
+        const int cbase = 1 + k * A;
+        for (int a = lane; a < A; a += 32) {
+            store_node(nodes + cbase + a, 0.0, 0, __fdiv_rn(eb[a], ssum));
+            eidx[cbase + a] = -1;
+        }
+        if (lane == 0) {
+            eidx[leaf] = k;
+            p.tv.exp_node[tt * (p.tv.S_max + 1) + k] = leaf;
+            p.tv.n_expanded[t] = k + 1;
+            leaf_value[t] = lg[A_net];
+        }
+    }
+}
+
+// ---- backup (mcts.py:199-203) -------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) backup_kernel(const StepParams p, const float* __restrict__ leaf_value) {
+    const int lane = threadIdx.x & 31;
+    const int t = warp_tree_index();
+    if (t >= p.tv.B) return;
+    backup_path<32>(p.tv.nodes + (size_t)t * p.tv.N, p.tv.path + (size_t)t * (p.tv.S_max + 2), p.tv.path_len[t], leaf_value[t], lane);
+}
+
+// ---- visit counts -> probabilities (mcts.py:143-155) ---------------------------------------------
+__global__ void finalize_kernel(const StepParams p, int32_t* __restrict__ out_visits, double* __restrict__ out_probs,
+                                double* __restrict__ out_root_value) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.tv.B) return;
+    const Node* nodes = p.tv.nodes + (size_t)t * p.tv.N;
+    const int A = p.tv.A;
+    long long total = 0;
+    for (int a = 0; a < A; ++a) total += load_node(nodes + 1 + a).visit;
+    for (int a = 0; a < p.A_cfg; ++a) {
+        const int c = a < A ? load_node(nodes + 1 + a).visit : 0;
+        if (out_visits) out_visits[(size_t)t * p.A_cfg + a] = c;
+        if (out_probs)
+            out_probs[(size_t)t * p.A_cfg + a] = total == 0 ? __ddiv_rn(1.0, (double)p.A_cfg) : __ddiv_rn((double)c, (double)total);
+    }
+    if (out_root_value) {
+        const Node r = load_node(nodes);
+        out_root_value[t] = r.visit == 0 ? 0.0 : __ddiv_rn(r.value_sum, (double)r.visit);
+    }
+}
+
+__global__ void dirichlet_kernel(double* __restrict__ noise, int B, int A, double alpha, unsigned long long seed,
+                                 unsigned long long tree_base) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B) return;
+    dirichlet_row(noise + (size_t)t * A, A, alpha, seed, tree_base + (unsigned long long)t);
+}
+
+// int(np.argmax(action_probs)) (agent.py:86): first maximum
+__global__ void argmax_first_kernel(const double* __restrict__ probs, int B, int A, int32_t* __restrict__ actions) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B) return;
+    int best = 0;
+    double bv = probs[(size_t)t * A];
+    for (int a = 1; a < A; ++a) { const double v = probs[(size_t)t * A + a]; if (v > bv) { bv = v; best = a; } }
+    actions[t] = best;
+}
+
+// ------------------------------------------------------------------------------------------------
+static inline int warp_grid(int B) { return (B + kWarpsPerBlock - 1) / kWarpsPerBlock; }
+
+cudaError_t launch_init_root(const StepParams& p, const float* root_hidden, const double* noise, cudaStream_t st) {
+    const size_t smem = (size_t)kWarpsPerBlock * (p.pk.H + 2 * p.pk.HP) * sizeof(float);
+    init_root_kernel<<<warp_grid(p.tv.B), kWarpsPerBlock * 32, smem, st>>>(p, root_hidden, noise);
+    return cudaGetLastError();
+}
+cudaError_t launch_select(const StepParams& p, cudaStream_t st) {
+    const int n_sqrt = 2 * p.tv.S_max + 2;
+    select_kernel<<<warp_grid(p.tv.B), kWarpsPerBlock * 32, n_sqrt * sizeof(double), st>>>(p, n_sqrt);
+    return cudaGetLastError();
+}
+cudaError_t launch_expand(const StepParams& p, float* leaf_value, cudaStream_t st) {
+    const size_t smem = (size_t)kWarpsPerBlock * (2 * p.pk.H + 2 * p.pk.HP) * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    expand_kernel<<<warp_grid(p.tv.B), kWarpsPerBlock * 32, smem, st>>>(p, leaf_value);
+    return cudaGetLastError();
+}
+cudaError_t launch_backup(const StepParams& p, const float* leaf_value, cudaStream_t st) {
+    backup_kernel<<<warp_grid(p.tv.B), kWarpsPerBlock * 32, 0, st>>>(p, leaf_value);
+    return cudaGetLastError();
+}
+cudaError_t launch_finalize(const StepParams& p, int32_t* out_visits, double* out_probs, double* out_root_value, cudaStream_t st) {
+    finalize_kernel<<<(p.tv.B + 127) / 128, 128, 0, st>>>(p, out_visits, out_probs, out_root_value);
+    return cudaGetLastError();
+}
+cudaError_t launch_dirichlet(double* noise, int B, int A, double alpha, unsigned long long seed, unsigned long long tree_base,
+                             cudaStream_t st) {
+    dirichlet_kernel<<<(B + 127) / 128, 128, 0, st>>>(noise, B, A, alpha, seed, tree_base);
+    return cudaGetLastError();
+}
+cudaError_t launch_argmax_first(const double* probs, int B, int A, int32_t* actions, cudaStream_t st) {
+    argmax_first_kernel<<<(B + 127) / 128, 128, 0, st>>>(probs, B, A, actions);
+    return cudaGetLastError();
+}
+
+}  // namespace cm

@@ -128,7 +128,7 @@ int cumind_prediction(const cumind_net* net, const float* d_hidden, int32_t B,
 int cumind_softmax(const float* d_logits, int32_t B, int32_t A, float* d_probs, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * Tree storage: B independent trees as structure-of-arrays in one caller-owned device slab.
+ * Tree storage: B independent trees as flat arrays in one caller-owned device slab.
  * Replaces the Python `Node` object graph (mcts.py:18-98).  Node slots per tree:
  *   N = 1 + A_tree*(S_max+1); slot 0 is the root; the e-th expansion (e=0 is the root) owns
  *   child slots 1+e*A_tree .. 1+(e+1)*A_tree-1 and hidden-state row e.
@@ -138,14 +138,22 @@ int cumind_tree_create(int32_t B, int32_t S_max, int32_t A_tree, int32_t H,
                        void* d_slab, size_t slab_bytes, cumind_tree** out);
 int cumind_tree_destroy(cumind_tree* tree);
 
-/* Device pointers of the SoA arrays inside the slab (for parity dumps / zero-copy readers). */
+/* One 16-byte record per node; the A children of a node are contiguous, so one 32-byte sector
+ * serves two children and one 128-bit load fetches everything Node.ucb_score reads. */
+typedef struct cumind_node {
+    double  value_sum;  /* Node.value_sum  (float64, mcts.py:29)                          */
+    int32_t visit;      /* Node.visit_count                                               */
+    float   prior;      /* Node.prior as produced by the fp32 softmax (root children: the
+                           float64 value after noise mixing is in root_prior)             */
+} cumind_node;
+
+/* Device pointers of the arrays inside the slab (for parity dumps / zero-copy readers).
+ * Slots that no expansion has created yet are uninitialised. */
 typedef struct cumind_tree_view {
     int32_t B, S_max, A, H, N;
-    int32_t* visit;        /* [B,N]        Node.visit_count                                  */
-    double*  value_sum;    /* [B,N]        Node.value_sum (float64, mcts.py:29)              */
-    float*   prior;        /* [B,N]        Node.prior as produced by the fp32 softmax        */
-    double*  root_prior;   /* [B,A]        root children priors after noise mixing (float64) */
+    cumind_node* nodes;    /* [B,N]        node records                                      */
     int32_t* child_eidx;   /* [B,N]        -1 if not expanded, else expansion index e        */
+    double*  root_prior;   /* [B,A]        root children priors after noise mixing (float64) */
     int32_t* exp_node;     /* [B,S_max+1]  slot of the e-th expanded node                    */
     float*   hidden;       /* [B,S_max+1,H] Node.hidden_state of the e-th expanded node      */
     int32_t* path;         /* [B,S_max+2]  scratch: parents on the current path (step API)   */
@@ -169,6 +177,11 @@ int cumind_search(cumind_tree* tree, const cumind_net* net, const float* d_root_
                   const cumind_search_cfg* cfg, const double* d_noise,
                   int32_t* d_out_visits, double* d_out_probs, double* d_out_root_value,
                   void* stream);
+
+/* The launch configuration cumind_search would use: out = {fused(0/1), lanes per tree G,
+ * outputs per lane R, grid, block, dynamic shared memory bytes}. */
+int cumind_search_plan(const cumind_tree* tree, const cumind_net* net, const cumind_search_cfg* cfg,
+                       int32_t* out6);
 
 /* Same search issued as separate kernels per phase (the fine-grained entry points below);
  * used by the tests to cross-check the fused kernel and by ncu to attribute time per phase. */
