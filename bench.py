@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py — batched MCTS simulations/sec of the CuMind search hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--trees B] [--sims S]
+
+One "step" = one full search pass over one batch of synthetic trees: initial_inference on the
+resident observations, root prediction + Dirichlet mix, S simulations (select -> dynamics ->
+prediction -> expand -> backup), visit-count normalisation.  Workload at every N: BASELINE.json
+configs[1] per GPU (B=4096 CartPole-shaped trees, S=50, fp32-exact network); trees shard by
+environment across ranks with no collective in the data path ("weak" scaling).
+
+`value`    = all trees x simulations of all ranks / device time of the K steps (CUDA events on the
+             launching stream, max over ranks), inputs resident in HBM.
+`e2e`      = the same metric through Agent.select_actions -> cumind_select_actions_host: host (pinned)
+             observations + noise in, host actions + probabilities out, copies inside the timed region.
+`roofline` = HBM roofline of the dominant kernel (the fused search kernel): algorithmic bytes per
+             simulation x simulations per launch / its CUDA-event duration, against
+             MEASURED_PEAKS.json hbm_gbs.
+`cpu_baseline` = the oracle's Python port of the reference search (one tree per call, NumPy/BLAS
+             network), one process per host core, bounded sample, timed in this run on rank 0.
+--impl reference times only that CPU path (rank 0; other ranks exit 0).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+# ---- workload (BASELINE.json configs[1]) -------------------------------
+OBS_SHAPE, A, H, L, CC = (4,), 2, 64, 2, 32
+C_PUCT, ALPHA, FRAC = 1.25, 0.3, 0.25
+PARAM_SEED, OBS_SEED, NOISE_SEED = 42, 0, 1
+FALLBACK_HBM_GBS = 6650.0
+
+
+def make_inputs(B: int, rank: int):
+    from oracle import network_np as nn  # parameter generator only (shared with the parity tests)
+
+    params = nn.random_params(OBS_SHAPE, A, H, L, CC, PARAM_SEED)
+    blob = nn.flatten_params(params, OBS_SHAPE)
+    obs = np.random.default_rng(OBS_SEED + 1000 * rank).standard_normal((B,) + OBS_SHAPE).astype(np.float32)
+    noise = np.random.default_rng(NOISE_SEED + 1000 * rank).dirichlet([ALPHA] * A, size=B)
+    return params, blob, obs, noise
+
+
+def algorithmic_bytes_per_sim(dbar: float) -> float:
+    """select d*(16A+8) + expand 8H+16A+4 + backup 24*d."""
+    return dbar * (16 * A + 8) + 8 * H + 16 * A + 4 + 24 * dbar
+
+
+# ---- CPU baseline: the oracle's Python port, one process per core -----------------------------------
+_W = {}
+
+
+def _cpu_init(S: int, max_trees: int):
+    os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = "1"
+    from oracle import mcts_port as port
+    from oracle import network_np as nn
+
+    params = nn.random_params(OBS_SHAPE, A, H, L, CC, PARAM_SEED)
+    net = nn.NumpyCuMindNetwork(params, OBS_SHAPE, blas=True)
+    rng = np.random.default_rng(os.getpid())
+    obs = rng.standard_normal((max_trees,) + OBS_SHAPE).astype(np.float32)
+    noise = rng.dirichlet([ALPHA] * A, size=max_trees)
+    hidden = net.representation_network(obs)
+    port.run_search(net, hidden[0], 5, A, C_PUCT, FRAC, noise[0])  # warm caches
+    _W.update(port=port, net=net, hidden=hidden, noise=noise, S=S, next=0, max=max_trees)
+
+
+def _cpu_work(seconds: float):
+    w = _W
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < seconds:
+        i = w["next"] % w["max"]
+        w["port"].run_search(w["net"], w["hidden"][i], w["S"], A, C_PUCT, FRAC, w["noise"][i])
+        w["next"] += 1
+        n += 1
+    return n, time.perf_counter() - t0
+
+
+class CpuPool:
+    """One worker process per host core, each running single-tree searches (the reference's shape of work)."""
+
+    def __init__(self, S: int):
+        self.S = S
+        self.cores = len(os.sched_getaffinity(0))
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_init, initargs=(S, 256))
+        self.pool.map(_cpu_work, [0.05] * self.cores)
+
+    def run(self, seconds: float):
+        res = self.pool.map(_cpu_work, [seconds] * self.cores, chunksize=1)
+        trees = sum(r[0] for r in res)
+        wall = max(r[1] for r in res)
+        return trees, wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_baseline(S: int, seconds: float):
+    pool = CpuPool(S)
+    try:
+        trees, wall = pool.run(seconds)
+    finally:
+        pool.close()
+    return {"value": trees * S / wall, "unit": "simulations/s", "cores": pool.cores, "kind": "port",
+            "sample": f"{trees} single-tree searches (S={S}, A={A}, H={H}) over {pool.cores} processes, {wall:.1f} s wall; " + CPU_NOTE}
+
+
+CPU_NOTE = ("oracle/mcts_port.py (Python port of mcts.py) + NumPy/BLAS network, one tree per call, one process per core; "
+            "no eager-JAX dispatch or log formatting, so faster than the real reference")
+
+
+def c_oracle_rate(S: int, trees: int = 512):
+    from oracle import liboracle as lo
+
+    _, blob, obs, noise = make_inputs(trees, 0)
+    desc = lo.make_desc(OBS_SHAPE, A, H, L)
+    h, _, _ = lo.initial_inference(desc, blob, obs)
+    t0 = time.perf_counter()
+    lo.search(desc, blob, h, S, A, C_PUCT, FRAC, noise)
+    return trees * S / (time.perf_counter() - t0)
+
+
+# ---- clocks ------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index: int, period: float = 0.01):
+        super().__init__(daemon=True)
+        self.period, self.samples, self.stop_flag, self.live = period, [], False, False
+        self.max_mhz, self.h, self.nv = None, None, None
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                if self.live:
+                    self.samples.append((mhz, int(reasons)))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+                 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+        mask = 0
+        for _, r in self.samples:
+            mask |= r
+        reasons = [n for b, n in names.items() if mask & b and n != "gpu_idle"]
+        return {"sm_mhz": statistics.median(m for m, _ in self.samples), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ---- the arms ----------------------------------------------------------------------------------------
+def run_reference(args, rank: int, world: int):
+    """The reference's CPU implementation of the path (Python port; /root/reference cannot travel)."""
+    if rank != 0:
+        return
+    S, K, W = args.sims, args.steps, args.warmup
+    box = min(4.0, max(0.3, 150.0 / (K + W)))  # whole run stays within a few minutes
+    t0 = time.perf_counter()
+    pool = CpuPool(S)
+    try:
+        for _ in range(W):
+            pool.run(box)
+        trees_total, wall_total = 0, 0.0
+        for _ in range(K):
+            trees, wall = pool.run(box)
+            trees_total += trees
+            wall_total += wall
+    finally:
+        pool.close()
+    value = trees_total * S / wall_total
+    base = {"value": value, "unit": "simulations/s", "cores": pool.cores, "kind": "port",
+            "sample": f"{K} steps x {box:.2f} s time box per core: {trees_total} single-tree searches (S={S}, A={A}, H={H}); " + CPU_NOTE}
+    line = {"impl": "reference", "metric": "batched MCTS simulations/sec", "value": value, "unit": "simulations/s", "n_gpus": args.gpus,
+            "steps": K, "warmup": W, "ms_per_step": 1e3 * wall_total / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": workload_config(args, per_gpu=args.trees), "cpu_baseline": base,
+            "e2e": {"value": value, "unit": "simulations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, per_gpu: int):
+    return {"workload": f"BASELINE configs[1]: CartPole-shaped synthetic self-play, B={per_gpu} trees per GPU, S={args.sims} simulations, "
+                        f"obs {OBS_SHAPE}, A={A}, hidden_dim={H}, num_blocks={L}, fp32-exact network, injected Dirichlet({ALPHA}) noise, c_puct={C_PUCT}",
+            "trees_per_gpu": per_gpu, "num_simulations": args.sims, "parallelism": f"trees sharded by environment x{args.gpus}, no collective",
+            "l2": "256 MiB device buffer written between timed steps (L2 flush); per-step CUDA events"}
+
+
+def run_native(args, rank: int, world: int, local_rank: int):
+    import torch
+
+    from cumind_b200 import Config, _native
+    from cumind_b200 import params as P
+    from cumind_b200.agent import Agent
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B, S, K, W = args.trees, args.sims, args.steps, args.warmup
+    _, blob, obs, noise = make_inputs(B, rank)
+    cfg = Config(hidden_dim=H, num_blocks=L, num_simulations=S, action_space_size=A, observation_shape=OBS_SHAPE, c_puct=C_PUCT,
+                 dirichlet_alpha=ALPHA, exploration_fraction=FRAC)
+    agent = Agent(cfg)
+    agent.network.load_state(P.unflatten(blob, OBS_SHAPE, A, H, L, CC))
+    agent.update_target_network()
+    agent.mcts.lanes_per_tree = args.lanes
+    net, mcts = agent.network, agent.mcts
+    dev = torch.device("cuda", local_rank)
+    d_obs = torch.as_tensor(obs).to(dev)
+    d_noise = torch.as_tensor(noise).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_dev():
+        hidden = net.representation_network(d_obs)
+        return _search_device(mcts, hidden, d_noise, rank * B)
+
+    for _ in range(max(W, 3)):
+        step_dev()
+        flush.fill_(1)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    k_start = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = _native.launch_count()
+    sampler.live = True
+    wall0 = time.perf_counter()
+    for i in range(K):
+        starts[i].record()
+        hidden = net.representation_network(d_obs)
+        k_start[i].record()
+        _search_device(mcts, hidden, d_noise, rank * B)
+        ends[i].record()
+        flush.fill_(i & 0xFF)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    sampler.live = False
+    launches = _native.launch_count() - launches0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    kern_ms = [s.elapsed_time(e) for s, e in zip(k_start, ends)]
+    total_ms = sum(step_ms)
+    dump = mcts.dump_trees()
+    dbar = float(dump["depth_sum"].mean()) / S
+    visits_ok = bool(np.all(dump["visit"][:, 0] == 2 * S))
+
+    # ---- end to end through the public API: host buffers in, host results out -------------------
+    for _ in range(3):
+        agent.select_actions(obs, training=False, noise=noise)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0 = time.perf_counter()
+    for _ in range(K):
+        actions, probs = agent.select_actions(obs, training=False, noise=noise)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - e0
+    sampler.stop_flag = True
+
+    t = torch.tensor([total_ms, e2e_s * 1e3, statistics.mean(kern_ms)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, kern_ms_mean = (float(x) for x in t.cpu())
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    sims_per_step = world * B * S
+    value = sims_per_step * K / (total_ms * 1e-3)
+    e2e_value = sims_per_step * K / (e2e_ms * 1e-3)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+    bytes_per_launch = algorithmic_bytes_per_sim(dbar) * B * S
+    achieved = bytes_per_launch / (kern_ms_mean * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("search_fused_dram_bytes_per_launch")
+    line = {
+        "metric": "batched MCTS simulations/sec", "value": value, "unit": "simulations/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": workload_config(args, per_gpu=B),
+        "e2e": {"value": e2e_value, "unit": "simulations/s", "h2d_bytes_per_step": int(obs.nbytes + noise.nbytes),
+                "d2h_bytes_per_step": int(actions.nbytes + probs.nbytes), "ms_per_step": e2e_ms / K},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "kernel": "search_fused_kernel", "kernel_ms": kern_ms_mean, "algorithmic_bytes_per_sim": algorithmic_bytes_per_sim(dbar),
+                     "mean_path_length": dbar, "peak_source": peak_src},
+        "clocks": sampler.summary(),
+        "plan": mcts.plan(B), "wall_s": wall, "root_visits_ok": visits_ok,
+    }
+    if not args.no_cpu and world >= 1:
+        line["cpu_baseline"] = cpu_baseline(S, args.cpu_seconds)
+        line["cpu_baseline_c"] = {"value": c_oracle_rate(S), "unit": "simulations/s", "cores": 1, "kind": "port",
+                                  "sample": "oracle/cumind_oracle.c, 512 trees, one thread (pinned fp32 order)"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def _search_device(mcts, hidden, d_noise, tree_index_base):
+    """cumind_search with every buffer already on the device (no host copies)."""
+    import ctypes as C
+
+    import torch
+
+    from cumind_b200 import _native
+    from cumind_b200.network import _ptr, _stream_ptr
+
+    net = mcts.network
+    B = hidden.shape[0]
+    A_cfg = int(mcts.config.action_space_size)
+    tree = mcts._tree(B, int(mcts.config.num_simulations), min(A_cfg, net.action_space_size))
+    cfg = mcts._cfg(1, 0, tree_index_base)
+    if not hasattr(mcts, "_bench_out") or mcts._bench_out[0].shape[0] != B:
+        mcts._bench_out = (torch.empty((B, A_cfg), dtype=torch.int32, device=net.device),
+                           torch.empty((B, A_cfg), dtype=torch.float64, device=net.device))
+    visits, probs = mcts._bench_out
+    _native.check(mcts._lib.cumind_search(tree.handle, net._handle, _ptr(hidden), C.byref(cfg), _ptr(d_noise), _ptr(visits), _ptr(probs),
+                                          None, _stream_ptr()))
+    return probs, visits
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--trees", type=int, default=4096, help="trees per GPU")
+    ap.add_argument("--sims", type=int, default=50)
+    ap.add_argument("--lanes", type=int, default=0, help="lanes per tree (0 = auto)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_native(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

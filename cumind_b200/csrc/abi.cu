@@ -328,25 +328,14 @@ static StepParams step_params(const cumind_tree* t, const cumind_net* n, const c
     return p;
 }
 
-// choose (G, R): R = H / G outputs per lane; valid pairs are H == G*R with R in {2,4,8,16}, or
-// H <= G with R == 1.
-static bool pick_lanes(int H, int want_G, int& G, int& R) {
-    const int cand[4] = {4, 8, 16, 32};
-    int best = -1, best_d = 1 << 30;
-    for (int i = 0; i < 4; ++i) {
-        const int g = cand[i];
-        bool ok = false;
-        if (H % g == 0) { const int r = H / g; ok = (r == 2 || r == 4 || r == 8 || r == 16); }
-        if (!ok && H <= g && (i == 0 || H > cand[i - 1])) ok = true;  // smallest G >= H, R = 1
-        if (!ok) continue;
-        int d = g > want_G ? g / want_G : want_G / g;
-        if (d < best_d) { best_d = d; best = g; }
-    }
-    if (best < 0) return false;
-    G = best;
-    R = H <= best ? 1 : H / best;
-    if (H == best) R = 1;
-    return true;
+// R = neurons per lane of the warp-cooperative network tile: H <= 32 -> 1, else the smallest of
+// {2,4,8} with 32*R >= H and H % R == 0 (vector alignment of the weight rows).
+static bool pick_R(int H, int& R) {
+    if (H <= 32) { R = 1; return true; }
+    const int cand[3] = {2, 4, 8};
+    for (int i = 0; i < 3; ++i)
+        if (32 * cand[i] >= H && H % cand[i] == 0 && H % 4 == 0) { R = cand[i]; return true; }
+    return false;
 }
 
 struct FusedPlan { int G, R, grid, block; size_t smem; FusedParams p; };
@@ -354,43 +343,45 @@ struct FusedPlan { int G, R, grid, block; size_t smem; FusedParams p; };
 static int plan_fused(const cumind_tree* t, const cumind_net* n, const cumind_search_cfg* c, FusedPlan& pl, std::string& why) {
     const int H = n->desc.hidden_dim, B = t->tv.B;
     const int sm = n->sm_count;
+    if (!pick_R(H, pl.R)) { why = "hidden_dim has no lane mapping"; return 1; }
+    if (t->tv.A > 65535 || t->tv.S_max > 65533) { why = "tree too large for the packed select payload"; return 1; }
     int want = c->lanes_per_tree;
     if (want <= 0) {
+        // lanes per tree so that the batch fills ~8 warps per SM (latency hiding), at least 4 lanes
         const int tps = (B + sm - 1) / sm;
         want = 256 / (tps > 0 ? tps : 1);
-        want = want < 4 ? 4 : (want > 32 ? 32 : want);
-        int p2 = 4; while (p2 * 2 <= want) p2 *= 2; want = p2;
     }
-    if (!pick_lanes(H, want, pl.G, pl.R)) { why = "hidden_dim has no lane mapping"; return 1; }
-    const int G = pl.G;
+    int G = 4;
+    while (G * 2 <= want && G < 32) G *= 2;
+    pl.G = G;
+    const int TW = 32 / G;
     const PackLayout& pk = n->pk;
     const size_t pack_bytes = pk.total * sizeof(float);
     const int n_sqrt = 2 * t->tv.S_max + 2;
     const size_t off_sqrt = (pack_bytes + 15) & ~(size_t)15;
     const size_t off_slots = (off_sqrt + (size_t)n_sqrt * sizeof(double) + 15) & ~(size_t)15;
-    const size_t slot_base = ((size_t)(2 * (H + 4) + 2 * pk.HP) * sizeof(float) + 15) & ~(size_t)15;
-    const size_t path_bytes = ((size_t)(t->tv.S_max + 2) * sizeof(int) + 15) & ~(size_t)15;
+    const size_t warp_base = ((size_t)(2 * H * TW + 2 * TW * pk.HP) * sizeof(float) + 15) & ~(size_t)15;
+    const size_t path_bytes = ((size_t)TW * (t->tv.S_max + 2) * sizeof(int) + 15) & ~(size_t)15;
     const size_t kMax = 227 * 1024;
-    // trees per block: one CTA per SM when the whole batch fits, else 512 threads per CTA
-    int tps = (B + sm - 1) / sm;
-    int tpb = tps * G <= 512 ? tps : 512 / G;
-    const int gran = 32 / G;  // trees per warp
-    tpb = ((tpb + gran - 1) / gran) * gran;
-    if (tpb * G > 512) tpb = 512 / G;
+    // warps per block: one CTA per SM when the whole batch fits in <= 16 warps, else 16 warps per CTA
+    const int warps_total = (B + TW - 1) / TW;
+    int wps = (warps_total + sm - 1) / sm;
+    int nw = wps <= 16 ? wps : 16;
+    if (nw < 1) nw = 1;
     int path_in_smem = 1;
-    size_t slot = slot_base + path_bytes;
-    auto total = [&](int tpb_, size_t slot_) { return off_slots + (size_t)tpb_ * slot_ + 16; };
-    if (total(tpb, slot) > kMax) { path_in_smem = 0; slot = slot_base; }
-    while (tpb > gran && total(tpb, slot) > kMax) tpb -= gran;
-    if (total(tpb, slot) > kMax) { why = "recurrent-path parameters do not fit in shared memory"; return 1; }
-    pl.block = tpb * G;
-    pl.smem = total(tpb, slot);
-    int blocks = (B + tpb - 1) / tpb;
+    size_t slot = warp_base + path_bytes;
+    auto total = [&](int nw_, size_t slot_) { return off_slots + (size_t)nw_ * slot_ + 16; };
+    if (total(nw, slot) > kMax) { path_in_smem = 0; slot = warp_base; }
+    while (nw > 1 && total(nw, slot) > kMax) nw -= 1;
+    if (total(nw, slot) > kMax) { why = "recurrent-path parameters do not fit in shared memory"; return 1; }
+    pl.block = nw * 32;
+    pl.smem = total(nw, slot);
+    const int blocks = (warps_total + nw - 1) / nw;
     int per_sm = (int)(kMax / pl.smem);
     if (per_sm < 1) per_sm = 1;
     const int by_threads = 2048 / pl.block;
     if (per_sm > by_threads) per_sm = by_threads < 1 ? 1 : by_threads;
-    if (per_sm > 1 && pl.block > 256) per_sm = 1;  // __launch_bounds__(512,1) register budget
+    if (per_sm * pl.block > 512) per_sm = 512 / pl.block > 0 ? 512 / pl.block : 1;  // register budget of __launch_bounds__(512,1)
     const int cap = sm * per_sm;
     pl.grid = blocks < cap ? blocks : cap;
     FusedParams& p = pl.p;
@@ -411,8 +402,7 @@ static int plan_fused(const cumind_tree* t, const cumind_net* n, const cumind_se
     p.off_sqrt = (unsigned)off_sqrt;
     p.off_slots = (unsigned)off_slots;
     p.slot_bytes = (unsigned)slot;
-    p.off_bar = (unsigned)(off_slots + (size_t)tpb * slot);
-    p.off_bar = (p.off_bar + 7u) & ~7u;
+    p.off_bar = (unsigned)((off_slots + (size_t)nw * slot + 7) & ~(size_t)7);
     p.n_sqrt = n_sqrt;
     return 0;
 }

@@ -1,9 +1,11 @@
 // common.cuh — shared declarations of the CuMind-B200 kernels (sm_100a).
 //
 // Canonical numerics: every value that feeds the bit-exactness gate is produced with
-// explicitly rounded intrinsics (__fmul_rn/__fadd_rn/__dmul_rn/__dadd_rn/__ddiv_rn/__dsqrt_rn),
-// which nvcc never contracts into FMAs, in the operation order of the reference
-// (src/cumind/core/mcts.py:51-65, 91-98, 222) and of the pinned network arithmetic.
+// explicitly rounded intrinsics (__fmaf_rn / fma.rn.f32x2 for the dot-product chains,
+// __fmul_rn/__fadd_rn/__dmul_rn/__dadd_rn/__ddiv_rn/__dsqrt_rn elsewhere), which nvcc never
+// re-associates or contracts, in the operation order of the reference
+// (src/cumind/core/mcts.py:51-65, 91-98, 222) and of the pinned network arithmetic
+// (dot product = sequential-k chain of IEEE fused multiply-adds, then + bias).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -124,6 +126,18 @@ struct NetView {
 #ifdef __CUDACC__
 CM_DEVICE float fmul(float a, float b) { return __fmul_rn(a, b); }
 CM_DEVICE float fadd(float a, float b) { return __fadd_rn(a, b); }
+CM_DEVICE float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+// Two independent IEEE fmas in one issue slot (SASS FFMA2): acc.{x,y} = fma(x, w.{x,y}, acc.{x,y}).
+CM_DEVICE float2 ffma2(float x, float2 w, float2 acc) {
+    unsigned long long xx, ww, aa, dd;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ww) : "f"(w.x), "f"(w.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(acc.x), "f"(acc.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(dd) : "l"(xx), "l"(ww), "l"(aa));
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(dd));
+    return r;
+}
 CM_DEVICE float frelu(float v) { return v > 0.0f ? v : 0.0f; }
 
 // exp(d), d <= 0, float64, mul/add only — the same operation sequence as cmo_pexp (oracle) so the
@@ -150,10 +164,15 @@ CM_DEVICE double pexp(double d) {
 
 // Node.ucb_score (mcts.py:51-65): inf if n == 0 else W/n + ((c*p)*sqrt(N))/(1+n), float64.
 // `sqrtN` is __dsqrt_rn((double)N_parent) (correctly rounded, same as math.sqrt).
+// The compiler if-converts the n == 0 case, so the divisions always execute: feed them 1/1 then
+// (0/0 would take the slow special-case path of the IEEE division routine on every unvisited child).
 CM_DEVICE double ucb_score(int32_t n, double W, double prior, double sqrtN, double c_puct) {
-    if (n == 0) return __longlong_as_double(0x7FF0000000000000LL);
-    double explo = __ddiv_rn(__dmul_rn(__dmul_rn(c_puct, prior), sqrtN), (double)(1 + n));
-    return __dadd_rn(__ddiv_rn(W, (double)n), explo);
+    const bool unvisited = n == 0;
+    const double nn = unvisited ? 1.0 : (double)n;
+    const double ww = unvisited ? 1.0 : W;
+    const double explo = __ddiv_rn(__dmul_rn(__dmul_rn(c_puct, prior), sqrtN), (double)(1 + n));
+    const double s = __dadd_rn(__ddiv_rn(ww, nn), explo);
+    return unvisited ? __longlong_as_double(0x7FF0000000000000LL) : s;
 }
 #endif
 

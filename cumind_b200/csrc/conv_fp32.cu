@@ -3,7 +3,7 @@
 //   ConvEncoder.__call__   network.py:131-147   relu(conv3x3 s2) -> L x ResidualBlock -> mean(H,W) -> Linear
 //   ResidualBlock.__call__ network.py:29-45     conv -> BN -> relu -> conv -> BN -> (+x) -> relu
 // NHWC, channels = obs_shape[-1] (network.py:127).  Pinned arithmetic (oracle/cumind_oracle.c):
-// taps in (ky,kx,ci) order, taps in the zero padding skipped, unfused fp32 multiply/add, then
+// taps in (ky,kx,ci) order, taps in the zero padding skipped, fp32 fused multiply-add chain, then
 // + bias, then the BatchNorm / residual / ReLU epilogue element-wise.  Runs once per search.
 //
 // Tiling: one CTA = 8x8 output pixels of one image, 256 threads = 64 pixels x 4 channel groups of
@@ -72,17 +72,17 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const ConvArgs a) {
                         const float v = tp[(size_t)ci * TIN * TW];
                         const float4 w0 = __ldg(reinterpret_cast<const float4*>(kp + (size_t)ci * a.Cout));
                         const float4 w1 = __ldg(reinterpret_cast<const float4*>(kp + (size_t)ci * a.Cout + 4));
-                        acc[0] = fadd(acc[0], fmul(v, w0.x)); acc[1] = fadd(acc[1], fmul(v, w0.y));
-                        acc[2] = fadd(acc[2], fmul(v, w0.z)); acc[3] = fadd(acc[3], fmul(v, w0.w));
-                        acc[4] = fadd(acc[4], fmul(v, w1.x)); acc[5] = fadd(acc[5], fmul(v, w1.y));
-                        acc[6] = fadd(acc[6], fmul(v, w1.z)); acc[7] = fadd(acc[7], fmul(v, w1.w));
+                        acc[0] = ffma(v, w0.x, acc[0]); acc[1] = ffma(v, w0.y, acc[1]);
+                        acc[2] = ffma(v, w0.z, acc[2]); acc[3] = ffma(v, w0.w, acc[3]);
+                        acc[4] = ffma(v, w1.x, acc[4]); acc[5] = ffma(v, w1.y, acc[5]);
+                        acc[6] = ffma(v, w1.z, acc[6]); acc[7] = ffma(v, w1.w, acc[7]);
                     }
                 } else {
                     for (int ci = 0; ci < a.Cin; ++ci) {
                         const float v = tp[(size_t)ci * TIN * TW];
 #pragma unroll
                         for (int c = 0; c < 8; ++c)
-                            if (co0 + c < a.Cout) acc[c] = fadd(acc[c], fmul(v, __ldg(kp + (size_t)ci * a.Cout + c)));
+                            if (co0 + c < a.Cout) acc[c] = ffma(v, __ldg(kp + (size_t)ci * a.Cout + c), acc[c]);
                     }
                 }
             }
@@ -120,7 +120,7 @@ __global__ void pool_dense_kernel(const float* __restrict__ x, int npix, int Cc,
     __syncthreads();
     for (int j = threadIdx.x; j < H; j += blockDim.x) {
         float acc = 0.0f;
-        for (int k = 0; k < Cc; ++k) acc = fadd(acc, fmul(pooled[k], K[(size_t)k * H + j]));
+        for (int k = 0; k < Cc; ++k) acc = ffma(pooled[k], K[(size_t)k * H + j], acc);
         hidden[(size_t)img * H + j] = fadd(acc, b[j]);
     }
 }

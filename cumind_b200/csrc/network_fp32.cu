@@ -5,7 +5,7 @@
 //                            (DynamicsNetwork.__call__ 217-236 + PredictionNetwork.__call__ 254-266)
 //   prediction_kernel     <- PredictionNetwork.__call__  network.py:254-266
 //   softmax_kernel        <- jax.nn.softmax              mcts.py:128,191
-// Arithmetic: sequential-k unfused fp32 dot products (see common.cuh); bit-identical to oracle/.
+// Arithmetic: sequential-k fp32 FMA-chain dot products (see common.cuh); bit-identical to oracle/.
 #include "kernels.h"
 #include "search_core.cuh"
 
@@ -17,7 +17,7 @@ CM_DEVICE void linear_any(const float* __restrict__ K, const float* __restrict__
                           int out, float* __restrict__ y, bool relu, int lane) {
     for (int j = lane; j < out; j += 32) {
         float acc = 0.0f;
-        for (int k = 0; k < in; ++k) acc = fadd(acc, fmul(x[k], K[(size_t)k * out + j]));
+        for (int k = 0; k < in; ++k) acc = ffma(x[k], K[(size_t)k * out + j], acc);
         const float v = fadd(acc, b[j]);
         y[j] = relu ? frelu(v) : v;
     }
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kWarps * 32) recurrent_kernel(const float* __r
                 const float* b = pack + pk.layer_b(l);
                 for (int j = lane; j < H; j += 32) {
                     float acc = 0.0f;
-                    for (int k = 0; k < H; ++k) acc = fadd(acc, fmul(cur[k], K[(size_t)k * H + j]));
+                    for (int k = 0; k < H; ++k) acc = ffma(cur[k], K[(size_t)k * H + j], acc);
                     nxt[j] = fadd(frelu(fadd(acc, b[j])), cur[j]);
                 }
             }

@@ -54,9 +54,14 @@ CM_DEVICE int select_leaf(const Node* __restrict__ nodes, const int32_t* __restr
                           int& plen_out, int& parent_e_out, int& action_out) {
     int node = 0, e = 0, n_parent = root_visits, plen = 0, action = 0, parent_e = 0;
     bool walking = active;
+    // lanes g >= A hold no child: only the first `span` lanes of the group take part in the butterfly
+    int span = 1;
+    while (span < A && span < G) span <<= 1;
     while (__any_sync(0xffffffffu, walking)) {
         double best_s = -dinf();
-        int best_a = 0x7fffffff, best_n = 0, best_e = -1;
+        // payload: action in the high half, expansion index + 1 in the low half (both < 65536)
+        unsigned best_ae = 0xffffffffu;
+        int best_n = 0;
         if (walking) {
             const int base = 1 + e * A;
             const double sq = sqrt_tab[n_parent];
@@ -67,25 +72,32 @@ CM_DEVICE int select_leaf(const Node* __restrict__ nodes, const int32_t* __restr
                 const double p = (node == 0) ? root_prior[a] : (double)nd.prior;
                 double s = ucb_score(nd.visit, nd.value_sum, p, sq, c_puct);
                 if (s != s) s = (a == 0) ? dinf() : -dinf();
-                if (best_a == 0x7fffffff || s > best_s) { best_s = s; best_a = a; best_n = nd.visit; best_e = ce; }
+                if (best_ae == 0xffffffffu || s > best_s) {
+                    best_s = s; best_ae = ((unsigned)a << 16) | (unsigned)(ce + 1); best_n = nd.visit;
+                }
             }
         }
 #pragma unroll
         for (int off = G / 2; off > 0; off >>= 1) {
-            const double os = __shfl_xor_sync(0xffffffffu, best_s, off);
-            const int oa = __shfl_xor_sync(0xffffffffu, best_a, off);
-            const int on = __shfl_xor_sync(0xffffffffu, best_n, off);
-            const int oe = __shfl_xor_sync(0xffffffffu, best_e, off);
-            if (os > best_s || (os == best_s && oa < best_a)) { best_s = os; best_a = oa; best_n = on; best_e = oe; }
+            if (off < span) {
+                const double os = __shfl_xor_sync(0xffffffffu, best_s, off);
+                const unsigned oae = __shfl_xor_sync(0xffffffffu, best_ae, off);
+                const int on = __shfl_xor_sync(0xffffffffu, best_n, off);
+                if (os > best_s || (os == best_s && oae < best_ae)) { best_s = os; best_ae = oae; best_n = on; }
+            }
+        }
+        if (span < G) {  // lanes beyond the butterfly take the result from the group's lane 0
+            best_ae = __shfl_sync(0xffffffffu, best_ae, 0, G);
+            best_n = __shfl_sync(0xffffffffu, best_n, 0, G);
         }
         if (walking) {
             if (g == 0) path[plen] = node;
             ++plen;
             parent_e = e;
-            action = best_a;
-            node = 1 + e * A + best_a;
+            action = (int)(best_ae >> 16);
+            node = 1 + e * A + action;
             n_parent = best_n;
-            e = best_e;
+            e = (int)(best_ae & 0xffffu) - 1;
             walking = e >= 0;
         }
     }
@@ -112,8 +124,9 @@ CM_DEVICE void backup_path(Node* __restrict__ nodes, const int* __restrict__ pat
 
 // ------------------------------------------------------------------------------------------------
 // Network, fp32-exact mode.  Lane g of the group owns output chunks c = g + G*i (i < R/V) of V
-// consecutive neurons; each dot product is sequential in k with unfused multiply and add, exactly
-// as oracle/cumind_oracle.c::cmo_linear.  x lives in shared memory (one row per tree).
+// consecutive neurons; each dot product is a sequential-k chain of IEEE fused multiply-adds,
+// exactly as oracle/cumind_oracle.c::cmo_linear (issued two per instruction as FFMA2 where a lane
+// owns an even number of outputs).  x lives in shared memory (one row per tree).
 // ------------------------------------------------------------------------------------------------
 template <int R> struct VecW { static constexpr int V = R >= 4 ? 4 : R; };
 
@@ -125,24 +138,34 @@ template <> CM_DEVICE void load_vec<2>(const float* p, float (&w)[2]) {
 template <> CM_DEVICE void load_vec<4>(const float* p, float (&w)[4]) {
     float4 t = *reinterpret_cast<const float4*>(p); w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
 }
+template <> CM_DEVICE void load_vec<8>(const float* p, float (&w)[8]) {
+    float4 t = *reinterpret_cast<const float4*>(p), u = *reinterpret_cast<const float4*>(p + 4);
+    w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w; w[4] = u.x; w[5] = u.y; w[6] = u.z; w[7] = u.w;
+}
 template <int V> CM_DEVICE void store_vec(float* p, const float (&w)[V]);
+template <> CM_DEVICE void store_vec<8>(float* p, const float (&w)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(w[4], w[5], w[6], w[7]);
+}
 template <> CM_DEVICE void store_vec<1>(float* p, const float (&w)[1]) { p[0] = w[0]; }
 template <> CM_DEVICE void store_vec<2>(float* p, const float (&w)[2]) { *reinterpret_cast<float2*>(p) = make_float2(w[0], w[1]); }
 template <> CM_DEVICE void store_vec<4>(float* p, const float (&w)[4]) { *reinterpret_cast<float4*>(p) = make_float4(w[0], w[1], w[2], w[3]); }
 
-// acc[R] = sum_k x[k] * W[k][own outputs]   (sequential k, unfused)
+// acc[R] = fma-chain over k of x[k] * W[k][own outputs]   (sequential k)
 template <int G, int R>
 CM_DEVICE void dot_rows(const float* __restrict__ W /*[H][H]*/, const float* __restrict__ x /*[H]*/, int H, int g,
                         float (&acc)[R]) {
     constexpr int V = VecW<R>::V;
     constexpr int NCH = R / V;
-#pragma unroll
-    for (int i = 0; i < R; ++i) acc[i] = 0.0f;
     if constexpr (R == 1) {
+        acc[0] = 0.0f;
         if (g < H) {
-            for (int k = 0; k < H; ++k) acc[0] = fadd(acc[0], fmul(x[k], W[(size_t)k * H + g]));
+            for (int k = 0; k < H; ++k) acc[0] = ffma(x[k], W[(size_t)k * H + g], acc[0]);
         }
     } else {
+        float2 a2[R / 2];
+#pragma unroll
+        for (int i = 0; i < R / 2; ++i) a2[i] = make_float2(0.0f, 0.0f);
 #pragma unroll 2
         for (int k4 = 0; k4 < H; k4 += 4) {
             float xv[4];
@@ -155,10 +178,13 @@ CM_DEVICE void dot_rows(const float* __restrict__ W /*[H][H]*/, const float* __r
                     float w[V];
                     load_vec<V>(wrow + (g + G * i) * V, w);
 #pragma unroll
-                    for (int v = 0; v < V; ++v) acc[i * V + v] = fadd(acc[i * V + v], fmul(xv[kk], w[v]));
+                    for (int v = 0; v < V; v += 2)
+                        a2[(i * V + v) / 2] = ffma2(xv[kk], make_float2(w[v], w[v + 1]), a2[(i * V + v) / 2]);
                 }
             }
         }
+#pragma unroll
+        for (int i = 0; i < R / 2; ++i) { acc[2 * i] = a2[i].x; acc[2 * i + 1] = a2[i].y; }
     }
 }
 
@@ -225,8 +251,91 @@ CM_DEVICE void heads(const float* __restrict__ Wh /*[H][HP]*/, const float* __re
                      int H, int HP, int n_out, float* __restrict__ out, int g) {
     for (int o = g; o < n_out; o += G) {
         float acc = 0.0f;
-        for (int k = 0; k < H; ++k) acc = fadd(acc, fmul(x[k], Wh[(size_t)k * HP + o]));
+        for (int k = 0; k < H; ++k) acc = ffma(x[k], Wh[(size_t)k * HP + o], acc);
         out[o] = fadd(acc, bh[o]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-cooperative network tile (fused kernel).  The TW trees of a warp share every weight load:
+// lane owns R consecutive neurons j0 = lane*R.. for ALL TW trees, the activations live in shared
+// memory k-major with the trees interleaved (x[k][t]) so one vector load fetches x_k of every tree.
+// Per k: one LDS of R weights + one broadcast LDS of TW activations feed TW*R fused multiply-adds,
+// issued two per instruction (FFMA2: packed over neuron pairs, or over tree pairs when R == 1).
+// Same sequential-k FMA chain per (tree, neuron) as cmo_linear.
+// ------------------------------------------------------------------------------------------------
+template <int TW, int R>
+struct WarpAcc {
+    static constexpr int NP = (R >= 2) ? TW * (R / 2) : (TW >= 2 ? TW / 2 : 1);
+    float2 v[NP];
+    CM_DEVICE void zero() {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) v[i] = make_float2(0.0f, 0.0f);
+    }
+    // value for tree t, neuron v_
+    CM_DEVICE float get(int t, int v_) const {
+        if constexpr (R >= 2) { const float2 q = v[t * (R / 2) + v_ / 2]; return (v_ & 1) ? q.y : q.x; }
+        else if constexpr (TW >= 2) { const float2 q = v[t / 2]; return (t & 1) ? q.y : q.x; }
+        else return v[0].x;
+    }
+};
+
+template <int TW, int R>
+CM_DEVICE void warp_dot(const float* __restrict__ W /*[H][H]*/, const float* __restrict__ x /*[H][TW]*/, int H, int lane,
+                        WarpAcc<TW, R>& acc) {
+    acc.zero();
+    const int j0 = lane * R;
+    if (j0 >= H) return;
+    const float* wp = W + j0;
+#pragma unroll 4
+    for (int k = 0; k < H; ++k) {
+        float xk[TW], w[R];
+        load_vec<TW>(x + (size_t)k * TW, xk);
+        load_vec<R>(wp + (size_t)k * H, w);
+        if constexpr (R >= 2) {
+#pragma unroll
+            for (int t = 0; t < TW; ++t)
+#pragma unroll
+                for (int v = 0; v < R; v += 2)
+                    acc.v[t * (R / 2) + v / 2] = ffma2(xk[t], make_float2(w[v], w[v + 1]), acc.v[t * (R / 2) + v / 2]);
+        } else if constexpr (TW >= 2) {
+#pragma unroll
+            for (int t = 0; t < TW; t += 2) acc.v[t / 2] = ffma2(w[0], make_float2(xk[t], xk[t + 1]), acc.v[t / 2]);
+        } else {
+            acc.v[0].x = ffma(xk[0], w[0], acc.v[0].x);
+        }
+    }
+}
+
+// one dynamics layer for the warp's TW trees: xout[j][t] = relu(dot + b[j]) + xin[j][t]
+template <int TW, int R>
+CM_DEVICE void warp_layer(const float* __restrict__ K, const float* __restrict__ b, const float* __restrict__ xin,
+                          float* __restrict__ xout, int H, int lane) {
+    WarpAcc<TW, R> acc;
+    warp_dot<TW, R>(K, xin, H, lane, acc);
+    const int j0 = lane * R;
+    if (j0 >= H) return;
+#pragma unroll
+    for (int v = 0; v < R; ++v) {
+        float xr[TW], y[TW];
+        load_vec<TW>(xin + (size_t)(j0 + v) * TW, xr);
+        const float bb = b[j0 + v];
+#pragma unroll
+        for (int t = 0; t < TW; ++t) y[t] = fadd(frelu(fadd(acc.get(t, v), bb)), xr[t]);
+        store_vec<TW>(xout + (size_t)(j0 + v) * TW, y);
+    }
+}
+
+// heads for the warp's TW trees: lane <-> (tree t, output o); out[t*HP + o] = x[:,t] @ Wh[:,o] + bh[o]
+template <int TW>
+CM_DEVICE void warp_heads(const float* __restrict__ Wh /*[H][HP]*/, const float* __restrict__ bh, const float* __restrict__ x,
+                          int H, int HP, int n_out, float* __restrict__ out, int lane) {
+    for (int idx = lane; idx < TW * n_out; idx += 32) {
+        const int t = idx / n_out, o = idx - t * n_out;
+        float acc = 0.0f;
+#pragma unroll 4
+        for (int k = 0; k < H; ++k) acc = ffma(x[(size_t)k * TW + t], Wh[(size_t)k * HP + o], acc);
+        out[t * HP + o] = fadd(acc, bh[o]);
     }
 }
 

@@ -43,19 +43,22 @@ CM_DEVICE void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes
                  : "memory");
 }
 
-template <int G, int R>
+// GS = lanes per tree in the select / expand / backup phases (TW = 32/GS trees per warp);
+// R = neurons per lane in the warp-cooperative network tile (32*R >= H).
+template <int GS, int R>
 __global__ void __launch_bounds__(512, 1) search_fused_kernel(const FusedParams p) {
+    constexpr int TW = 32 / GS;
     extern __shared__ __align__(128) unsigned char smem[];
     float* w_s = reinterpret_cast<float*>(smem);
     double* sq_s = reinterpret_cast<double*>(smem + p.off_sqrt);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
 
     const int tid = threadIdx.x;
-    const int g = tid & (G - 1);
-    const int slot = tid / G;
-    const int TPB = blockDim.x / G;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane & (GS - 1);   // lane within the tree's sub-group
+    const int tw = lane / GS;        // tree within the warp
+    const int TPB = (blockDim.x >> 5) * TW;
     const int H = p.pk.H, L = p.pk.L, HP = p.pk.HP, A = p.tv.A, A_net = p.A_net;
-    const int HX = H + 4;
 
     // ---- stage parameters (TMA bulk) + sqrt table -------------------------------------------
     if (tid == 0) mbar_init(bar, 1);
@@ -77,38 +80,48 @@ __global__ void __launch_bounds__(512, 1) search_fused_kernel(const FusedParams 
     const float* wh_s = w_s + p.pk.heads_w;
     const float* bh_s = w_s + p.pk.heads_b;
 
-    unsigned char* my = smem + p.off_slots + (size_t)slot * p.slot_bytes;
+    // per-warp scratch: x0,x1 [H][TW] | lg,eb [TW][HP] | path [TW][S_max+2]
+    unsigned char* my = smem + p.off_slots + (size_t)warp * p.slot_bytes;
     float* x0 = reinterpret_cast<float*>(my);
-    float* x1 = x0 + HX;
-    float* lg = x1 + HX;
-    float* eb = lg + HP;
-    int* path_s = reinterpret_cast<int*>(eb + HP);
+    float* x1 = x0 + (size_t)H * TW;
+    float* lg_w = x1 + (size_t)H * TW;
+    float* eb_w = lg_w + TW * HP;
+    float* lg = lg_w + tw * HP;
+    float* eb = eb_w + tw * HP;
+    int* path_s = reinterpret_cast<int*>(eb_w + TW * HP) + tw * (p.tv.S_max + 2);
+    const int j0 = lane * R;
+    const bool own = j0 < H;
+    const size_t hstride = (size_t)(p.tv.S_max + 1) * H;
 
     for (int t0 = blockIdx.x * TPB; t0 < p.tv.B; t0 += gridDim.x * TPB) {
-        const int t = t0 + slot;
+        const int tbase = t0 + warp * TW;          // first tree of this warp
+        const int t = tbase + tw;
         const bool active = t < p.tv.B;
         const size_t tt = active ? (size_t)t : 0;
         Node* nodes = p.tv.nodes + tt * p.tv.N;
         int32_t* eidx = p.tv.child_eidx + tt * p.tv.N;
         double* rprior = p.tv.root_prior + tt * A;
         int32_t* exp_node = p.tv.exp_node + tt * (p.tv.S_max + 1);
-        float* hidden = p.tv.hidden + tt * (size_t)(p.tv.S_max + 1) * H;
+        float* hidden = p.tv.hidden + tt * hstride;
         int* path = p.path_in_smem ? path_s : (p.tv.path + tt * (p.tv.S_max + 2));
 
         // ---- root: prediction -> softmax -> expand -> noise (mcts.py:126-136) ---------------
         if (active) {
-            copy_row<G, R>(p.root_hidden + tt * H, x0, H, g);
-            copy_row<G, R>(p.root_hidden + tt * H, hidden, H, g);
+            for (int j = g; j < H; j += GS) {
+                const float v = p.root_hidden[tt * H + j];
+                x0[(size_t)j * TW + tw] = v;
+                hidden[j] = v;
+            }
         }
         __syncwarp();
-        if (active) heads<G>(wh_s, bh_s, x0, H, HP, A_net, lg, g);
+        warp_heads<TW>(wh_s, bh_s, x0, H, HP, A_net, lg_w, lane);
         if (active && p.noise_mode == 2 && g == 0)
             dirichlet_row(rprior, A, p.alpha, p.seed, p.tree_base + (unsigned long long)t);
         __syncwarp();
         {
-            const float ssum = softmax_prepare<G>(lg, eb, A_net, g, active);
+            const float ssum = softmax_prepare<GS>(lg, eb, A_net, g, active);
             if (active) {
-                for (int a = g; a < A; a += G) {
+                for (int a = g; a < A; a += GS) {
                     const float p32 = __fdiv_rn(eb[a], ssum);
                     double pd = (double)p32;
                     if (p.noise_mode == 1)
@@ -132,34 +145,72 @@ __global__ void __launch_bounds__(512, 1) search_fused_kernel(const FusedParams 
         long long depth = 0;
         for (int s = 0; s < p.S; ++s) {
             int plen, parent_e, action;
-            const int leaf = select_leaf<G>(nodes, eidx, rprior, sq_s, A, p.c_puct, 2 * s, path, g, active, plen,
-                                            parent_e, action);
+            const int leaf = select_leaf<GS>(nodes, eidx, rprior, sq_s, A, p.c_puct, 2 * s, path, g, active, plen,
+                                             parent_e, action);
             __syncwarp();
             const int k = s + 1;  // expansion index of the leaf
-            if (active) embed_add<G, R>(hidden + (size_t)parent_e * H, emb_s + (size_t)action * H, x0, H, g);
+            // x0[j][t'] = hidden_{t'}[parent_e][j] + Emb[action_{t'}][j] for the warp's TW trees
+            if (own) {
+                float hv[TW][R];
+#pragma unroll
+                for (int u = 0; u < TW; ++u) {
+                    const int pe = __shfl_sync(0xffffffffu, parent_e, u * GS);
+                    const int ac = __shfl_sync(0xffffffffu, action, u * GS);
+                    const size_t tu = (tbase + u < p.tv.B) ? (size_t)(tbase + u) : 0;
+                    float ev[R];
+                    load_vec<R>(p.tv.hidden + tu * hstride + (size_t)pe * H + j0, hv[u]);
+                    load_vec<R>(emb_s + (size_t)ac * H + j0, ev);
+#pragma unroll
+                    for (int v = 0; v < R; ++v) hv[u][v] = fadd(hv[u][v], ev[v]);
+                }
+#pragma unroll
+                for (int v = 0; v < R; ++v) {
+                    float y[TW];
+#pragma unroll
+                    for (int u = 0; u < TW; ++u) y[u] = hv[u][v];
+                    store_vec<TW>(x0 + (size_t)(j0 + v) * TW, y);
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < TW; ++u) {  // keep the shuffles warp-uniform
+                    (void)__shfl_sync(0xffffffffu, parent_e, u * GS);
+                    (void)__shfl_sync(0xffffffffu, action, u * GS);
+                }
+            }
             __syncwarp();
             float* cur = x0;
             float* nxt = x1;
             for (int l = 0; l < L; ++l) {
-                if (active) dyn_layer<G, R>(w_s + p.pk.layer_k(l), w_s + p.pk.layer_b(l), cur, nxt, H, g);
+                warp_layer<TW, R>(w_s + p.pk.layer_k(l), w_s + p.pk.layer_b(l), cur, nxt, H, lane);
                 __syncwarp();
                 float* tmp = cur; cur = nxt; nxt = tmp;
             }
-            if (active) {
-                copy_row<G, R>(cur, hidden + (size_t)k * H, H, g);
-                heads<G>(wh_s, bh_s, cur, H, HP, A_net + 1, lg, g);
+            if (own) {
+                float hv[R][TW];
+#pragma unroll
+                for (int v = 0; v < R; ++v) load_vec<TW>(cur + (size_t)(j0 + v) * TW, hv[v]);
+#pragma unroll
+                for (int u = 0; u < TW; ++u) {
+                    if (tbase + u < p.tv.B) {
+                        float y[R];
+#pragma unroll
+                        for (int v = 0; v < R; ++v) y[v] = hv[v][u];
+                        store_vec<R>(p.tv.hidden + (size_t)(tbase + u) * hstride + (size_t)k * H + j0, y);
+                    }
+                }
             }
+            warp_heads<TW>(wh_s, bh_s, cur, H, HP, A_net + 1, lg_w, lane);
             __syncwarp();
-            const float ssum = softmax_prepare<G>(lg, eb, A_net, g, active);
+            const float ssum = softmax_prepare<GS>(lg, eb, A_net, g, active);
             if (active) {
                 const float value = lg[A_net];
                 const int cbase = 1 + k * A;
-                for (int a = g; a < A; a += G) {
+                for (int a = g; a < A; a += GS) {
                     store_node(nodes + cbase + a, 0.0, 0, __fdiv_rn(eb[a], ssum));
                     eidx[cbase + a] = -1;
                 }
                 if (g == 0) { eidx[leaf] = k; exp_node[k] = leaf; }
-                backup_path<G>(nodes, path, plen, value, g);
+                backup_path<GS>(nodes, path, plen, value, g);
                 depth += plen;
             }
             __syncwarp();
@@ -169,7 +220,7 @@ __global__ void __launch_bounds__(512, 1) search_fused_kernel(const FusedParams 
         if (active) {
             long long total = 0;
             for (int a = 0; a < A; ++a) total += load_node(nodes + 1 + a).visit;
-            for (int a = g; a < p.A_cfg; a += G) {
+            for (int a = g; a < p.A_cfg; a += GS) {
                 const int c = a < A ? load_node(nodes + 1 + a).visit : 0;
                 p.out_visits[tt * p.A_cfg + a] = c;
                 p.out_probs[tt * p.A_cfg + a] =
@@ -189,28 +240,27 @@ __global__ void __launch_bounds__(512, 1) search_fused_kernel(const FusedParams 
 // ------------------------------------------------------------------------------------------------
 // host-side launch
 // ------------------------------------------------------------------------------------------------
-template <int G, int R>
+template <int GS, int R>
 static cudaError_t launch_one(const FusedParams& p, int grid, int block, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(search_fused_kernel<G, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(search_fused_kernel<GS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    search_fused_kernel<G, R><<<grid, block, smem, st>>>(p);
+    search_fused_kernel<GS, R><<<grid, block, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-template <int G>
+template <int GS>
 static cudaError_t launch_g(int R, const FusedParams& p, int grid, int block, size_t smem, cudaStream_t st) {
     switch (R) {
-        case 1: return launch_one<G, 1>(p, grid, block, smem, st);
-        case 2: return launch_one<G, 2>(p, grid, block, smem, st);
-        case 4: return launch_one<G, 4>(p, grid, block, smem, st);
-        case 8: return launch_one<G, 8>(p, grid, block, smem, st);
-        case 16: return launch_one<G, 16>(p, grid, block, smem, st);
+        case 1: return launch_one<GS, 1>(p, grid, block, smem, st);
+        case 2: return launch_one<GS, 2>(p, grid, block, smem, st);
+        case 4: return launch_one<GS, 4>(p, grid, block, smem, st);
+        case 8: return launch_one<GS, 8>(p, grid, block, smem, st);
         default: return cudaErrorInvalidValue;
     }
 }
 
-cudaError_t launch_search_fused(int G, int R, const FusedParams& p, int grid, int block, size_t smem, cudaStream_t st) {
-    switch (G) {
+cudaError_t launch_search_fused(int GS, int R, const FusedParams& p, int grid, int block, size_t smem, cudaStream_t st) {
+    switch (GS) {
         case 4: return launch_g<4>(R, p, grid, block, smem, st);
         case 8: return launch_g<8>(R, p, grid, block, smem, st);
         case 16: return launch_g<16>(R, p, grid, block, smem, st);

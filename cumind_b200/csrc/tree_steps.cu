@@ -13,12 +13,12 @@ static constexpr int kWarpsPerBlock = 4;
 
 CM_DEVICE int warp_tree_index() { return blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); }
 
-// generic-H layer: lane computes outputs j = lane, lane+32, ... (sequential k, unfused)
+// generic-H layer: lane computes outputs j = lane, lane+32, ... (sequential-k FMA chain)
 CM_DEVICE void dyn_layer_any(const float* __restrict__ K, const float* __restrict__ b, const float* __restrict__ xin,
                              float* __restrict__ xout, int H, int lane) {
     for (int j = lane; j < H; j += 32) {
         float acc = 0.0f;
-        for (int k = 0; k < H; ++k) acc = fadd(acc, fmul(xin[k], K[(size_t)k * H + j]));
+        for (int k = 0; k < H; ++k) acc = ffma(xin[k], K[(size_t)k * H + j], acc);
         xout[j] = fadd(frelu(fadd(acc, b[j])), xin[j]);
     }
 }

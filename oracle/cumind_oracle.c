@@ -16,8 +16,10 @@
  * cross-correlation; BatchNorm inference (x-mean)*rsqrt(var+1e-5)*scale+bias; softmax =
  * exp(x-max)/sum.  Those libraries do not define a floating-point summation order, so this file
  * PINS one (DESIGN.md "Canonical numerics"):
- *   - every dot product is sequential k = 0..K-1, acc = fl32(acc + fl32(x_k*w_k)), acc0 = +0,
- *     then fl32(acc + bias); never fused (compile with -ffp-contract=off);
+ *   - every dot product is a sequential chain of IEEE fused multiply-adds over k = 0..K-1:
+ *     acc = fmaf(x_k, w_k, acc) (ONE rounding per step), acc0 = +0, then fl32(acc + bias).
+ *     Every other operation is a single correctly rounded fp32 op and is never contracted
+ *     (compile with -ffp-contract=off);
  *   - conv taps in (ky,kx,ci) order, taps that fall in the zero padding are skipped;
  *   - exp for softmax is cm_pexp() below: fp64, plain mul/add only, rounded once to fp32;
  *   - tree statistics are float64 in the reference's operation order (mcts.py:64-65, 97-98, 222).
@@ -123,6 +125,11 @@ CMO_EXPORT double cmo_pexp(double d) {
     return p * scale;
 }
 
+/* fmaf() exposed so the tests can pin network_np.fma32 (the NumPy emulation) against it. */
+CMO_EXPORT void cmo_fmaf_array(const float* a, const float* b, const float* c, float* out, long n) {
+    for (long i = 0; i < n; ++i) out[i] = fmaf(a[i], b[i], c[i]);
+}
+
 /* jax.nn.softmax(logits, axis=-1) in fp32 (mcts.py:128,191) with the pinned exp. */
 CMO_EXPORT void cmo_softmax(const float* logits, int A, float* out) {
     float m = logits[0];
@@ -137,14 +144,11 @@ CMO_EXPORT void cmo_softmax(const float* logits, int A, float* out) {
     for (int a = 0; a < A; ++a) out[a] = out[a] / s;
 }
 
-/* nnx.Linear for one row: y[j] = fl(sum_k fl(x[k]*K[k,j]) + b[j]); K is [in,out] row-major. */
+/* nnx.Linear for one row: y[j] = fl(fma-chain_k(x[k], K[k,j]) + b[j]); K is [in,out] row-major. */
 static void cmo_linear(const float* x, const float* K, const float* b, int in, int out, float* y) {
     for (int j = 0; j < out; ++j) {
         float acc = 0.0f;
-        for (int k = 0; k < in; ++k) {
-            float p = x[k] * K[(size_t)k * out + j];
-            acc = acc + p;
-        }
+        for (int k = 0; k < in; ++k) acc = fmaf(x[k], K[(size_t)k * out + j], acc);
         y[j] = acc + b[j];
     }
 }
@@ -211,10 +215,7 @@ static void cmo_conv3x3(const float* in, int Hh, int Ww, int Cin, const float* K
                         if (ix < 0 || ix >= Ww) continue;
                         const float* ip = in + ((size_t)iy * Ww + ix) * Cin;
                         const float* kp = K + ((size_t)(ky * 3 + kx) * Cin) * Cout + co;
-                        for (int ci = 0; ci < Cin; ++ci) {
-                            float p = ip[ci] * kp[(size_t)ci * Cout];
-                            acc = acc + p;
-                        }
+                        for (int ci = 0; ci < Cin; ++ci) acc = fmaf(ip[ci], kp[(size_t)ci * Cout], acc);
                     }
                 }
                 out[((size_t)oy * Wo + ox) * Cout + co] = acc + b[co];

@@ -10,7 +10,18 @@ from typing import Dict, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "_build", "libcumind_oracle.so")
+def _host_has_fma() -> bool:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return " fma" in line
+    except OSError:
+        pass
+    return False
+
+
+_SO = os.path.join(_HERE, "_build", "libcumind_oracle_fma.so" if _host_has_fma() else "libcumind_oracle.so")
 _lib = None
 
 
@@ -59,6 +70,13 @@ def param_count(desc: NetDesc) -> int:
 
 def pexp(d: float) -> float:
     return float(lib().cmo_pexp(float(d)))
+
+
+def fmaf(a: np.ndarray, b: np.ndarray, c: np.ndarray) -> np.ndarray:
+    a, b, c = (np.ascontiguousarray(np.broadcast_to(np.asarray(v, np.float32), np.broadcast(a, b, c).shape)) for v in (a, b, c))
+    out = np.empty_like(a)
+    lib().cmo_fmaf_array(_p(a), _p(b), _p(c), _p(out), C.c_long(a.size))
+    return out
 
 
 def softmax(logits: np.ndarray) -> np.ndarray:

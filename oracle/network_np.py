@@ -11,9 +11,11 @@ flax.nnx / jax are absent from this image (flax 0.10.6, jax 0.6.2 pinned in uv.l
 semantics are restated from their published behaviour (Linear: x@kernel[in,out]+bias; Embed: row
 lookup; Conv: NHWC cross-correlation, symmetric padding; BatchNorm inference; softmax).
 
-NumPy float32 element-wise ops are IEEE-exact and never fused, so the sequential-k loops below are
-bit-identical to oracle/cumind_oracle.c (checked by tests/test_oracle_golden.py) and to the CUDA
-fp32-exact kernels.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
+Canonical dot product = sequential chain of IEEE fp32 fused multiply-adds (fma32 below emulates
+fmaf exactly in NumPy: exact float64 product, TwoSum error term, round-to-odd, one rounding to
+float32); everything else is a single float32 op, which NumPy never fuses.  The loops below are
+therefore bit-identical to oracle/cumind_oracle.c (checked by tests/test_oracle_golden.py) and to
+the CUDA fp32-exact kernels.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
 import this module; cumind_b200/ never does.
 """
 
@@ -63,13 +65,36 @@ def softmax(logits: np.ndarray) -> np.ndarray:
     return e / s[..., None]
 
 
+def fma32(a: np.ndarray, b: np.ndarray, c: np.ndarray) -> np.ndarray:
+    """Exact IEEE-754 binary32 fused multiply-add fl32(a*b + c) for float32 arrays.
+
+    a*b is exact in float64 (24+24 significand bits).  The float64 sum s = p + c may round; the
+    TwoSum error term tells whether and in which direction, s is turned into the round-to-odd
+    result (truncate toward zero, OR a sticky bit into the last place) and a single final rounding
+    to float32 is then exact because float64 carries more than two extra bits.  Checked against
+    fmaf() in tests/test_oracle_golden.py, including true double-rounding cases."""
+    a64, b64, c64 = (np.asarray(v, dtype=f32).astype(np.float64) for v in (a, b, c))
+    with np.errstate(over="ignore", invalid="ignore"):
+        p = a64 * b64
+        s = np.asarray(p + c64)
+        bb = s - p
+        err = (p - (s - bb)) + (c64 - bb)
+    bits = s.view(np.uint64)
+    inexact = np.isfinite(s) & np.isfinite(err) & (err != 0)
+    toward_zero = inexact & ((err < 0) != (s < 0)) & (s != 0)
+    bits = np.where(toward_zero, bits - np.uint64(1), bits)
+    bits = np.where(inexact, bits | np.uint64(1), bits)
+    with np.errstate(over="ignore"):
+        return bits.view(np.float64).astype(f32)
+
+
 def linear(x: np.ndarray, kernel: np.ndarray, bias: np.ndarray) -> np.ndarray:
-    """nnx.Linear: sequential-k, unfused fp32. x [B,in], kernel [in,out], bias [out]."""
+    """nnx.Linear: sequential-k chain of fp32 FMAs, then + bias. x [B,in], kernel [in,out], bias [out]."""
     x = np.asarray(x, dtype=f32)
     kernel = np.asarray(kernel, dtype=f32)
     acc = np.zeros((x.shape[0], kernel.shape[1]), dtype=f32)
     for k in range(kernel.shape[0]):
-        acc = acc + x[:, k : k + 1] * kernel[k][None, :]
+        acc = fma32(x[:, k : k + 1], kernel[k][None, :], acc)
     return acc + np.asarray(bias, dtype=f32)[None, :]
 
 
@@ -99,7 +124,7 @@ def conv3x3(x: np.ndarray, kernel: np.ndarray, bias: np.ndarray, stride: int) ->
             patch = x[:, iy[vy]][:, :, ix[vx]]  # [B, ny, nx, Cin]
             sub = acc[:, ys[0] : ys[-1] + 1, xs[0] : xs[-1] + 1]  # valid output positions are contiguous
             for ci in range(Cin):
-                sub = sub + patch[..., ci : ci + 1] * kernel[ky, kx, ci][None, None, None, :]
+                sub = fma32(patch[..., ci : ci + 1], kernel[ky, kx, ci][None, None, None, :], sub)
             acc[:, ys[0] : ys[-1] + 1, xs[0] : xs[-1] + 1] = sub
     return acc + np.asarray(bias, dtype=f32)
 

@@ -111,6 +111,34 @@ def test_pinned_exp_is_bit_reproducible_and_accurate():
     assert np.all(np.abs(f.view(np.int32).astype(np.int64) - e.view(np.int32).astype(np.int64)) <= 1)
 
 
+def test_numpy_fma_emulation_is_exact():
+    """network_np.fma32 == fmaf bit for bit: random operands over wide exponent ranges, exact
+    cancellation, specials, and a family of true double-rounding cases that a naive float64
+    evaluation gets wrong."""
+    rng = np.random.default_rng(0)
+
+    def rnd(n, span):
+        return (rng.standard_normal(n) * np.exp2(rng.integers(-span, span, n))).astype(np.float32)
+
+    for span in (2, 10, 40, 120):
+        a, b, c = rnd(300000, span), rnd(300000, span), rnd(300000, span)
+        assert hp.bits_equal(nn.fma32(a, b, c), lo.fmaf(a, b, c))
+    a, b = rnd(100000, 3), rnd(100000, 3)
+    c = (-(a.astype(np.float64) * b.astype(np.float64))).astype(np.float32)
+    assert hp.bits_equal(nn.fma32(a, b, c), lo.fmaf(a, b, c))
+    sp = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 3.4e38, -3.4e38, 1.0, -1.0, 1e-38], np.float32)
+    A, B, Cc = (m.ravel() for m in np.meshgrid(sp, sp, sp, indexing="ij"))
+    assert hp.bits_equal(nn.fma32(A, B, Cc), lo.fmaf(A, B, Cc))
+    u = np.arange(1, 200, dtype=np.float64)
+    a = (1 + u * 2.0**-23).astype(np.float32)
+    b = (2.0**-24 * (1 - u * 2.0**-23)).astype(np.float32)
+    c = np.full(a.shape, 1 + 2.0**-23, np.float32)      # a*b + c sits just below a float32 midpoint
+    want = lo.fmaf(a, b, c)
+    assert hp.bits_equal(nn.fma32(a, b, c), want) and hp.bits_equal(nn.fma32(-a, b, -c), lo.fmaf(-a, b, -c))
+    naive = (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+    assert not np.array_equal(naive, want)  # double rounding is real; the emulation avoids it
+
+
 def test_reference_quirks_are_reproduced():
     """root.n == 2S, leaf never backed up, sum of root-children visits == S - A once S >= 2A-1."""
     case = next(c for c in SEARCH if c["A_net"] == 4 and c["A_cfg"] == 4 and c["S"] == 25)
