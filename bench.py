@@ -138,7 +138,7 @@ def c_oracle_rate(S: int, trees: int = 512):
 
 # ---- clocks ------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    def __init__(self, index: int, period: float = 0.01):
+    def __init__(self, index: int, period: float = 0.002):
         super().__init__(daemon=True)
         self.period, self.samples, self.stop_flag, self.live = period, [], False, False
         self.max_mhz, self.h, self.nv = None, None, None
@@ -233,7 +233,14 @@ def run_native(args, rank: int, world: int, local_rank: int):
 
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    B, S, K, W = args.trees, args.sims, args.steps, args.warmup
+    S, K, W = args.sims, args.steps, args.warmup
+    tree_base = rank * args.trees
+    if args.total_trees > 0:
+        from cumind_b200.dist import shard_bounds
+
+        lo_, hi_ = shard_bounds(args.total_trees, rank, world)
+        args.trees, tree_base = hi_ - lo_, lo_
+    B = args.trees
     _, blob, obs, noise = make_inputs(B, rank)
     cfg = Config(hidden_dim=H, num_blocks=L, num_simulations=S, action_space_size=A, observation_shape=OBS_SHAPE, c_puct=C_PUCT,
                  dirichlet_alpha=ALPHA, exploration_fraction=FRAC)
@@ -249,7 +256,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
 
     def step_dev():
         hidden = net.representation_network(d_obs)
-        return _search_device(mcts, hidden, d_noise, rank * B)
+        return _search_device(mcts, hidden, d_noise, tree_base)
 
     for _ in range(max(W, 3)):
         step_dev()
@@ -271,7 +278,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
         starts[i].record()
         hidden = net.representation_network(d_obs)
         k_start[i].record()
-        _search_device(mcts, hidden, d_noise, rank * B)
+        _search_device(mcts, hidden, d_noise, tree_base)
         ends[i].record()
         flush.fill_(i & 0xFF)
     torch.cuda.synchronize()
@@ -304,11 +311,14 @@ def run_native(args, rank: int, world: int, local_rank: int):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, e2e_ms, kern_ms_mean = (float(x) for x in t.cpu())
+    t_trees = torch.tensor([B], dtype=torch.int64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_trees)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-    sims_per_step = world * B * S
+    sims_per_step = int(t_trees.item()) * S
     value = sims_per_step * K / (total_ms * 1e-3)
     e2e_value = sims_per_step * K / (e2e_ms * 1e-3)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -324,8 +334,8 @@ def run_native(args, rank: int, world: int, local_rank: int):
         traffic = json.load(open(tpath)).get("search_fused_dram_bytes_per_launch")
     line = {
         "metric": "batched MCTS simulations/sec", "value": value, "unit": "simulations/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
-        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": workload_config(args, per_gpu=B),
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong" if args.total_trees > 0 else "weak", "vs_baseline": None, "dtype": "fp32",
+        "data": "synthetic", "config": workload_config(args, per_gpu=B),
         "e2e": {"value": e2e_value, "unit": "simulations/s", "h2d_bytes_per_step": int(obs.nbytes + noise.nbytes),
                 "d2h_bytes_per_step": int(actions.nbytes + probs.nbytes), "ms_per_step": e2e_ms / K},
         "gpu_launches": int(launches),
@@ -370,10 +380,12 @@ def _search_device(mcts, hidden, d_noise, tree_index_base):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--trees", type=int, default=4096, help="trees per GPU")
+    ap.add_argument("--trees", type=int, default=4096, help="trees per GPU (weak scaling)")
+    ap.add_argument("--total-trees", type=int, default=0,
+                    help="global batch sharded across the ranks (strong scaling; BASELINE configs[3] uses 65536)")
     ap.add_argument("--sims", type=int, default=50)
     ap.add_argument("--lanes", type=int, default=0, help="lanes per tree (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")

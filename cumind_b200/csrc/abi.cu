@@ -20,11 +20,13 @@ struct cumind_net {
     size_t n_params;
     float* d_blob;
     float* d_pack;
+    float* d_fpack;       // FusedPackLayout copy for the fused search kernel
     BlobLayout lo;
     PackLayout pk;
+    FusedPackLayout fpk;
     float* d_work;        // activation workspace of the image encoder (lazily sized, grow-only)
     size_t work_bytes;
-    std::vector<float> h_pack;
+    std::vector<float> h_pack, h_fpack;
 };
 
 struct cumind_tree {
@@ -87,6 +89,36 @@ static void build_pack(const cumind_net* n, const float* blob, std::vector<float
     pack[pk.heads_b + A + 1] = blob[lo.rew_b];
 }
 
+// canonical blob -> FusedPackLayout (lane-blocked layer kernels, transposed heads)
+static void build_fused_pack(const cumind_net* n, const float* blob, std::vector<float>& fp) {
+    const FusedPackLayout& pk = n->fpk;
+    const BlobLayout& lo = n->lo;
+    const int H = pk.H, L = pk.L, A = pk.A, R = pk.R > 0 ? pk.R : 1;
+    fp.assign(pk.total, 0.0f);
+    memcpy(&fp[pk.emb], blob + lo.emb, sizeof(float) * (size_t)A * H);
+    for (int l = 0; l < L; ++l) {
+        const float* K = blob + lo.dyn + (size_t)l * ((size_t)H * H + H);
+        const float* b = K + (size_t)H * H;
+        if (pk.R > 0) {
+            for (int k = 0; k < H; ++k)
+                for (int lane = 0; lane < 32; ++lane)
+                    for (int v = 0; v < R; ++v) {
+                        const int j = lane * R + v;
+                        if (j < H) fp[pk.layer_w(l) + FusedPackLayout::w_index(k, lane, v, R)] = K[(size_t)k * H + j];
+                    }
+        }
+        memcpy(&fp[pk.layer_b(l)], b, sizeof(float) * H);
+    }
+    for (int k = 0; k < H; ++k) {
+        for (int a = 0; a < A; ++a) fp[pk.heads_w + (size_t)a * pk.HS + k] = blob[lo.pol_k + (size_t)k * A + a];
+        fp[pk.heads_w + (size_t)A * pk.HS + k] = blob[lo.val_k + k];
+        fp[pk.heads_w + (size_t)(A + 1) * pk.HS + k] = blob[lo.rew_k + k];
+    }
+    for (int a = 0; a < A; ++a) fp[pk.heads_b + a] = blob[lo.pol_b + a];
+    fp[pk.heads_b + A] = blob[lo.val_b];
+    fp[pk.heads_b + A + 1] = blob[lo.rew_b];
+}
+
 extern "C" int cumind_net_create(const cumind_net_desc* desc, const float* h_params, size_t n_params, cumind_net** out) {
     if (!out) return fail("cumind_net_create: out is NULL");
     *out = nullptr;
@@ -102,15 +134,17 @@ extern "C" int cumind_net_create(const cumind_net_desc* desc, const float* h_par
     n->desc = *desc;
     n->lo = lo;
     n->pk = make_pack_layout(desc->hidden_dim, desc->num_blocks, desc->action_space_size);
+    n->fpk = make_fused_pack_layout(desc->hidden_dim, desc->num_blocks, desc->action_space_size);
     n->n_params = n_params;
-    n->d_blob = n->d_pack = n->d_work = nullptr;
+    n->d_blob = n->d_pack = n->d_fpack = n->d_work = nullptr;
     n->work_bytes = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&n->device)) != cudaSuccess ||
         (e = cudaDeviceGetAttribute(&n->sm_count, cudaDevAttrMultiProcessorCount, n->device)) != cudaSuccess ||
         (e = cudaMalloc(&n->d_blob, sizeof(float) * lo.total)) != cudaSuccess ||
-        (e = cudaMalloc(&n->d_pack, sizeof(float) * n->pk.total)) != cudaSuccess) {
-        cudaFree(n->d_blob); cudaFree(n->d_pack);
+        (e = cudaMalloc(&n->d_pack, sizeof(float) * n->pk.total)) != cudaSuccess ||
+        (e = cudaMalloc(&n->d_fpack, sizeof(float) * n->fpk.total)) != cudaSuccess) {
+        cudaFree(n->d_blob); cudaFree(n->d_pack); cudaFree(n->d_fpack);
         delete n;
         return fail_cuda("cumind_net_create", e);
     }
@@ -126,6 +160,8 @@ extern "C" int cumind_net_update_params(cumind_net* n, const float* h_params, si
     if (n_params != n->n_params) return fail("cumind_net_update_params: parameter blob has the wrong size");
     cudaStream_t st = (cudaStream_t)stream;
     build_pack(n, h_params, n->h_pack);
+    build_fused_pack(n, h_params, n->h_fpack);
+    CM_CUDA(cudaMemcpyAsync(n->d_fpack, n->h_fpack.data(), sizeof(float) * n->fpk.total, cudaMemcpyHostToDevice, st));
     CM_CUDA(cudaMemcpyAsync(n->d_blob, h_params, sizeof(float) * n_params, cudaMemcpyHostToDevice, st));
     CM_CUDA(cudaMemcpyAsync(n->d_pack, n->h_pack.data(), sizeof(float) * n->pk.total, cudaMemcpyHostToDevice, st));
     CM_CUDA(cudaStreamSynchronize(st));  // h_pack is reused by the next update
@@ -136,6 +172,7 @@ extern "C" int cumind_net_destroy(cumind_net* n) {
     if (!n) return 0;
     cudaFree(n->d_blob);
     cudaFree(n->d_pack);
+    cudaFree(n->d_fpack);
     cudaFree(n->d_work);
     delete n;
     return 0;
@@ -328,22 +365,13 @@ static StepParams step_params(const cumind_tree* t, const cumind_net* n, const c
     return p;
 }
 
-// R = neurons per lane of the warp-cooperative network tile: H <= 32 -> 1, else the smallest of
-// {2,4,8} with 32*R >= H and H % R == 0 (vector alignment of the weight rows).
-static bool pick_R(int H, int& R) {
-    if (H <= 32) { R = 1; return true; }
-    const int cand[3] = {2, 4, 8};
-    for (int i = 0; i < 3; ++i)
-        if (32 * cand[i] >= H && H % cand[i] == 0 && H % 4 == 0) { R = cand[i]; return true; }
-    return false;
-}
-
 struct FusedPlan { int G, R, grid, block; size_t smem; FusedParams p; };
 
 static int plan_fused(const cumind_tree* t, const cumind_net* n, const cumind_search_cfg* c, FusedPlan& pl, std::string& why) {
     const int H = n->desc.hidden_dim, B = t->tv.B;
     const int sm = n->sm_count;
-    if (!pick_R(H, pl.R)) { why = "hidden_dim has no lane mapping"; return 1; }
+    pl.R = n->fpk.R;
+    if (pl.R <= 0) { why = "hidden_dim has no lane mapping"; return 1; }
     if (t->tv.A > 65535 || t->tv.S_max > 65533) { why = "tree too large for the packed select payload"; return 1; }
     int want = c->lanes_per_tree;
     if (want <= 0) {
@@ -355,11 +383,12 @@ static int plan_fused(const cumind_tree* t, const cumind_net* n, const cumind_se
     while (G * 2 <= want && G < 32) G *= 2;
     pl.G = G;
     const int TW = 32 / G;
-    const PackLayout& pk = n->pk;
+    const FusedPackLayout& pk = n->fpk;
     const size_t pack_bytes = pk.total * sizeof(float);
-    const int n_sqrt = 2 * t->tv.S_max + 2;
+    const int n_sqrt = 2 * t->tv.S_max + 4;
     const size_t off_sqrt = (pack_bytes + 15) & ~(size_t)15;
-    const size_t off_slots = (off_sqrt + (size_t)n_sqrt * sizeof(double) + 15) & ~(size_t)15;
+    const size_t off_recip = (off_sqrt + (size_t)n_sqrt * sizeof(double) + 15) & ~(size_t)15;
+    const size_t off_slots = (off_recip + (size_t)n_sqrt * sizeof(double) + 15) & ~(size_t)15;
     const size_t warp_base = ((size_t)(2 * H * TW + 2 * TW * pk.HP) * sizeof(float) + 15) & ~(size_t)15;
     const size_t path_bytes = ((size_t)TW * (t->tv.S_max + 2) * sizeof(int) + 15) & ~(size_t)15;
     const size_t kMax = 227 * 1024;
@@ -386,7 +415,7 @@ static int plan_fused(const cumind_tree* t, const cumind_net* n, const cumind_se
     pl.grid = blocks < cap ? blocks : cap;
     FusedParams& p = pl.p;
     p.tv = t->tv;
-    p.pack = n->d_pack;
+    p.pack = n->d_fpack;
     p.pk = pk;
     p.S = c->num_simulations;
     p.A_cfg = c->action_space_size;
@@ -400,6 +429,7 @@ static int plan_fused(const cumind_tree* t, const cumind_net* n, const cumind_se
     p.tree_base = c->tree_index_base;
     p.path_in_smem = path_in_smem;
     p.off_sqrt = (unsigned)off_sqrt;
+    p.off_recip = (unsigned)off_recip;
     p.off_slots = (unsigned)off_slots;
     p.slot_bytes = (unsigned)slot;
     p.off_bar = (unsigned)((off_slots + (size_t)nw * slot + 7) & ~(size_t)7);
@@ -509,6 +539,14 @@ extern "C" int cumind_dirichlet(double* d_noise, int32_t B, int32_t A, double al
                                 void* stream) {
     if (!d_noise || B <= 0 || A <= 0 || !(alpha > 0.0)) return fail("cumind_dirichlet: bad argument");
     CM_CUDA(launch_dirichlet(d_noise, B, A, alpha, seed, tree_index_base, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+extern "C" int cumind_selftest_division(uint64_t n_per_thread, uint64_t seed, int32_t max_divisor, uint64_t* d_counts2,
+                                        void* stream) {
+    if (!d_counts2 || max_divisor <= 0) return fail("cumind_selftest_division: bad argument");
+    CM_CUDA(launch_selftest_div(n_per_thread, seed, max_divisor, (unsigned long long*)d_counts2, (cudaStream_t)stream));
     g_launches += 1;
     return 0;
 }

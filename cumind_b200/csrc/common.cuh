@@ -86,6 +86,54 @@ inline PackLayout make_pack_layout(int H, int L, int A) {
     return p;
 }
 
+// R = neurons per lane of the fused kernel's warp-cooperative network tile: H <= 32 -> 1, else the
+// smallest of {2,4,8} with 32*R >= H and H % R == 0.  0 = no mapping (H % 4 != 0 or H > 256).
+inline int pick_neurons_per_lane(int H) {
+    if (H % 4 != 0) return 0;
+    if (H <= 32) return 1;
+    const int cand[3] = {2, 4, 8};
+    for (int i = 0; i < 3; ++i)
+        if (32 * cand[i] >= H && H % cand[i] == 0) return cand[i];
+    return 0;
+}
+
+// Parameters as the FUSED search kernel wants them in shared memory ("fpack"), one bulk copy:
+//   emb [A][H] | L x ( Wb_l | b_l [H] ) | Wht [HP][HS] | bh [HP]
+// Wb_l is the layer kernel in lane-blocked order: the lane that owns neurons j0 = lane*R .. j0+R-1
+// finds, for every block of 4 consecutive k, its 4*R weights in R 16-byte chunks laid out
+// [k/4][chunk][lane][4] (float index f = (k%4)*R + v -> chunk f/4, slot f%4), so each LDS.128 is
+// conflict-free and all offsets from the lane's base pointer are compile-time constants.
+// Lanes with j0 >= H hold zeros.  Wht is the head matrix transposed (row o = output o, stride
+// HS = H+1 so that rows start in different banks).
+struct FusedPackLayout {
+    int H, L, A, HP, R, HS;
+    size_t emb, layers, layer_stride, heads_w, heads_b, total;  // float offsets
+    CM_HOST_DEVICE size_t layer_w(int l) const { return layers + (size_t)l * layer_stride; }
+    CM_HOST_DEVICE size_t layer_b(int l) const { return layer_w(l) + (size_t)32 * R * H; }
+    CM_HOST_DEVICE static size_t w_index(int k, int lane, int v, int R) {
+        const int f = (k & 3) * R + v;
+        return ((((size_t)(k >> 2) * R + (f >> 2)) * 32 + lane) << 2) + (f & 3);
+    }
+};
+
+inline FusedPackLayout make_fused_pack_layout(int H, int L, int A) {
+    FusedPackLayout p;
+    p.H = H; p.L = L; p.A = A;
+    p.HP = (A + 2 + 3) & ~3;
+    p.R = pick_neurons_per_lane(H);
+    p.HS = H + 1;
+    auto al = [](size_t x) { return (x + 3) & ~(size_t)3; };
+    const int R = p.R > 0 ? p.R : 1;
+    size_t o = 0;
+    p.emb = o;     o = al(o + (size_t)A * H);
+    p.layer_stride = al((size_t)32 * R * H + H);
+    p.layers = o;  o = al(o + (size_t)L * p.layer_stride);
+    p.heads_w = o; o = al(o + (size_t)p.HP * p.HS);
+    p.heads_b = o; o = al(o + (size_t)p.HP);
+    p.total = o;
+    return p;
+}
+
 // ------------------------------------------------------------------------------------------------
 // tree storage
 // ------------------------------------------------------------------------------------------------
@@ -164,13 +212,39 @@ CM_DEVICE double pexp(double d) {
 
 // Node.ucb_score (mcts.py:51-65): inf if n == 0 else W/n + ((c*p)*sqrt(N))/(1+n), float64.
 // `sqrtN` is __dsqrt_rn((double)N_parent) (correctly rounded, same as math.sqrt).
+// a / d for a small positive integer d, correctly rounded, from r = RN(1/d):
+//   q0 = RN(a*r); two FMA residual corrections (Markstein): after the first q1 is faithful, and a
+//   faithful quotient corrected once more with an exact residual and r = RN(1/d) is RN(a/d)
+//   (the exception, a divisor significand of all ones, cannot occur for d < 2^53 - 1).
+// Outside the range where residuals are exact (|a| not in [2^-900, 2^900], a == 0, inf, NaN) it
+// falls back to the IEEE division.  tests/test_gpu_parity.py::test_small_divisor_division_is_ieee
+// checks it against __ddiv_rn on the device.
+CM_DEVICE double div_small(double a, double d, double r) {
+    double q = __dmul_rn(a, r);
+    q = __fma_rn(__fma_rn(-d, q, a), r, q);
+    q = __fma_rn(__fma_rn(-d, q, a), r, q);
+    const double m = fabs(a);
+    if (!(m >= 1.1830521861667747e-271 && m <= 8.452712498170644e+270))  // 2^-900 .. 2^900
+        q = (a == 0.0) ? a : __ddiv_rn(a, d);
+    return q;
+}
+
+// Node.ucb_score with the reciprocal table: recip[i] = RN(1/i).
+CM_DEVICE double ucb_score_tab(int32_t n, double W, double prior, double sqrtN, double c_puct,
+                               const double* __restrict__ recip) {
+    if (n == 0) return __longlong_as_double(0x7FF0000000000000LL);
+    const double explo = div_small(__dmul_rn(__dmul_rn(c_puct, prior), sqrtN), (double)(1 + n), recip[1 + n]);
+    return __dadd_rn(div_small(W, (double)n, recip[n]), explo);
+}
+
 // The compiler if-converts the n == 0 case, so the divisions always execute: feed them 1/1 then
 // (0/0 would take the slow special-case path of the IEEE division routine on every unvisited child).
 CM_DEVICE double ucb_score(int32_t n, double W, double prior, double sqrtN, double c_puct) {
     const bool unvisited = n == 0;
     const double nn = unvisited ? 1.0 : (double)n;
     const double ww = unvisited ? 1.0 : W;
-    const double explo = __ddiv_rn(__dmul_rn(__dmul_rn(c_puct, prior), sqrtN), (double)(1 + n));
+    const double num = unvisited ? 1.0 : __dmul_rn(__dmul_rn(c_puct, prior), sqrtN);  // sqrt(0) = 0 under a fresh parent
+    const double explo = __ddiv_rn(num, (double)(1 + n));
     const double s = __dadd_rn(__ddiv_rn(ww, nn), explo);
     return unvisited ? __longlong_as_double(0x7FF0000000000000LL) : s;
 }

@@ -7,8 +7,8 @@ namespace cm {
 
 struct FusedParams {
     TreeView tv;
-    const float* pack;      // device, PackLayout order
-    PackLayout pk;
+    const float* pack;      // device, FusedPackLayout order
+    FusedPackLayout pk;
     const float* root_hidden;  // [B][H]
     const double* noise;       // [B][A] or nullptr
     int32_t* out_visits;       // [B][A_cfg]
@@ -20,7 +20,7 @@ struct FusedParams {
     unsigned long long seed, tree_base;
     int path_in_smem;
     // shared-memory carve-up (bytes)
-    unsigned off_sqrt, off_slots, slot_bytes, off_bar;
+    unsigned off_sqrt, off_recip, off_slots, slot_bytes, off_bar;
     int n_sqrt;
 };
 
@@ -44,6 +44,8 @@ cudaError_t launch_backup(const StepParams& p, const float* leaf_value, cudaStre
 cudaError_t launch_finalize(const StepParams& p, int32_t* out_visits, double* out_probs, double* out_root_value, cudaStream_t st);
 cudaError_t launch_dirichlet(double* noise, int B, int A, double alpha, unsigned long long seed,
                              unsigned long long tree_base, cudaStream_t st);
+cudaError_t launch_selftest_div(unsigned long long n_per_thread, unsigned long long seed, int max_d, unsigned long long* counts,
+                                cudaStream_t st);
 cudaError_t launch_argmax_first(const double* probs, int B, int A, int32_t* actions, cudaStream_t st);
 
 // network_fp32.cu — batched fp32-exact network entry points (warp per row)

@@ -47,33 +47,55 @@ CM_DEVICE double dinf() { return __longlong_as_double(0x7FF0000000000000LL); }
 // Returns the leaf slot; `parent_e`/`action` identify the edge that reaches it; the parents on the
 // path are written to path[0..plen).
 // ------------------------------------------------------------------------------------------------
-template <int G>
-CM_DEVICE int select_leaf(const Node* __restrict__ nodes, const int32_t* __restrict__ eidx,
-                          const double* __restrict__ root_prior, const double* __restrict__ sqrt_tab,
-                          int A, double c_puct, int root_visits, int* __restrict__ path, int g, bool active,
-                          int& plen_out, int& parent_e_out, int& action_out) {
+// `recip` (RN(1/i) table) selects the table-driven division of ucb_score_tab; nullptr = IEEE division.
+template <int G, bool ONE, bool TAB>
+CM_DEVICE int select_leaf_impl(const Node* __restrict__ nodes, const int32_t* __restrict__ eidx,
+                               const double* __restrict__ root_prior, const double* __restrict__ sqrt_tab,
+                               const double* __restrict__ recip,
+                               int A, double c_puct, int root_visits, int* __restrict__ path, int g, bool active,
+                               int& plen_out, int& parent_e_out, int& action_out) {
     int node = 0, e = 0, n_parent = root_visits, plen = 0, action = 0, parent_e = 0;
     bool walking = active;
     // lanes g >= A hold no child: only the first `span` lanes of the group take part in the butterfly
     int span = 1;
     while (span < A && span < G) span <<= 1;
+    // ONE: A <= G, exactly one child per lane -> no inner loop, per-lane base pointers
+    const bool has_child = g < A;
+    const Node* my_nodes = nodes + 1 + g;
+    const int32_t* my_eidx = eidx + 1 + g;
+    double my_root_prior = 0.0;
+    if (ONE && has_child) my_root_prior = root_prior[g];
     while (__any_sync(0xffffffffu, walking)) {
         double best_s = -dinf();
         // payload: action in the high half, expansion index + 1 in the low half (both < 65536)
         unsigned best_ae = 0xffffffffu;
         int best_n = 0;
-        if (walking) {
-            const int base = 1 + e * A;
-            const double sq = sqrt_tab[n_parent];
-            for (int a = g; a < A; a += G) {
-                const int c = base + a;
-                const Node nd = load_node(nodes + c);
-                const int ce = eidx[c];
-                const double p = (node == 0) ? root_prior[a] : (double)nd.prior;
-                double s = ucb_score(nd.visit, nd.value_sum, p, sq, c_puct);
-                if (s != s) s = (a == 0) ? dinf() : -dinf();
-                if (best_ae == 0xffffffffu || s > best_s) {
-                    best_s = s; best_ae = ((unsigned)a << 16) | (unsigned)(ce + 1); best_n = nd.visit;
+        if constexpr (ONE) {
+            if (walking && has_child) {
+                const int off = e * A;
+                const Node nd = load_node(my_nodes + off);
+                const int ce = my_eidx[off];
+                const double p = (node == 0) ? my_root_prior : (double)nd.prior;
+                double s = TAB ? ucb_score_tab(nd.visit, nd.value_sum, p, sqrt_tab[n_parent], c_puct, recip)
+                               : ucb_score(nd.visit, nd.value_sum, p, sqrt_tab[n_parent], c_puct);
+                if (s != s) s = (g == 0) ? dinf() : -dinf();
+                best_s = s; best_ae = ((unsigned)g << 16) | (unsigned)(ce + 1); best_n = nd.visit;
+            }
+        } else {
+            if (walking) {
+                const int base = 1 + e * A;
+                const double sq = sqrt_tab[n_parent];
+                for (int a = g; a < A; a += G) {
+                    const int c = base + a;
+                    const Node nd = load_node(nodes + c);
+                    const int ce = eidx[c];
+                    const double p = (node == 0) ? root_prior[a] : (double)nd.prior;
+                    double s = TAB ? ucb_score_tab(nd.visit, nd.value_sum, p, sq, c_puct, recip)
+                                   : ucb_score(nd.visit, nd.value_sum, p, sq, c_puct);
+                    if (s != s) s = (a == 0) ? dinf() : -dinf();
+                    if (best_ae == 0xffffffffu || s > best_s) {
+                        best_s = s; best_ae = ((unsigned)a << 16) | (unsigned)(ce + 1); best_n = nd.visit;
+                    }
                 }
             }
         }
@@ -107,11 +129,37 @@ CM_DEVICE int select_leaf(const Node* __restrict__ nodes, const int32_t* __restr
     return node;
 }
 
+template <int G>
+CM_DEVICE int select_leaf(const Node* __restrict__ nodes, const int32_t* __restrict__ eidx,
+                          const double* __restrict__ root_prior, const double* __restrict__ sqrt_tab,
+                          int A, double c_puct, int root_visits, int* __restrict__ path, int g, bool active,
+                          int& plen_out, int& parent_e_out, int& action_out) {
+    if (A <= G)
+        return select_leaf_impl<G, true, false>(nodes, eidx, root_prior, sqrt_tab, nullptr, A, c_puct, root_visits, path, g,
+                                                active, plen_out, parent_e_out, action_out);
+    return select_leaf_impl<G, false, false>(nodes, eidx, root_prior, sqrt_tab, nullptr, A, c_puct, root_visits, path, g,
+                                             active, plen_out, parent_e_out, action_out);
+}
+
+// fused kernel: reciprocal-table division
+template <int G>
+CM_DEVICE int select_leaf_tab(const Node* __restrict__ nodes, const int32_t* __restrict__ eidx,
+                              const double* __restrict__ root_prior, const double* __restrict__ sqrt_tab,
+                              const double* __restrict__ recip, int A, double c_puct, int root_visits,
+                              int* __restrict__ path, int g, bool active, int& plen_out, int& parent_e_out, int& action_out) {
+    if (A <= G)
+        return select_leaf_impl<G, true, true>(nodes, eidx, root_prior, sqrt_tab, recip, A, c_puct, root_visits, path, g, active,
+                                               plen_out, parent_e_out, action_out);
+    return select_leaf_impl<G, false, true>(nodes, eidx, root_prior, sqrt_tab, recip, A, c_puct, root_visits, path, g, active,
+                                            plen_out, parent_e_out, action_out);
+}
+
 // Backup (mcts.py:199-203): every parent on the path gets n += 1, W += v; the root (always
 // path[0]) is backed up a second time, sequentially: W = (W + v) + v.
 template <int G>
 CM_DEVICE void backup_path(Node* __restrict__ nodes, const int* __restrict__ path, int plen, float leaf_value, int g) {
     const double v = (double)leaf_value;
+#pragma unroll 1
     for (int i = g; i < plen; i += G) {
         const int nd = path[i];
         Node r = load_node(nodes + nd);
@@ -280,39 +328,50 @@ struct WarpAcc {
     }
 };
 
+// Wb: lane-blocked layer kernel (FusedPackLayout): chunk (kb, c) of this lane is at
+// Wb + ((kb*R + c)*32 + lane)*4; float f = (k%4)*R + v of a k-block sits in chunk f/4, slot f%4.
 template <int TW, int R>
-CM_DEVICE void warp_dot(const float* __restrict__ W /*[H][H]*/, const float* __restrict__ x /*[H][TW]*/, int H, int lane,
+CM_DEVICE void warp_dot(const float* __restrict__ Wb, const float* __restrict__ x /*[H][TW]*/, int H, int lane,
                         WarpAcc<TW, R>& acc) {
     acc.zero();
-    const int j0 = lane * R;
-    if (j0 >= H) return;
-    const float* wp = W + j0;
-#pragma unroll 4
-    for (int k = 0; k < H; ++k) {
-        float xk[TW], w[R];
-        load_vec<TW>(x + (size_t)k * TW, xk);
-        load_vec<R>(wp + (size_t)k * H, w);
-        if constexpr (R >= 2) {
+    const float* wp = Wb + lane * 4;
+#pragma unroll 2
+    for (int kb = 0; kb < H; kb += 4) {
+        float wq[4 * R];
 #pragma unroll
-            for (int t = 0; t < TW; ++t)
+        for (int c = 0; c < R; ++c) {
+            float t4[4];
+            load_vec<4>(wp + (size_t)((kb >> 2) * R + c) * 128, t4);
 #pragma unroll
-                for (int v = 0; v < R; v += 2)
-                    acc.v[t * (R / 2) + v / 2] = ffma2(xk[t], make_float2(w[v], w[v + 1]), acc.v[t * (R / 2) + v / 2]);
-        } else if constexpr (TW >= 2) {
+            for (int i = 0; i < 4; ++i) wq[c * 4 + i] = t4[i];
+        }
 #pragma unroll
-            for (int t = 0; t < TW; t += 2) acc.v[t / 2] = ffma2(w[0], make_float2(xk[t], xk[t + 1]), acc.v[t / 2]);
-        } else {
-            acc.v[0].x = ffma(xk[0], w[0], acc.v[0].x);
+        for (int kk = 0; kk < 4; ++kk) {
+            float xk[TW];
+            load_vec<TW>(x + (size_t)(kb + kk) * TW, xk);
+            if constexpr (R >= 2) {
+#pragma unroll
+                for (int t = 0; t < TW; ++t)
+#pragma unroll
+                    for (int v = 0; v < R; v += 2)
+                        acc.v[t * (R / 2) + v / 2] =
+                            ffma2(xk[t], make_float2(wq[kk * R + v], wq[kk * R + v + 1]), acc.v[t * (R / 2) + v / 2]);
+            } else if constexpr (TW >= 2) {
+#pragma unroll
+                for (int t = 0; t < TW; t += 2) acc.v[t / 2] = ffma2(wq[kk], make_float2(xk[t], xk[t + 1]), acc.v[t / 2]);
+            } else {
+                acc.v[0].x = ffma(xk[0], wq[kk], acc.v[0].x);
+            }
         }
     }
 }
 
 // one dynamics layer for the warp's TW trees: xout[j][t] = relu(dot + b[j]) + xin[j][t]
 template <int TW, int R>
-CM_DEVICE void warp_layer(const float* __restrict__ K, const float* __restrict__ b, const float* __restrict__ xin,
+CM_DEVICE void warp_layer(const float* __restrict__ Wb, const float* __restrict__ b, const float* __restrict__ xin,
                           float* __restrict__ xout, int H, int lane) {
     WarpAcc<TW, R> acc;
-    warp_dot<TW, R>(K, xin, H, lane, acc);
+    warp_dot<TW, R>(Wb, xin, H, lane, acc);
     const int j0 = lane * R;
     if (j0 >= H) return;
 #pragma unroll
@@ -326,15 +385,22 @@ CM_DEVICE void warp_layer(const float* __restrict__ K, const float* __restrict__
     }
 }
 
-// heads for the warp's TW trees: lane <-> (tree t, output o); out[t*HP + o] = x[:,t] @ Wh[:,o] + bh[o]
+// heads for the warp's TW trees: lane <-> (tree t, output o); out[t*HP + o] = x[:,t] @ Wht[o,:] + bh[o]
+// Wht is transposed (row o, stride HS) so the k loop walks both operands with constant offsets.
 template <int TW>
-CM_DEVICE void warp_heads(const float* __restrict__ Wh /*[H][HP]*/, const float* __restrict__ bh, const float* __restrict__ x,
-                          int H, int HP, int n_out, float* __restrict__ out, int lane) {
+CM_DEVICE void warp_heads(const float* __restrict__ Wht /*[HP][HS]*/, const float* __restrict__ bh, const float* __restrict__ x,
+                          int H, int HS, int HP, int n_out, float* __restrict__ out, int lane) {
     for (int idx = lane; idx < TW * n_out; idx += 32) {
         const int t = idx / n_out, o = idx - t * n_out;
+        const float* xp = x + t;
+        const float* wp = Wht + (size_t)o * HS;
         float acc = 0.0f;
-#pragma unroll 4
-        for (int k = 0; k < H; ++k) acc = ffma(x[(size_t)k * TW + t], Wh[(size_t)k * HP + o], acc);
+#pragma unroll 1
+        for (int kb = 0; kb < H; kb += 8) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+                if (kk < 4 || kb + kk < H) acc = ffma(xp[(size_t)(kb + kk) * TW], wp[kb + kk], acc);
+        }
         out[t * HP + o] = fadd(acc, bh[o]);
     }
 }

@@ -45,12 +45,17 @@ CM_DEVICE void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes
 
 // GS = lanes per tree in the select / expand / backup phases (TW = 32/GS trees per warp);
 // R = neurons per lane in the warp-cooperative network tile (32*R >= H).
+// e / s of the softmax; a saturated softmax produces exact zeros, which would send the IEEE
+// division down its slow special-case path: 0 / s == 0 exactly for the finite s >= 1 of a softmax.
+CM_DEVICE float prior_div(float e, float s) { return (e == 0.0f && s >= 1.0f) ? 0.0f : __fdiv_rn(e, s); }
+
 template <int GS, int R>
 __global__ void __launch_bounds__(512, 1) search_fused_kernel(const FusedParams p) {
     constexpr int TW = 32 / GS;
     extern __shared__ __align__(128) unsigned char smem[];
     float* w_s = reinterpret_cast<float*>(smem);
     double* sq_s = reinterpret_cast<double*>(smem + p.off_sqrt);
+    double* rc_s = reinterpret_cast<double*>(smem + p.off_recip);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
 
     const int tid = threadIdx.x;
@@ -58,7 +63,7 @@ __global__ void __launch_bounds__(512, 1) search_fused_kernel(const FusedParams 
     const int g = lane & (GS - 1);   // lane within the tree's sub-group
     const int tw = lane / GS;        // tree within the warp
     const int TPB = (blockDim.x >> 5) * TW;
-    const int H = p.pk.H, L = p.pk.L, HP = p.pk.HP, A = p.tv.A, A_net = p.A_net;
+    const int H = p.pk.H, L = p.pk.L, HP = p.pk.HP, HS = p.pk.HS, A = p.tv.A, A_net = p.A_net;
 
     // ---- stage parameters (TMA bulk) + sqrt table -------------------------------------------
     if (tid == 0) mbar_init(bar, 1);
@@ -72,7 +77,10 @@ __global__ void __launch_bounds__(512, 1) search_fused_kernel(const FusedParams 
             tma_bulk_g2s(smem + o, reinterpret_cast<const unsigned char*>(p.pack) + o, n, bar);
         }
     }
-    for (int i = tid; i < p.n_sqrt; i += blockDim.x) sq_s[i] = __dsqrt_rn((double)i);
+    for (int i = tid; i < p.n_sqrt; i += blockDim.x) {
+        sq_s[i] = __dsqrt_rn((double)i);
+        rc_s[i] = __ddiv_rn(1.0, (double)i);  // RN(1/i); entry 0 is never used
+    }
     mbar_wait(bar, 0);
     __syncthreads();
 
@@ -114,7 +122,7 @@ __global__ void __launch_bounds__(512, 1) search_fused_kernel(const FusedParams 
             }
         }
         __syncwarp();
-        warp_heads<TW>(wh_s, bh_s, x0, H, HP, A_net, lg_w, lane);
+        warp_heads<TW>(wh_s, bh_s, x0, H, HS, HP, A_net, lg_w, lane);
         if (active && p.noise_mode == 2 && g == 0)
             dirichlet_row(rprior, A, p.alpha, p.seed, p.tree_base + (unsigned long long)t);
         __syncwarp();
@@ -122,7 +130,7 @@ __global__ void __launch_bounds__(512, 1) search_fused_kernel(const FusedParams 
             const float ssum = softmax_prepare<GS>(lg, eb, A_net, g, active);
             if (active) {
                 for (int a = g; a < A; a += GS) {
-                    const float p32 = __fdiv_rn(eb[a], ssum);
+                    const float p32 = prior_div(eb[a], ssum);
                     double pd = (double)p32;
                     if (p.noise_mode == 1)
                         pd = __dadd_rn(__dmul_rn(pd, p.one_minus_frac), __dmul_rn(p.noise[tt * A + a], p.frac));
@@ -145,8 +153,8 @@ __global__ void __launch_bounds__(512, 1) search_fused_kernel(const FusedParams 
         long long depth = 0;
         for (int s = 0; s < p.S; ++s) {
             int plen, parent_e, action;
-            const int leaf = select_leaf<GS>(nodes, eidx, rprior, sq_s, A, p.c_puct, 2 * s, path, g, active, plen,
-                                             parent_e, action);
+            const int leaf = select_leaf_tab<GS>(nodes, eidx, rprior, sq_s, rc_s, A, p.c_puct, 2 * s, path, g, active, plen,
+                                                 parent_e, action);
             __syncwarp();
             const int k = s + 1;  // expansion index of the leaf
             // x0[j][t'] = hidden_{t'}[parent_e][j] + Emb[action_{t'}][j] for the warp's TW trees
@@ -181,7 +189,7 @@ __global__ void __launch_bounds__(512, 1) search_fused_kernel(const FusedParams 
             float* cur = x0;
             float* nxt = x1;
             for (int l = 0; l < L; ++l) {
-                warp_layer<TW, R>(w_s + p.pk.layer_k(l), w_s + p.pk.layer_b(l), cur, nxt, H, lane);
+                warp_layer<TW, R>(w_s + p.pk.layer_w(l), w_s + p.pk.layer_b(l), cur, nxt, H, lane);
                 __syncwarp();
                 float* tmp = cur; cur = nxt; nxt = tmp;
             }
@@ -199,14 +207,14 @@ __global__ void __launch_bounds__(512, 1) search_fused_kernel(const FusedParams 
                     }
                 }
             }
-            warp_heads<TW>(wh_s, bh_s, cur, H, HP, A_net + 1, lg_w, lane);
+            warp_heads<TW>(wh_s, bh_s, cur, H, HS, HP, A_net + 1, lg_w, lane);
             __syncwarp();
             const float ssum = softmax_prepare<GS>(lg, eb, A_net, g, active);
             if (active) {
                 const float value = lg[A_net];
                 const int cbase = 1 + k * A;
                 for (int a = g; a < A; a += GS) {
-                    store_node(nodes + cbase + a, 0.0, 0, __fdiv_rn(eb[a], ssum));
+                    store_node(nodes + cbase + a, 0.0, 0, prior_div(eb[a], ssum));
                     eidx[cbase + a] = -1;
                 }
                 if (g == 0) { eidx[leaf] = k; exp_node[k] = leaf; }

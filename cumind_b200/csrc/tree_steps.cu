@@ -189,6 +189,51 @@ __global__ void argmax_first_kernel(const double* __restrict__ probs, int B, int
     actions[t] = best;
 }
 
+// Self-test of div_small (the table-driven division of the fused select): random and structured
+// numerators against the IEEE division, bitwise.  counts[0] = mismatches, counts[1] = cases.
+__global__ void selftest_div_kernel(unsigned long long n_per_thread, unsigned long long seed, int max_d,
+                                    unsigned long long* __restrict__ counts) {
+    Philox rng;
+    rng.init(seed, (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x);
+    unsigned long long bad = 0, total = 0;
+    for (unsigned long long i = 0; i < n_per_thread; ++i) {
+        const unsigned r0 = rng.next(), r1 = rng.next(), r2 = rng.next(), r3 = rng.next();
+        const int d = 1 + (int)(r0 % (unsigned)max_d);
+        const double dd = (double)d;
+        const double recip = __ddiv_rn(1.0, dd);
+        double a;
+        const unsigned mode = r3 & 7u;
+        const unsigned long long mant = (((unsigned long long)r1 << 32) | r2) & 0x000FFFFFFFFFFFFFULL;
+        if (mode < 3) {            // random significand, moderate exponent (the values a search produces)
+            const long long ex = 1023 + (long long)((r3 >> 3) % 41) - 20;
+            a = __longlong_as_double(((unsigned long long)(r3 >> 31) << 63) | ((unsigned long long)ex << 52) | mant);
+        } else if (mode < 5) {     // exact multiples of d and their neighbours (ties / near-ties of the quotient)
+            const double q = __longlong_as_double((1023ULL << 52) | mant);
+            const double m = __dmul_rn(q, dd);
+            const long long step = (long long)((r3 >> 3) % 5) - 2;
+            a = __longlong_as_double(__double_as_longlong(m) + step);
+        } else if (mode < 7) {     // any exponent, including subnormals, huge values, inf and NaN
+            a = __longlong_as_double(((unsigned long long)r1 << 32) | r2);
+        } else {                   // small integers and zeros
+            a = (double)((int)(r1 % 4001u) - 2000);
+            if ((r3 >> 3) & 1) a = -0.0;
+        }
+        const double want = __ddiv_rn(a, dd);
+        const double got = div_small(a, dd, recip);
+        const bool same = (__double_as_longlong(want) == __double_as_longlong(got)) || (want != want && got != got);
+        if (!same) ++bad;
+        ++total;
+    }
+    atomicAdd(counts, bad);
+    atomicAdd(counts + 1, total);
+}
+
+cudaError_t launch_selftest_div(unsigned long long n_per_thread, unsigned long long seed, int max_d, unsigned long long* counts,
+                                cudaStream_t st) {
+    selftest_div_kernel<<<148 * 4, 256, 0, st>>>(n_per_thread, seed, max_d, counts);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 static inline int warp_grid(int B) { return (B + kWarpsPerBlock - 1) / kWarpsPerBlock; }
 

@@ -220,6 +220,13 @@ int cumind_finalize(cumind_tree* tree, const cumind_search_cfg* cfg, int32_t* d_
 int cumind_dirichlet(double* d_noise, int32_t B, int32_t A, double alpha, uint64_t seed,
                      uint64_t tree_index_base, void* stream);
 
+/* Diagnostic: checks the table-driven small-divisor division used by the fused select kernel
+ * (a/d from RN(1/d) with two FMA residual corrections) against the IEEE division on the device,
+ * bitwise, over 148*4*256*n_per_thread random and structured numerators and divisors 1..max_divisor.
+ * d_counts2 is a zero-initialised device uint64[2]: {mismatches, cases}. */
+int cumind_selftest_division(uint64_t n_per_thread, uint64_t seed, int32_t max_divisor,
+                             uint64_t* d_counts2, void* stream);
+
 /* Counters: kernels launched by this library since load (bench.py reports the delta). */
 uint64_t cumind_launch_count(void);
 

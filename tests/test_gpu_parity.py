@@ -199,6 +199,24 @@ def test_search_is_independent_of_batch_split():
     assert np.array_equal(full, np.concatenate([lo_half, hi_half]))
 
 
+def test_small_divisor_division_is_ieee():
+    """The fused select divides by small integers through RN(1/d) + two FMA residual corrections; it must
+    equal the IEEE division bit for bit (random, near-tie, subnormal, huge, inf/NaN, signed-zero numerators)."""
+    import ctypes as C
+
+    import torch
+
+    from cumind_b200 import _native
+
+    lib = _native.load()
+    for seed, max_d in ((1, 202), (2, 4097), (3, 65535)):
+        counts = torch.zeros(2, dtype=torch.int64, device="cuda")
+        _native.check(lib.cumind_selftest_division(2000, seed, max_d, C.c_void_p(counts.data_ptr()), None))
+        bad, total = (int(v) for v in counts.cpu())
+        assert total == 148 * 4 * 256 * 2000
+        assert bad == 0, f"{bad} of {total} quotients differ from the IEEE division (max divisor {max_d})"
+
+
 def test_philox_dirichlet_statistics():
     import ctypes as C
 
