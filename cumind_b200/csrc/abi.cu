@@ -21,12 +21,16 @@ struct cumind_net {
     float* d_blob;
     float* d_pack;
     float* d_fpack;       // FusedPackLayout copy for the fused search kernel
+    unsigned char* d_tcpack;  // TcPackLayout (bf16 tiles) for the tensor-core kernels, or null
+    TcPackLayout tpk;
+    bool tc_ok;
     BlobLayout lo;
     PackLayout pk;
     FusedPackLayout fpk;
     float* d_work;        // activation workspace of the image encoder (lazily sized, grow-only)
     size_t work_bytes;
     std::vector<float> h_pack, h_fpack;
+    std::vector<unsigned char> h_tcpack;
 };
 
 struct cumind_tree {
@@ -119,6 +123,46 @@ static void build_fused_pack(const cumind_net* n, const float* blob, std::vector
     fp[pk.heads_b + A + 1] = blob[lo.rew_b];
 }
 
+// fp32 -> bf16, round to nearest even (NaN kept quiet)
+static inline uint16_t to_bf16(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    const uint32_t lsb = (u >> 16) & 1u;
+    u += 0x7fffu + lsb;
+    return (uint16_t)(u >> 16);
+}
+
+// canonical blob -> TcPackLayout
+static void build_tc_pack(const cumind_net* n, const float* blob, std::vector<unsigned char>& tp) {
+    const TcPackLayout& pk = n->tpk;
+    const BlobLayout& lo = n->lo;
+    const int H = pk.H, L = pk.L, A = pk.A, NP = pk.NP;
+    tp.assign(pk.total_bytes, 0);
+    for (int l = 0; l < L; ++l) {
+        const float* K = blob + lo.dyn + (size_t)l * ((size_t)H * H + H);
+        unsigned char* tile = tp.data() + pk.layer_off + (size_t)l * H * H * 2;
+        for (int k = 0; k < H; ++k)
+            for (int j = 0; j < H; ++j) {
+                const uint16_t v = to_bf16(K[(size_t)k * H + j]);
+                memcpy(tile + tc_tile_offset_host(j, k, H), &v, 2);
+            }
+        memcpy(tp.data() + pk.bias_off + (size_t)l * H * 4, K + (size_t)H * H, (size_t)H * 4);
+    }
+    unsigned char* ht = tp.data() + pk.heads_off;
+    float* bh = reinterpret_cast<float*>(tp.data() + pk.bh_off);
+    for (int k = 0; k < H; ++k) {
+        for (int a = 0; a < A; ++a) { const uint16_t v = to_bf16(blob[lo.pol_k + (size_t)k * A + a]); memcpy(ht + tc_tile_offset_host(a, k, NP), &v, 2); }
+        const uint16_t vv = to_bf16(blob[lo.val_k + k]), vr = to_bf16(blob[lo.rew_k + k]);
+        memcpy(ht + tc_tile_offset_host(A, k, NP), &vv, 2);
+        memcpy(ht + tc_tile_offset_host(A + 1, k, NP), &vr, 2);
+    }
+    for (int a = 0; a < A; ++a) bh[a] = blob[lo.pol_b + a];
+    bh[A] = blob[lo.val_b];
+    bh[A + 1] = blob[lo.rew_b];
+    memcpy(tp.data() + pk.emb_off, blob + lo.emb, (size_t)A * H * 4);
+}
+
 extern "C" int cumind_net_create(const cumind_net_desc* desc, const float* h_params, size_t n_params, cumind_net** out) {
     if (!out) return fail("cumind_net_create: out is NULL");
     *out = nullptr;
@@ -137,13 +181,17 @@ extern "C" int cumind_net_create(const cumind_net_desc* desc, const float* h_par
     n->fpk = make_fused_pack_layout(desc->hidden_dim, desc->num_blocks, desc->action_space_size);
     n->n_params = n_params;
     n->d_blob = n->d_pack = n->d_fpack = n->d_work = nullptr;
+    n->d_tcpack = nullptr;
+    n->tc_ok = tc_supported(desc->hidden_dim, desc->num_blocks, desc->action_space_size);
+    n->tpk = make_tc_pack_layout(desc->hidden_dim, desc->num_blocks, desc->action_space_size);
     n->work_bytes = 0;
     cudaError_t e;
     if ((e = cudaGetDevice(&n->device)) != cudaSuccess ||
         (e = cudaDeviceGetAttribute(&n->sm_count, cudaDevAttrMultiProcessorCount, n->device)) != cudaSuccess ||
         (e = cudaMalloc(&n->d_blob, sizeof(float) * lo.total)) != cudaSuccess ||
         (e = cudaMalloc(&n->d_pack, sizeof(float) * n->pk.total)) != cudaSuccess ||
-        (e = cudaMalloc(&n->d_fpack, sizeof(float) * n->fpk.total)) != cudaSuccess) {
+        (e = cudaMalloc(&n->d_fpack, sizeof(float) * n->fpk.total)) != cudaSuccess ||
+        (n->tc_ok && (e = cudaMalloc(&n->d_tcpack, n->tpk.total_bytes)) != cudaSuccess)) {
         cudaFree(n->d_blob); cudaFree(n->d_pack); cudaFree(n->d_fpack);
         delete n;
         return fail_cuda("cumind_net_create", e);
@@ -161,6 +209,10 @@ extern "C" int cumind_net_update_params(cumind_net* n, const float* h_params, si
     cudaStream_t st = (cudaStream_t)stream;
     build_pack(n, h_params, n->h_pack);
     build_fused_pack(n, h_params, n->h_fpack);
+    if (n->tc_ok) {
+        build_tc_pack(n, h_params, n->h_tcpack);
+        CM_CUDA(cudaMemcpyAsync(n->d_tcpack, n->h_tcpack.data(), n->tpk.total_bytes, cudaMemcpyHostToDevice, st));
+    }
     CM_CUDA(cudaMemcpyAsync(n->d_fpack, n->h_fpack.data(), sizeof(float) * n->fpk.total, cudaMemcpyHostToDevice, st));
     CM_CUDA(cudaMemcpyAsync(n->d_blob, h_params, sizeof(float) * n_params, cudaMemcpyHostToDevice, st));
     CM_CUDA(cudaMemcpyAsync(n->d_pack, n->h_pack.data(), sizeof(float) * n->pk.total, cudaMemcpyHostToDevice, st));
@@ -173,6 +225,7 @@ extern "C" int cumind_net_destroy(cumind_net* n) {
     cudaFree(n->d_blob);
     cudaFree(n->d_pack);
     cudaFree(n->d_fpack);
+    cudaFree(n->d_tcpack);
     cudaFree(n->d_work);
     delete n;
     return 0;
@@ -181,17 +234,26 @@ extern "C" int cumind_net_destroy(cumind_net* n) {
 // ------------------------------------------------------------------------------------------------
 // network entry points
 // ------------------------------------------------------------------------------------------------
-static int check_mode(int net_mode) {
+static int check_mode(const cumind_net* n, int net_mode, bool tc_allowed) {
     if (net_mode == CUMIND_NET_FP32_EXACT) return 0;
-    return fail("net_mode not available in this build (only CUMIND_NET_FP32_EXACT)");
+    if (net_mode == CUMIND_NET_BF16_TC) {
+        if (!tc_allowed) return fail("CUMIND_NET_BF16_TC is not available for this entry point");
+        if (!n->tc_ok) return fail("CUMIND_NET_BF16_TC needs hidden_dim in {16,32,64,128} and action_space_size <= 14");
+        return 0;
+    }
+    return fail("unknown net_mode");
 }
 
 extern "C" int cumind_prediction(const cumind_net* n, const float* d_hidden, int32_t B, float* d_logits, float* d_value,
                                  int32_t net_mode, void* stream) {
     if (!n || !d_hidden || B < 0) return fail("cumind_prediction: bad argument");
-    if (check_mode(net_mode)) return 1;
+    if (check_mode(n, net_mode, true)) return 1;
     if (B == 0) return 0;
-    CM_CUDA(launch_prediction(view_of(n), d_hidden, B, d_logits, d_value, (cudaStream_t)stream));
+    if (net_mode == CUMIND_NET_BF16_TC)
+        CM_CUDA(launch_recurrent_tc(n->d_tcpack, n->tpk, n->sm_count, d_hidden, nullptr, B, nullptr, nullptr, d_logits, d_value, 0,
+                                    (cudaStream_t)stream));
+    else
+        CM_CUDA(launch_prediction(view_of(n), d_hidden, B, d_logits, d_value, (cudaStream_t)stream));
     g_launches += 1;
     return 0;
 }
@@ -200,7 +262,7 @@ extern "C" int cumind_initial_inference(const cumind_net* cn, const float* d_obs
                                         float* d_value, int32_t net_mode, void* stream) {
     cumind_net* n = const_cast<cumind_net*>(cn);
     if (!n || !d_obs || !d_hidden || B < 0) return fail("cumind_initial_inference: bad argument");
-    if (check_mode(net_mode)) return 1;
+    if (check_mode(n, net_mode, true)) return 1;
     if (B == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const NetView nv = view_of(n);
@@ -223,7 +285,10 @@ extern "C" int cumind_initial_inference(const cumind_net* cn, const float* d_obs
         g_launches += (unsigned long long)((B + chunk - 1) / chunk) * (2 + 2 * n->desc.num_blocks);
     }
     if (d_logits || d_value) {
-        CM_CUDA(launch_prediction(nv, d_hidden, B, d_logits, d_value, st));
+        if (net_mode == CUMIND_NET_BF16_TC)
+            CM_CUDA(launch_recurrent_tc(n->d_tcpack, n->tpk, n->sm_count, d_hidden, nullptr, B, nullptr, nullptr, d_logits, d_value, 0, st));
+        else
+            CM_CUDA(launch_prediction(nv, d_hidden, B, d_logits, d_value, st));
         g_launches += 1;
     }
     return 0;
@@ -233,9 +298,13 @@ extern "C" int cumind_recurrent_inference(const cumind_net* n, const float* d_hi
                                           float* d_next, float* d_reward, float* d_logits, float* d_value, int32_t net_mode,
                                           void* stream) {
     if (!n || !d_hidden || !d_action || B < 0) return fail("cumind_recurrent_inference: bad argument");
-    if (check_mode(net_mode)) return 1;
+    if (check_mode(n, net_mode, true)) return 1;
     if (B == 0) return 0;
-    CM_CUDA(launch_recurrent(view_of(n), d_hidden, d_action, B, d_next, d_reward, d_logits, d_value, (cudaStream_t)stream));
+    if (net_mode == CUMIND_NET_BF16_TC)
+        CM_CUDA(launch_recurrent_tc(n->d_tcpack, n->tpk, n->sm_count, d_hidden, d_action, B, d_next, d_reward, d_logits, d_value, 1,
+                                    (cudaStream_t)stream));
+    else
+        CM_CUDA(launch_recurrent(view_of(n), d_hidden, d_action, B, d_next, d_reward, d_logits, d_value, (cudaStream_t)stream));
     g_launches += 1;
     return 0;
 }
@@ -343,7 +412,7 @@ static int check_search(const char* fn, const cumind_tree* t, const cumind_net* 
     if (c->noise_mode < 0 || c->noise_mode > 2) return fail("noise_mode must be 0, 1 or 2");
     if (c->noise_mode == 1 && !d_noise) return fail("noise_mode 1 needs d_noise");
     if (c->tree_mode != CUMIND_TREE_REFERENCE) return fail("tree_mode not available in this build");
-    if (c->net_mode != CUMIND_NET_FP32_EXACT) return fail("net_mode not available in this build (only CUMIND_NET_FP32_EXACT)");
+    if (check_mode(n, c->net_mode, true)) return 1;
     return 0;
 }
 
@@ -447,7 +516,10 @@ extern "C" int cumind_search_stepwise(cumind_tree* t, const cumind_net* n, const
     CM_CUDA(launch_init_root(p, d_root_hidden, d_noise, st));
     for (int s = 0; s < c->num_simulations; ++s) {
         CM_CUDA(launch_select(p, st));
-        CM_CUDA(launch_expand(p, t->leaf_value, st));
+        if (c->net_mode == CUMIND_NET_BF16_TC)
+            CM_CUDA(launch_expand_tc(n->d_tcpack, n->tpk, n->sm_count, t->tv, t->leaf_value, st));
+        else
+            CM_CUDA(launch_expand(p, t->leaf_value, st));
         CM_CUDA(launch_backup(p, t->leaf_value, st));
     }
     CM_CUDA(launch_finalize(p, d_out_visits, d_out_probs, d_out_root_value, st));
@@ -462,7 +534,8 @@ extern "C" int cumind_search(cumind_tree* t, const cumind_net* n, const float* d
     if (!d_root_hidden || !d_out_visits || !d_out_probs) return fail("cumind_search: NULL device pointer");
     FusedPlan pl;
     std::string why;
-    if (plan_fused(t, n, c, pl, why) != 0)
+    // the fused kernel is the fp32-exact path; the tensor-core mode runs one launch per phase
+    if (c->net_mode != CUMIND_NET_FP32_EXACT || plan_fused(t, n, c, pl, why) != 0)
         return cumind_search_stepwise(t, n, d_root_hidden, c, d_noise, d_out_visits, d_out_probs, d_out_root_value, stream);
     pl.p.root_hidden = d_root_hidden;
     pl.p.noise = d_noise;

@@ -134,6 +134,29 @@ inline FusedPackLayout make_fused_pack_layout(int H, int L, int A) {
     return p;
 }
 
+// Parameters for the tensor-core (bf16) network kernel: bf16 weight tiles in the UMMA K-major
+// core-matrix layout ([k/8][n/8][n%8][k%8], one tile per layer with rows n = output neuron, then the
+// head tile with NP = 16 rows: policy 0..A-1, value A, reward A+1, zero padded), followed by the
+// fp32 biases and the fp32 embedding.  Byte offsets, every section 128-byte aligned.
+struct TcPackLayout {
+    int H, L, A, NP;
+    size_t layer_off, heads_off, bias_off, bh_off, emb_off, total_bytes;
+};
+
+inline TcPackLayout make_tc_pack_layout(int H, int L, int A) {
+    TcPackLayout p;
+    p.H = H; p.L = L; p.A = A; p.NP = 16;
+    auto al = [](size_t x) { return (x + 127) & ~(size_t)127; };
+    size_t o = 0;
+    p.layer_off = o; o = al(o + (size_t)L * H * H * 2);
+    p.heads_off = o; o = al(o + (size_t)p.NP * H * 2);
+    p.bias_off = o;  o = al(o + (size_t)L * H * 4);
+    p.bh_off = o;    o = al(o + (size_t)p.NP * 4);
+    p.emb_off = o;   o = al(o + (size_t)A * H * 4);
+    p.total_bytes = o;
+    return p;
+}
+
 // ------------------------------------------------------------------------------------------------
 // tree storage
 // ------------------------------------------------------------------------------------------------

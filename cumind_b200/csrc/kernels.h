@@ -55,6 +55,15 @@ cudaError_t launch_recurrent(const NetView& nv, const float* hidden, const int32
 cudaError_t launch_prediction(const NetView& nv, const float* hidden, int B, float* logits, float* value, cudaStream_t st);
 cudaError_t launch_softmax(const float* logits, int B, int A, float* probs, cudaStream_t st);
 
+// network_tc.cu — bf16 tensor-core (tcgen05) dynamics + prediction, 128-row tiles
+bool tc_supported(int H, int L, int A);
+size_t tc_tile_offset_host(int r, int k, int rows);
+cudaError_t launch_recurrent_tc(const unsigned char* pack, const TcPackLayout& pk, int sm_count, const float* hidden,
+                                const int32_t* action, int B, float* next, float* reward, float* logits, float* value,
+                                int with_dynamics, cudaStream_t st);
+cudaError_t launch_expand_tc(const unsigned char* pack, const TcPackLayout& pk, int sm_count, const TreeView& tv, float* leaf_value,
+                             cudaStream_t st);
+
 // conv_fp32.cu — image encoder, fp32-exact (ConvEncoder, network.py:111-147)
 size_t conv_encoder_work_bytes(const cumind_net_desc& d, int chunk);
 cudaError_t launch_conv_encoder(const NetView& nv, const float* obs, int B, float* hidden, float* work, int chunk,

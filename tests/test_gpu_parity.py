@@ -237,3 +237,70 @@ def test_philox_dirichlet_statistics():
     out2 = torch.empty((1000, A), dtype=torch.float64, device="cuda")
     _native.check(lib.cumind_dirichlet(C.c_void_p(out2.data_ptr()), 1000, A, alpha, 7, 5000, None))
     assert np.array_equal(out2.cpu().numpy(), x[5000:6000])
+
+
+# ---- bf16 tensor-core mode (tcgen05): tolerance rtol 2e-2 against the fp32-exact path --------------
+def _close(a, b, scale, rtol=2e-2):
+    """|a-b| <= rtol*(|b| + scale); `scale` = typical magnitude of that output over a large batch (a single
+    near-zero element has no meaningful relative error of its own)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return bool(np.all(np.abs(a - b) <= rtol * (np.abs(b) + scale)))
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 2), (4, 64, 2), (3, 16, 3), (2, 128, 2), (6, 32, 1)], ids=lambda s: f"A{s[0]}H{s[1]}L{s[2]}")
+def test_tensor_core_recurrent_inference_within_tolerance(shape):
+    from cumind_b200 import _native
+    from cumind_b200 import params as P
+    from cumind_b200.network import CuMindNetwork
+    from oracle import network_np as nn
+
+    A, H, L = shape
+    tree = nn.random_params((4,), A, H, L, 32, 77 + H, bias_scale=0.1)
+    blob = nn.flatten_params(tree, (4,))
+    exact = _network((4,), A, H, L, 32, blob)
+    tc = CuMindNetwork((4,), A, H, L, 32, params=P.unflatten(blob, (4,), A, H, L, 32), net_mode=_native.NET_BF16_TC)
+    rng = np.random.default_rng(H)
+    scales = None
+    for B in (5000, 1, 127, 128, 300):
+        h = rng.standard_normal((B, H)).astype(np.float32)
+        act = rng.integers(0, A, size=B).astype(np.int32)
+        want = [t.cpu().numpy() for t in exact.recurrent_inference(h, act)]
+        got = [t.cpu().numpy() for t in tc.recurrent_inference(h, act)]
+        lg, v = tc.prediction_network(h)
+        lw, vw = exact.prediction_network(h)
+        if scales is None:
+            scales = [float(np.sqrt(np.mean(np.square(w)))) for w in want] + [float(np.sqrt(np.mean(np.square(t.cpu().numpy())))) for t in (lw, vw)]
+        for name, g, w, sc in zip(("next", "reward", "logits", "value"), got, want, scales):
+            assert g.shape == w.shape and _close(g, w, sc), (name, B, float(np.abs(g - w).max()), sc)
+        assert _close(lg.cpu().numpy(), lw.cpu().numpy(), scales[4]) and _close(v.cpu().numpy(), vw.cpu().numpy(), scales[5])
+    # not silently the fp32 path: bf16 rounding must be visible
+    assert not np.array_equal(got[0], want[0])
+
+
+def test_tensor_core_search_agrees_with_exact_search():
+    """Config-3-like tree shape (A=4, H=64, S=50) in bf16 tensor-core mode: root policies and values stay
+    close to the fp32-exact search (trees may differ in individual visit counts: bf16 is not bit-pinned)."""
+    from cumind_b200 import _native
+    from cumind_b200 import params as P
+    from cumind_b200.mcts import MCTS
+    from cumind_b200.network import CuMindNetwork
+    from oracle import network_np as nn
+
+    A, H, S, B = 4, 64, 50, 1024
+    blob = nn.flatten_params(nn.random_params((4,), A, H, 2, 32, 5), (4,))
+    exact = _network((4,), A, H, 2, 32, blob)
+    tc = CuMindNetwork((4,), A, H, 2, 32, params=P.unflatten(blob, (4,), A, H, 2, 32), net_mode=_native.NET_BF16_TC)
+    rng = np.random.default_rng(3)
+    h = (0.3 * rng.standard_normal((B, H))).astype(np.float32)
+    noise = rng.dirichlet([0.3] * A, size=B)
+    m_exact, m_tc = MCTS(exact, _Cfg(S, A)), MCTS(tc, _Cfg(S, A))
+    p_exact, v_exact = m_exact.search_batch(h, noise=noise)
+    p_tc, v_tc = m_tc.search_batch(h, noise=noise)
+    assert np.all(v_tc.sum(axis=1) == S - A) and np.allclose(p_tc.sum(axis=1), 1.0)
+    assert np.all(m_tc.dump_trees()["visit"][:, 0] == 2 * S)
+    same_action = np.mean(np.argmax(p_tc, axis=1) == np.argmax(p_exact, axis=1))
+    assert same_action >= 0.9, same_action
+    assert np.mean(np.abs(p_tc - p_exact)) <= 0.03
+    rv_e, rv_t = m_exact.last_root_value.cpu().numpy(), m_tc.last_root_value.cpu().numpy()
+    rel = np.abs(rv_t - rv_e) / np.maximum(np.abs(rv_e), 1e-3)
+    assert np.median(rel) <= 2e-2, float(np.median(rel))
