@@ -1,6 +1,7 @@
 // abi.cu — the C ABI of include/cumind_b200.h: handles, validation, kernel selection.
 #include <atomic>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <string>
@@ -24,13 +25,16 @@ struct cumind_net {
     unsigned char* d_tcpack;  // TcPackLayout (bf16 tiles) for the tensor-core kernels, or null
     TcPackLayout tpk;
     bool tc_ok;
+    unsigned char* d_cpack;   // ConvTcPackLayout (bf16 conv tiles) or null
+    ConvTcPackLayout cpk;
+    bool conv_tc_ok;
     BlobLayout lo;
     PackLayout pk;
     FusedPackLayout fpk;
     float* d_work;        // activation workspace of the image encoder (lazily sized, grow-only)
     size_t work_bytes;
     std::vector<float> h_pack, h_fpack;
-    std::vector<unsigned char> h_tcpack;
+    std::vector<unsigned char> h_tcpack, h_cpack;
 };
 
 struct cumind_tree {
@@ -163,6 +167,45 @@ static void build_tc_pack(const cumind_net* n, const float* blob, std::vector<un
     memcpy(tp.data() + pk.emb_off, blob + lo.emb, (size_t)A * H * 4);
 }
 
+// canonical blob -> ConvTcPackLayout (bias + inference BatchNorm folded into gain / shift)
+static void build_conv_tc_pack(const cumind_net* n, const float* blob, std::vector<unsigned char>& cp) {
+    const ConvTcPackLayout& pk = n->cpk;
+    const int C = n->desc.obs_shape[2], Cc = n->desc.conv_channels, L = n->desc.num_blocks;
+    cp.assign(pk.total_bytes, 0);
+    const float* p = blob + n->lo.enc;
+    auto emit = [&](int i, const float* K, const float* bias, const float* bn, int cin) {
+        unsigned char* tile = cp.data() + pk.off[i];
+        for (int k = 0; k < 9 * cin; ++k)
+            for (int co = 0; co < Cc; ++co) {
+                const uint16_t v = to_bf16(K[(size_t)k * Cc + co]);
+                memcpy(tile + tc_tile_offset_host(co, k, Cc), &v, 2);
+            }
+        float* gain = reinterpret_cast<float*>(tile + pk.gain_off[i]);
+        float* shift = gain + Cc;
+        for (int co = 0; co < Cc; ++co) {
+            if (bn) {
+                const float g = bn[co] / sqrtf(bn[3 * Cc + co] + 1e-5f);
+                gain[co] = g;
+                shift[co] = (bias[co] - bn[2 * Cc + co]) * g + bn[Cc + co];
+            } else {
+                gain[co] = 1.0f;
+                shift[co] = bias[co];
+            }
+        }
+    };
+    emit(0, p, p + (size_t)9 * C * Cc, nullptr, C);
+    p += (size_t)9 * C * Cc + Cc;
+    for (int l = 0; l < L; ++l) {
+        const float* k1 = p;           const float* b1 = k1 + (size_t)9 * Cc * Cc;
+        const float* bn1 = b1 + Cc;    const float* k2 = bn1 + 4 * Cc;
+        const float* b2 = k2 + (size_t)9 * Cc * Cc;
+        const float* bn2 = b2 + Cc;
+        emit(1 + 2 * l, k1, b1, bn1, Cc);
+        emit(2 + 2 * l, k2, b2, bn2, Cc);
+        p = bn2 + 4 * Cc;
+    }
+}
+
 extern "C" int cumind_net_create(const cumind_net_desc* desc, const float* h_params, size_t n_params, cumind_net** out) {
     if (!out) return fail("cumind_net_create: out is NULL");
     *out = nullptr;
@@ -182,6 +225,9 @@ extern "C" int cumind_net_create(const cumind_net_desc* desc, const float* h_par
     n->n_params = n_params;
     n->d_blob = n->d_pack = n->d_fpack = n->d_work = nullptr;
     n->d_tcpack = nullptr;
+    n->d_cpack = nullptr;
+    n->conv_tc_ok = conv_tc_supported(*desc) && desc->num_blocks <= 8;
+    if (n->conv_tc_ok) n->cpk = make_conv_tc_pack_layout(*desc);
     n->tc_ok = tc_supported(desc->hidden_dim, desc->num_blocks, desc->action_space_size);
     n->tpk = make_tc_pack_layout(desc->hidden_dim, desc->num_blocks, desc->action_space_size);
     n->work_bytes = 0;
@@ -191,7 +237,8 @@ extern "C" int cumind_net_create(const cumind_net_desc* desc, const float* h_par
         (e = cudaMalloc(&n->d_blob, sizeof(float) * lo.total)) != cudaSuccess ||
         (e = cudaMalloc(&n->d_pack, sizeof(float) * n->pk.total)) != cudaSuccess ||
         (e = cudaMalloc(&n->d_fpack, sizeof(float) * n->fpk.total)) != cudaSuccess ||
-        (n->tc_ok && (e = cudaMalloc(&n->d_tcpack, n->tpk.total_bytes)) != cudaSuccess)) {
+        (n->tc_ok && (e = cudaMalloc(&n->d_tcpack, n->tpk.total_bytes)) != cudaSuccess) ||
+        (n->conv_tc_ok && (e = cudaMalloc(&n->d_cpack, n->cpk.total_bytes)) != cudaSuccess)) {
         cudaFree(n->d_blob); cudaFree(n->d_pack); cudaFree(n->d_fpack);
         delete n;
         return fail_cuda("cumind_net_create", e);
@@ -209,6 +256,10 @@ extern "C" int cumind_net_update_params(cumind_net* n, const float* h_params, si
     cudaStream_t st = (cudaStream_t)stream;
     build_pack(n, h_params, n->h_pack);
     build_fused_pack(n, h_params, n->h_fpack);
+    if (n->conv_tc_ok) {
+        build_conv_tc_pack(n, h_params, n->h_cpack);
+        CM_CUDA(cudaMemcpyAsync(n->d_cpack, n->h_cpack.data(), n->cpk.total_bytes, cudaMemcpyHostToDevice, st));
+    }
     if (n->tc_ok) {
         build_tc_pack(n, h_params, n->h_tcpack);
         CM_CUDA(cudaMemcpyAsync(n->d_tcpack, n->h_tcpack.data(), n->tpk.total_bytes, cudaMemcpyHostToDevice, st));
@@ -226,6 +277,7 @@ extern "C" int cumind_net_destroy(cumind_net* n) {
     cudaFree(n->d_pack);
     cudaFree(n->d_fpack);
     cudaFree(n->d_tcpack);
+    cudaFree(n->d_cpack);
     cudaFree(n->d_work);
     delete n;
     return 0;
@@ -271,8 +323,10 @@ extern "C" int cumind_initial_inference(const cumind_net* cn, const float* d_obs
         g_launches += 1;
     } else {
         if ((n->desc.conv_channels & 3) != 0) return fail("image encoder needs conv_channels % 4 == 0");
-        const int chunk = B < 128 ? B : 128;
-        const size_t need = conv_encoder_work_bytes(n->desc, chunk);
+        const bool tc = net_mode == CUMIND_NET_BF16_TC;
+        if (tc && !n->conv_tc_ok) return fail("CUMIND_NET_BF16_TC image encoder needs conv_channels % 16 == 0 and <= 256");
+        const int chunk = tc ? (B < 256 ? B : 256) : (B < 128 ? B : 128);
+        const size_t need = tc ? conv_tc_work_bytes(n->desc, chunk) : conv_encoder_work_bytes(n->desc, chunk);
         if (need > n->work_bytes) {
             CM_CUDA(cudaStreamSynchronize(st));
             cudaFree(n->d_work);
@@ -281,7 +335,10 @@ extern "C" int cumind_initial_inference(const cumind_net* cn, const float* d_obs
             CM_CUDA(cudaMalloc(&n->d_work, need));
             n->work_bytes = need;
         }
-        CM_CUDA(launch_conv_encoder(nv, d_obs, B, d_hidden, n->d_work, chunk, st));
+        if (tc)
+            CM_CUDA(launch_conv_encoder_tc(nv, n->d_cpack, n->cpk, n->sm_count, d_obs, B, d_hidden, (unsigned char*)n->d_work, chunk, st));
+        else
+            CM_CUDA(launch_conv_encoder(nv, d_obs, B, d_hidden, n->d_work, chunk, st));
         g_launches += (unsigned long long)((B + chunk - 1) / chunk) * (2 + 2 * n->desc.num_blocks);
     }
     if (d_logits || d_value) {

@@ -157,6 +157,17 @@ inline TcPackLayout make_tc_pack_layout(int H, int L, int A) {
     return p;
 }
 
+// Per-layer sections of the tensor-core conv pack: bf16 weight tile [Kpad/8][Cout/8][8][8]
+// (row = output channel, k = (ky*3+kx)*Cin + ci, zero padded to Kpad), then fp32 gain[Cout] and
+// shift[Cout] (conv bias and inference BatchNorm folded: y = acc*gain + shift).
+struct ConvTcPackLayout {
+    static constexpr int kMaxLayers = 17;  // 1 + 2*L, L <= 8
+    int n_layers;
+    int K[kMaxLayers], Kpad[kMaxLayers], cin[kMaxLayers];
+    size_t off[kMaxLayers], bytes[kMaxLayers], gain_off[kMaxLayers];
+    size_t total_bytes;
+};
+
 // ------------------------------------------------------------------------------------------------
 // tree storage
 // ------------------------------------------------------------------------------------------------

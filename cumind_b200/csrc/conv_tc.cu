@@ -1,0 +1,288 @@
+// conv_tc.cu — image encoder on the tensor cores (bf16 mode): every 3x3 convolution of ConvEncoder /
+// ResidualBlock (network.py:131-147, 29-45) as an implicit GEMM on tcgen05.
+//
+//   GEMM view:  D[pixels, Cout] = A[pixels, 9*Cin] . B[9*Cin, Cout]
+//   M tile = 128 output pixels (flattened over the image chunk) = the 128 TMEM lanes; thread r builds row
+//   r of the im2col operand straight into the UMMA K-major core-matrix layout in shared memory (taps in
+//   (ky,kx,ci) order, zero rows for padding taps); the bf16 weights (pre-tiled on the host) are staged
+//   once per CTA by TMA bulk copies; K is walked in chunks that accumulate in TMEM;
+//   the epilogue (thread = pixel) applies  y = acc*gain + shift  (conv bias and the inference
+//   BatchNorm folded per channel), the residual, ReLU, and writes bf16 NHWC.
+// Activations between layers are bf16; accumulation and the epilogue are fp32.  rtol 2e-2 vs fp32-exact.
+#include "kernels.h"
+#include "search_core.cuh"
+#include "tc_common.cuh"
+
+namespace cm {
+
+struct ConvTcArgs {
+    const float* in_f32;            // first layer: fp32 NHWC observations, or null
+    const __nv_bfloat16* in_bf16;   // other layers: bf16 NHWC activations
+    __nv_bfloat16* out;             // [n][Ho][Wo][Cout] bf16
+    const __nv_bfloat16* res;       // residual (same shape as out) or null
+    const unsigned char* wpack;     // bf16 weight tile [Kpad/8][Cout/8][8][8] | gain[Cout] | shift[Cout] (fp32)
+    int w_bytes;                    // bytes of the whole pack section of this layer
+    int gain_off;                   // byte offset of gain inside the section (shift follows)
+    int n_img, Hi, Wi, Cin, Ho, Wo, Cout, stride, relu;
+    int K, Kpad, KCH;               // 9*Cin, rounded up to 16, chunk size (multiple of 16)
+};
+
+__global__ void __launch_bounds__(128) conv_tc_kernel(const ConvTcArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* w_s = smem;
+    unsigned char* a_s = smem + ((a.w_bytes + 127) & ~127);
+    uint64_t* bar_w = reinterpret_cast<uint64_t*>(a_s + (size_t)128 * a.KCH * 2);
+    uint64_t* bar_mma = bar_w + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < a.Cout) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        tc_mbar_init(bar_w, 1);
+        tc_mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) {
+        tc_mbar_expect_tx(bar_w, (uint32_t)a.w_bytes);
+        const uint32_t CH = 32768;
+        for (uint32_t o = 0; o < (uint32_t)a.w_bytes; o += CH) {
+            const uint32_t n = (uint32_t)a.w_bytes - o < CH ? (uint32_t)a.w_bytes - o : CH;
+            tc_bulk_g2s(w_s + o, a.wpack + o, n, bar_w);
+        }
+    }
+    tc_mbar_wait(bar_w, 0);
+    const float* gain_s = reinterpret_cast<const float*>(w_s + a.gain_off);
+    const float* shift_s = gain_s + a.Cout;
+    const uint32_t a_addr = smem_addr(a_s), w_addr = smem_addr(w_s);
+    const uint32_t idesc = umma_idesc(128, a.Cout);
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t b_lbo = (uint32_t)(a.Cout / 8) * 128;
+    uint32_t mma_phase = 0;
+
+    const long long n_pix = (long long)a.n_img * a.Ho * a.Wo;
+    const int hw = a.Ho * a.Wo;
+    for (long long row0 = (long long)blockIdx.x * 128; row0 < n_pix; row0 += (long long)gridDim.x * 128) {
+        const long long pix = row0 + tid;
+        const bool live = pix < n_pix;
+        int img = 0, oy = 0, ox = 0;
+        if (live) { img = (int)(pix / hw); const int rem = (int)(pix - (long long)img * hw); oy = rem / a.Wo; ox = rem - oy * a.Wo; }
+        unsigned char* my_row = a_s + ((size_t)(tid >> 3) * 64 + (tid & 7) * 8) * 2;  // + kc*16*128 per 8-wide K chunk
+        bool first_mma = true;
+        for (int k0 = 0; k0 < a.Kpad; k0 += a.KCH) {
+            const int kn = a.Kpad - k0 < a.KCH ? a.Kpad - k0 : a.KCH;  // multiple of 16
+            // ---- im2col gather of this row, K range [k0, k0+kn) -----------------------------------------
+            if (a.in_bf16 && (a.Cin & 7) == 0) {
+                const __nv_bfloat16* in = a.in_bf16 + (size_t)img * a.Hi * a.Wi * a.Cin;
+                for (int kc = 0; kc < kn / 8; ++kc) {
+                    const int k = k0 + kc * 8;
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (live && k < a.K) {
+                        const int tap = k / a.Cin, ci = k - tap * a.Cin;
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        const int iy = oy * a.stride - 1 + ky, ix = ox * a.stride - 1 + kx;
+                        if (iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi)
+                            v = *reinterpret_cast<const uint4*>(in + ((size_t)iy * a.Wi + ix) * a.Cin + ci);
+                    }
+                    *reinterpret_cast<uint4*>(my_row + (size_t)kc * 16 * 128) = v;
+                }
+            } else {
+                const float* in = a.in_f32 + (size_t)img * a.Hi * a.Wi * a.Cin;
+                for (int kc = 0; kc < kn / 8; ++kc) {
+                    float f[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int k = k0 + kc * 8 + i;
+                        float v = 0.f;
+                        if (live && k < a.K) {
+                            const int tap = k / a.Cin, ci = k - tap * a.Cin;
+                            const int ky = tap / 3, kx = tap - ky * 3;
+                            const int iy = oy * a.stride - 1 + ky, ix = ox * a.stride - 1 + kx;
+                            if (iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi) v = in[((size_t)iy * a.Wi + ix) * a.Cin + ci];
+                        }
+                        f[i] = v;
+                    }
+                    uint32_t w4[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                        w4[i] = *reinterpret_cast<const uint32_t*>(&b2);
+                    }
+                    *reinterpret_cast<uint4*>(my_row + (size_t)kc * 16 * 128) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                }
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                for (int ks = 0; ks < kn / 16; ++ks) {
+                    const uint64_t ad = umma_desc(a_addr + (uint32_t)ks * 2 * 2048, 2048, 128);
+                    const uint64_t bd = umma_desc(w_addr + (uint32_t)(k0 / 8 + 2 * ks) * b_lbo, b_lbo, 128);
+                    umma_f16(tmem_base, ad, bd, idesc, first_mma ? 0u : 1u);
+                    first_mma = false;
+                }
+                umma_commit(bar_mma);
+            }
+            tc_mbar_wait(bar_mma, mma_phase);
+            mma_phase ^= 1;
+            tc_fence_after();
+        }
+        // ---- epilogue: y = acc*gain + shift (+res) -> relu -> bf16 NHWC --------------------------------
+        for (int c0 = 0; c0 < a.Cout; c0 += 16) {
+            float acc[16];
+            tmem_ld16(lane_taddr + c0, acc);
+            if (live) {
+                const size_t o = (size_t)pix * a.Cout + c0;
+                float r[16];
+                if (a.res) {
+                    const uint4 r0 = *reinterpret_cast<const uint4*>(a.res + o), r1 = *reinterpret_cast<const uint4*>(a.res + o + 8);
+                    const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[i]));
+                        r[2 * i] = f2.x; r[2 * i + 1] = f2.y;
+                    }
+                }
+                uint32_t ow[8];
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    float y0 = acc[i] * gain_s[c0 + i] + shift_s[c0 + i];
+                    float y1 = acc[i + 1] * gain_s[c0 + i + 1] + shift_s[c0 + i + 1];
+                    if (a.res) { y0 += r[i]; y1 += r[i + 1]; }
+                    if (a.relu) { y0 = y0 > 0.f ? y0 : 0.f; y1 = y1 > 0.f ? y1 : 0.f; }
+                    const __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
+                    ow[i / 2] = *reinterpret_cast<const uint32_t*>(&b2);
+                }
+                *reinterpret_cast<uint4*>(a.out + o) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                *reinterpret_cast<uint4*>(a.out + o + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// mean over pixels (fp32 accumulation, tree reduction over 8 pixel slices) then final_dense in fp32
+__global__ void __launch_bounds__(256) pool_dense_bf16_kernel(const __nv_bfloat16* __restrict__ x, int npix, int Cc,
+                                                             const float* __restrict__ K, const float* __restrict__ b, int H,
+                                                             float* __restrict__ hidden) {
+    extern __shared__ __align__(16) float sm[];  // [8][Cc] partial sums, then pooled [Cc]
+    const int img = blockIdx.x;
+    const __nv_bfloat16* xi = x + (size_t)img * npix * Cc;
+    const int slices = 8;
+    for (int idx = threadIdx.x; idx < slices * Cc; idx += blockDim.x) {
+        const int sl = idx / Cc, c = idx - sl * Cc;
+        float s = 0.f;
+        for (int i = sl; i < npix; i += slices) s += __bfloat162float(xi[(size_t)i * Cc + c]);
+        sm[idx] = s;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < Cc; c += blockDim.x) {
+        float s = 0.f;
+        for (int sl = 0; sl < slices; ++sl) s += sm[sl * Cc + c];
+        sm[slices * Cc + c] = s / (float)npix;
+    }
+    __syncthreads();
+    const float* pooled = sm + slices * Cc;
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        float acc = 0.f;
+        for (int k = 0; k < Cc; ++k) acc = fmaf(pooled[k], K[(size_t)k * H + j], acc);
+        hidden[(size_t)img * H + j] = acc + b[j];
+    }
+}
+
+static inline int out_dim2(int n) { return (n - 1) / 2 + 1; }
+
+bool conv_tc_supported(const cumind_net_desc& d) {
+    return d.obs_ndim == 3 && d.conv_channels % 16 == 0 && d.conv_channels <= 256 && d.obs_shape[2] <= 512;
+}
+
+ConvTcPackLayout make_conv_tc_pack_layout(const cumind_net_desc& d) {
+    ConvTcPackLayout p{};
+    const int C = d.obs_shape[2], Cc = d.conv_channels, L = d.num_blocks;
+    p.n_layers = 1 + 2 * L;
+    size_t o = 0;
+    for (int i = 0; i < p.n_layers && i < ConvTcPackLayout::kMaxLayers; ++i) {
+        const int cin = i == 0 ? C : Cc;
+        const int K = 9 * cin, Kpad = (K + 15) & ~15;
+        p.K[i] = K; p.Kpad[i] = Kpad; p.cin[i] = cin;
+        p.off[i] = o;
+        const size_t wbytes = ((size_t)Kpad * Cc * 2 + 127) & ~(size_t)127;
+        p.gain_off[i] = wbytes;
+        p.bytes[i] = (wbytes + (size_t)2 * Cc * 4 + 127) & ~(size_t)127;
+        o += p.bytes[i];
+    }
+    p.total_bytes = o;
+    return p;
+}
+
+size_t conv_tc_work_bytes(const cumind_net_desc& d, int chunk) {
+    const size_t npix = (size_t)out_dim2(d.obs_shape[0]) * out_dim2(d.obs_shape[1]);
+    return 3 * (((size_t)chunk * npix * d.conv_channels * 2 + 255) & ~(size_t)255);
+}
+
+static cudaError_t run_conv_tc(ConvTcArgs a, int sm_count, cudaStream_t st) {
+    a.KCH = a.Kpad < 384 ? a.Kpad : 384;
+    const size_t smem = ((a.w_bytes + 127) & ~127) + (size_t)128 * a.KCH * 2 + 64;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long n_pix = (long long)a.n_img * a.Ho * a.Wo;
+    const long long tiles = (n_pix + 127) / 128;
+    int per_sm = (int)((227 * 1024) / smem);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    const long long cap = (long long)sm_count * per_sm;
+    const int grid = (int)(tiles < cap ? tiles : cap);
+    conv_tc_kernel<<<grid, 128, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_conv_encoder_tc(const NetView& nv, const unsigned char* cpack, const ConvTcPackLayout& cpk, int sm_count,
+                                   const float* obs, int B, float* hidden, unsigned char* work, int chunk, cudaStream_t st) {
+    const cumind_net_desc& d = nv.desc;
+    const int Hi = d.obs_shape[0], Wi = d.obs_shape[1], C = d.obs_shape[2], Cc = d.conv_channels, L = d.num_blocks, H = d.hidden_dim;
+    const int Ho = out_dim2(Hi), Wo = out_dim2(Wi);
+    const size_t npix = (size_t)Ho * Wo;
+    const size_t buf = ((size_t)chunk * npix * Cc * 2 + 255) & ~(size_t)255;
+    __nv_bfloat16* x = reinterpret_cast<__nv_bfloat16*>(work);
+    __nv_bfloat16* t = reinterpret_cast<__nv_bfloat16*>(work + buf);
+    __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(work + 2 * buf);
+    // final_dense parameters live in the canonical fp32 blob after the conv / bn parameters
+    const float* fd = nv.blob + nv.lo.enc + ((size_t)9 * C * Cc + Cc) + (size_t)L * (2 * ((size_t)9 * Cc * Cc + Cc) + 8 * Cc);
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int n = B - b0 < chunk ? B - b0 : chunk;
+        auto layer = [&](int i, const float* in_f32, const __nv_bfloat16* in_bf16, __nv_bfloat16* out, const __nv_bfloat16* res,
+                         int hi, int wi, int cin, int stride) {
+            ConvTcArgs a{};
+            a.in_f32 = in_f32; a.in_bf16 = in_bf16; a.out = out; a.res = res;
+            a.wpack = cpack + cpk.off[i]; a.w_bytes = (int)cpk.bytes[i]; a.gain_off = (int)cpk.gain_off[i];
+            a.n_img = n; a.Hi = hi; a.Wi = wi; a.Cin = cin; a.Ho = Ho; a.Wo = Wo; a.Cout = Cc; a.stride = stride; a.relu = 1;
+            a.K = cpk.K[i]; a.Kpad = cpk.Kpad[i];
+            return run_conv_tc(a, sm_count, st);
+        };
+        cudaError_t e = layer(0, obs + (size_t)b0 * Hi * Wi * C, nullptr, x, nullptr, Hi, Wi, C, 2);
+        if (e != cudaSuccess) return e;
+        for (int l = 0; l < L; ++l) {
+            if ((e = layer(1 + 2 * l, nullptr, x, t, nullptr, Ho, Wo, Cc, 1)) != cudaSuccess) return e;
+            if ((e = layer(2 + 2 * l, nullptr, t, u, x, Ho, Wo, Cc, 1)) != cudaSuccess) return e;
+            __nv_bfloat16* tmp = x; x = u; u = tmp;
+        }
+        pool_dense_bf16_kernel<<<n, 256, (size_t)9 * Cc * sizeof(float), st>>>(x, (int)npix, Cc, fd, fd + (size_t)Cc * H, H,
+                                                                            hidden + (size_t)b0 * H);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace cm

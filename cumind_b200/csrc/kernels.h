@@ -64,6 +64,13 @@ cudaError_t launch_recurrent_tc(const unsigned char* pack, const TcPackLayout& p
 cudaError_t launch_expand_tc(const unsigned char* pack, const TcPackLayout& pk, int sm_count, const TreeView& tv, float* leaf_value,
                              cudaStream_t st);
 
+// conv_tc.cu — image encoder as implicit GEMM on tcgen05 (bf16 mode)
+bool conv_tc_supported(const cumind_net_desc& d);
+ConvTcPackLayout make_conv_tc_pack_layout(const cumind_net_desc& d);
+size_t conv_tc_work_bytes(const cumind_net_desc& d, int chunk);
+cudaError_t launch_conv_encoder_tc(const NetView& nv, const unsigned char* cpack, const ConvTcPackLayout& cpk, int sm_count,
+                                   const float* obs, int B, float* hidden, unsigned char* work, int chunk, cudaStream_t st);
+
 // conv_fp32.cu — image encoder, fp32-exact (ConvEncoder, network.py:111-147)
 size_t conv_encoder_work_bytes(const cumind_net_desc& d, int chunk);
 cudaError_t launch_conv_encoder(const NetView& nv, const float* obs, int B, float* hidden, float* work, int chunk,
