@@ -41,6 +41,28 @@ import numpy as np  # noqa: E402
 # ---- workload (BASELINE.json configs[1]) -------------------------------
 OBS_SHAPE, A, H, L, CC = (4,), 2, 64, 2, 32
 C_PUCT, ALPHA, FRAC = 1.25, 0.3, 0.25
+WORKLOAD, MODEL_DTYPE = "cartpole", "float32"
+
+
+def set_workload(name: str):
+    """cartpole = BASELINE configs[1] (the bench line); atari = configs[2] (3x84x84 image observations, NHWC
+    (84,84,3), A=4, residual conv trunk, bf16 tensor-core mode) — measured for profiles/, not the bench line."""
+    global OBS_SHAPE, A, H, L, CC, WORKLOAD, MODEL_DTYPE
+    WORKLOAD = name
+    if name == "atari":
+        OBS_SHAPE, A, H, L, CC, MODEL_DTYPE = (84, 84, 3), 4, 64, 2, 32, "bfloat16"
+    elif name == "atari-literal":
+        OBS_SHAPE, A, H, L, CC, MODEL_DTYPE = (3, 84, 84), 4, 64, 2, 32, "bfloat16"
+    elif name != "cartpole":
+        raise ValueError(name)
+
+
+def encoder_flops_per_obs() -> float:
+    if len(OBS_SHAPE) == 1:
+        return 2.0 * OBS_SHAPE[0] * H + 2.0 * (L - 1) * H * H
+    hh, ww, c = OBS_SHAPE
+    npix = ((hh - 1) // 2 + 1) * ((ww - 1) // 2 + 1)
+    return 2.0 * npix * 9 * c * CC + L * 2 * (2.0 * npix * 9 * CC * CC) + 2.0 * CC * H
 PARAM_SEED, OBS_SEED, NOISE_SEED = 42, 0, 1
 FALLBACK_HBM_GBS = 6650.0
 
@@ -50,7 +72,8 @@ def make_inputs(B: int, rank: int):
 
     params = nn.random_params(OBS_SHAPE, A, H, L, CC, PARAM_SEED)
     blob = nn.flatten_params(params, OBS_SHAPE)
-    obs = np.random.default_rng(OBS_SEED + 1000 * rank).standard_normal((B,) + OBS_SHAPE).astype(np.float32)
+    rng_obs = np.random.default_rng(OBS_SEED + 1000 * rank)
+    obs = (rng_obs.standard_normal((B,) + OBS_SHAPE) if len(OBS_SHAPE) == 1 else rng_obs.random((B,) + OBS_SHAPE)).astype(np.float32)
     noise = np.random.default_rng(NOISE_SEED + 1000 * rank).dirichlet([ALPHA] * A, size=B)
     return params, blob, obs, noise
 
@@ -213,8 +236,10 @@ def run_reference(args, rank: int, world: int):
 
 
 def workload_config(args, per_gpu: int):
-    return {"workload": f"BASELINE configs[1]: CartPole-shaped synthetic self-play, B={per_gpu} trees per GPU, S={args.sims} simulations, "
-                        f"obs {OBS_SHAPE}, A={A}, hidden_dim={H}, num_blocks={L}, fp32-exact network, injected Dirichlet({ALPHA}) noise, c_puct={C_PUCT}",
+    title = "BASELINE configs[1]: CartPole-shaped synthetic self-play" if WORKLOAD == "cartpole" else f"BASELINE configs[2] ({WORKLOAD}): image observations"
+    mode = "fp32-exact network" if MODEL_DTYPE == "float32" else "bf16 tensor-core (tcgen05) network"
+    return {"workload": f"{title}, B={per_gpu} trees per GPU, S={args.sims} simulations, "
+                        f"obs {OBS_SHAPE}, A={A}, hidden_dim={H}, num_blocks={L}, {mode}, injected Dirichlet({ALPHA}) noise, c_puct={C_PUCT}",
             "trees_per_gpu": per_gpu, "num_simulations": args.sims, "parallelism": f"trees sharded by environment x{args.gpus}, no collective",
             "l2": "256 MiB device buffer written between timed steps (L2 flush); per-step CUDA events"}
 
@@ -243,7 +268,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
     B = args.trees
     _, blob, obs, noise = make_inputs(B, rank)
     cfg = Config(hidden_dim=H, num_blocks=L, num_simulations=S, action_space_size=A, observation_shape=OBS_SHAPE, c_puct=C_PUCT,
-                 dirichlet_alpha=ALPHA, exploration_fraction=FRAC)
+                 dirichlet_alpha=ALPHA, exploration_fraction=FRAC, conv_channels=CC, model_dtype=MODEL_DTYPE)
     agent = Agent(cfg)
     agent.network.load_state(P.unflatten(blob, OBS_SHAPE, A, H, L, CC))
     agent.update_target_network()
@@ -289,6 +314,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
     launches = _native.launch_count() - launches0
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     kern_ms = [s.elapsed_time(e) for s, e in zip(k_start, ends)]
+    enc_ms = [s.elapsed_time(e) for s, e in zip(starts, k_start)]
     total_ms = sum(step_ms)
     dump = mcts.dump_trees()
     dbar = float(dump["depth_sum"].mean()) / S
@@ -307,10 +333,10 @@ def run_native(args, rank: int, world: int, local_rank: int):
     e2e_s = time.perf_counter() - e0
     sampler.stop_flag = True
 
-    t = torch.tensor([total_ms, e2e_s * 1e3, statistics.mean(kern_ms)], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_s * 1e3, statistics.mean(kern_ms), statistics.mean(enc_ms)], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, kern_ms_mean = (float(x) for x in t.cpu())
+    total_ms, e2e_ms, kern_ms_mean, enc_ms_mean = (float(x) for x in t.cpu())
     t_trees = torch.tensor([B], dtype=torch.int64, device=dev)
     if dist is not None:
         dist.all_reduce(t_trees)
@@ -332,16 +358,25 @@ def run_native(args, rank: int, world: int, local_rank: int):
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("search_fused_dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "search_fused_kernel", "kernel_ms": kern_ms_mean, "algorithmic_bytes_per_sim": algorithmic_bytes_per_sim(dbar),
+                "mean_path_length": dbar, "peak_source": peak_src}
+    if WORKLOAD != "cartpole":
+        # image workload: the conv trunk dominates and is tensor-pipe bound
+        tf_peak = float(json.load(open(peaks_path)).get("bf16_tflops", 1590.0)) if os.path.exists(peaks_path) else 1590.0
+        tf = encoder_flops_per_obs() * B / (enc_ms_mean * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf / tf_peak, "traffic": None,
+                    "kernel": "conv_tc_kernel (all launches of one initial_inference)", "kernel_ms": enc_ms_mean,
+                    "flops_per_obs": encoder_flops_per_obs(), "search_ms": kern_ms_mean, "mean_path_length": dbar,
+                    "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops)" if os.path.exists(peaks_path) else "fallback"}
     line = {
         "metric": "batched MCTS simulations/sec", "value": value, "unit": "simulations/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
-        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong" if args.total_trees > 0 else "weak", "vs_baseline": None, "dtype": "fp32",
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong" if args.total_trees > 0 else "weak", "vs_baseline": None, "dtype": "fp32" if MODEL_DTYPE == "float32" else "bf16",
         "data": "synthetic", "config": workload_config(args, per_gpu=B),
         "e2e": {"value": e2e_value, "unit": "simulations/s", "h2d_bytes_per_step": int(obs.nbytes + noise.nbytes),
                 "d2h_bytes_per_step": int(actions.nbytes + probs.nbytes), "ms_per_step": e2e_ms / K},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "search_fused_kernel", "kernel_ms": kern_ms_mean, "algorithmic_bytes_per_sim": algorithmic_bytes_per_sim(dbar),
-                     "mean_path_length": dbar, "peak_source": peak_src},
+        "roofline": roofline,
         "clocks": sampler.summary(),
         "plan": mcts.plan(B), "wall_s": wall, "root_visits_ok": visits_ok,
     }
@@ -390,7 +425,14 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="lanes per tree (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--workload", default="cartpole", choices=["cartpole", "atari", "atari-literal"],
+                    help="cartpole = BASELINE configs[1] (the bench line); atari = configs[2], measured for profiles/ only")
     args = ap.parse_args()
+    set_workload(args.workload)
+    if args.workload != "cartpole":
+        args.no_cpu = True
+        if args.trees == 4096:
+            args.trees = 1024
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

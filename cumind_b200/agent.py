@@ -41,9 +41,12 @@ class Agent:
         self.device = torch.device("cuda", torch.cuda.current_device())
         key.seed(config.seed)
         rngs = Rngs(params=key())
+        # config.model_dtype (validated but unused by the reference, config.py:164-167) selects the arithmetic:
+        # "float32" = fp32-exact parity mode, "bfloat16" = tcgen05 tensor-core mode
+        net_mode = _native.NET_BF16_TC if getattr(config, "model_dtype", "float32") == "bfloat16" else _native.NET_FP32_EXACT
         self.network = CuMindNetwork(observation_shape=config.observation_shape, action_space_size=config.action_space_size,
                                      hidden_dim=config.hidden_dim, num_blocks=config.num_blocks,
-                                     conv_channels=config.conv_channels, rngs=rngs, device=self.device)
+                                     conv_channels=config.conv_channels, rngs=rngs, device=self.device, net_mode=net_mode)
         self.target_network = self.network.clone()
         self.optimizer = AdamW(config.learning_rate, config.weight_decay)
         if existing_state:

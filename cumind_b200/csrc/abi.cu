@@ -325,7 +325,7 @@ extern "C" int cumind_initial_inference(const cumind_net* cn, const float* d_obs
         if ((n->desc.conv_channels & 3) != 0) return fail("image encoder needs conv_channels % 4 == 0");
         const bool tc = net_mode == CUMIND_NET_BF16_TC;
         if (tc && !n->conv_tc_ok) return fail("CUMIND_NET_BF16_TC image encoder needs conv_channels % 16 == 0 and <= 256");
-        const int chunk = tc ? (B < 256 ? B : 256) : (B < 128 ? B : 128);
+        const int chunk = tc ? (B < 1024 ? B : 1024) : (B < 128 ? B : 128);
         const size_t need = tc ? conv_tc_work_bytes(n->desc, chunk) : conv_encoder_work_bytes(n->desc, chunk);
         if (need > n->work_bytes) {
             CM_CUDA(cudaStreamSynchronize(st));
@@ -591,8 +591,12 @@ extern "C" int cumind_search(cumind_tree* t, const cumind_net* n, const float* d
     if (!d_root_hidden || !d_out_visits || !d_out_probs) return fail("cumind_search: NULL device pointer");
     FusedPlan pl;
     std::string why;
-    // the fused kernel is the fp32-exact path; the tensor-core mode runs one launch per phase
-    if (c->net_mode != CUMIND_NET_FP32_EXACT || plan_fused(t, n, c, pl, why) != 0)
+    // The fused kernel computes the in-search MLP in fp32-exact arithmetic.  It is also what
+    // CUMIND_NET_BF16_TC runs when the parameters fit its shared-memory staging: at these layer widths
+    // one fused launch beats 3 launches per simulation through the tensor-core expansion kernel
+    // (measured in profiles/README.md), and it is more accurate.  cumind_search_stepwise always
+    // honours net_mode (tcgen05 expansion kernel in bf16 mode).
+    if (plan_fused(t, n, c, pl, why) != 0)
         return cumind_search_stepwise(t, n, d_root_hidden, c, d_noise, d_out_visits, d_out_probs, d_out_root_value, stream);
     pl.p.root_hidden = d_root_hidden;
     pl.p.noise = d_noise;

@@ -27,6 +27,10 @@ struct ConvTcArgs {
     int K, Kpad, KCH;               // 9*Cin, rounded up to 16, chunk size (multiple of 16)
 };
 
+// CIN32: Cin == 32 and the whole K = 288 fits one chunk: all 36 16-byte loads of a row are issued
+// before the first dependent shared-memory store (a warp issues in order, so a store waiting for its
+// load would otherwise serialise the global-memory latency tap by tap).
+template <bool CIN32>
 __global__ void __launch_bounds__(128) conv_tc_kernel(const ConvTcArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* w_s = smem;
@@ -77,36 +81,79 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const ConvTcArgs a) {
         bool first_mma = true;
         for (int k0 = 0; k0 < a.Kpad; k0 += a.KCH) {
             const int kn = a.Kpad - k0 < a.KCH ? a.Kpad - k0 : a.KCH;  // multiple of 16
-            // ---- im2col gather of this row, K range [k0, k0+kn) -----------------------------------------
-            if (a.in_bf16 && (a.Cin & 7) == 0) {
+            // ---- im2col gather of this row, K range [k0, k0+kn): (tap, ci) advance incrementally, loads are
+            // issued in batches of 8 independent 16-byte requests before the shared-memory stores -------------
+            const int nkc = kn / 8;
+            int tap = k0 / a.Cin, ci = k0 - tap * a.Cin;
+            int ky = tap / 3, kx = tap - ky * 3;
+            const int iy_base = oy * a.stride - 1, ix_base = ox * a.stride - 1;
+            if constexpr (CIN32) {
+                // K chunk = 3 whole taps of 32 channels (KCH = 96): 12 independent 16-byte loads, then 12 stores
+                const __nv_bfloat16* in = a.in_bf16 + (size_t)img * a.Hi * a.Wi * 32;
+                uint4 v[12];
+#pragma unroll
+                for (int t3 = 0; t3 < 3; ++t3) {
+                    const int iy = iy_base + ky, ix = ix_base + kx + t3;   // a chunk is one kernel row: ky fixed, kx = 0..2
+                    const bool ok = live && iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi;
+                    const uint4* src = reinterpret_cast<const uint4*>(in + ((size_t)(ok ? iy : 0) * a.Wi + (ok ? ix : 0)) * 32);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[t3 * 4 + j] = ok ? src[j] : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int kc = 0; kc < 12; ++kc) *reinterpret_cast<uint4*>(my_row + (size_t)kc * 2048) = v[kc];
+            } else if (a.in_bf16 && (a.Cin & 31) == 0 && ci == 0) {
+                // whole taps, Cin a multiple of 32: one bounds test and one base pointer per tap, then
+                // Cin/8 independent 16-byte loads in groups of 4
                 const __nv_bfloat16* in = a.in_bf16 + (size_t)img * a.Hi * a.Wi * a.Cin;
-                for (int kc = 0; kc < kn / 8; ++kc) {
-                    const int k = k0 + kc * 8;
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (live && k < a.K) {
-                        const int tap = k / a.Cin, ci = k - tap * a.Cin;
-                        const int ky = tap / 3, kx = tap - ky * 3;
-                        const int iy = oy * a.stride - 1 + ky, ix = ox * a.stride - 1 + kx;
-                        if (iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi)
-                            v = *reinterpret_cast<const uint4*>(in + ((size_t)iy * a.Wi + ix) * a.Cin + ci);
+                const int per_tap = a.Cin >> 3;
+                int kc = 0;
+                for (; tap < 9 && kc + per_tap <= nkc; ++tap) {
+                    const int iy = iy_base + ky, ix = ix_base + kx;
+                    const bool ok = live && iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi;
+                    const uint4* src = reinterpret_cast<const uint4*>(in + ((size_t)(ok ? iy : 0) * a.Wi + (ok ? ix : 0)) * a.Cin);
+                    for (int j = 0; j < per_tap; j += 4) {
+                        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
+                        if (ok) { v0 = src[j]; v1 = src[j + 1]; v2 = src[j + 2]; v3 = src[j + 3]; }
+                        unsigned char* dst = my_row + (size_t)(kc + j) * 2048;
+                        *reinterpret_cast<uint4*>(dst) = v0;
+                        *reinterpret_cast<uint4*>(dst + 2048) = v1;
+                        *reinterpret_cast<uint4*>(dst + 4096) = v2;
+                        *reinterpret_cast<uint4*>(dst + 6144) = v3;
                     }
-                    *reinterpret_cast<uint4*>(my_row + (size_t)kc * 16 * 128) = v;
+                    kc += per_tap;
+                    if (++kx == 3) { kx = 0; ++ky; }
+                }
+                for (; kc < nkc; ++kc) *reinterpret_cast<uint4*>(my_row + (size_t)kc * 2048) = make_uint4(0, 0, 0, 0);
+            } else if (a.in_bf16 && (a.Cin & 7) == 0) {
+                const __nv_bfloat16* in = a.in_bf16 + (size_t)img * a.Hi * a.Wi * a.Cin;
+                for (int kc0 = 0; kc0 < nkc; kc0 += 8) {
+                    uint4 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        v[u] = make_uint4(0, 0, 0, 0);
+                        if (kc0 + u < nkc) {
+                            const int iy = iy_base + ky, ix = ix_base + kx;
+                            if (live && tap < 9 && iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi)
+                                v[u] = *reinterpret_cast<const uint4*>(in + ((size_t)iy * a.Wi + ix) * a.Cin + ci);
+                            ci += 8;
+                            if (ci == a.Cin) { ci = 0; ++tap; if (++kx == 3) { kx = 0; ++ky; } }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (kc0 + u < nkc) *reinterpret_cast<uint4*>(my_row + (size_t)(kc0 + u) * 2048) = v[u];
                 }
             } else {
                 const float* in = a.in_f32 + (size_t)img * a.Hi * a.Wi * a.Cin;
-                for (int kc = 0; kc < kn / 8; ++kc) {
+                for (int kc = 0; kc < nkc; ++kc) {
                     float f[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const int k = k0 + kc * 8 + i;
+                        const int iy = iy_base + ky, ix = ix_base + kx;
                         float v = 0.f;
-                        if (live && k < a.K) {
-                            const int tap = k / a.Cin, ci = k - tap * a.Cin;
-                            const int ky = tap / 3, kx = tap - ky * 3;
-                            const int iy = oy * a.stride - 1 + ky, ix = ox * a.stride - 1 + kx;
-                            if (iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi) v = in[((size_t)iy * a.Wi + ix) * a.Cin + ci];
-                        }
+                        if (live && tap < 9 && iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi) v = in[((size_t)iy * a.Wi + ix) * a.Cin + ci];
                         f[i] = v;
+                        if (++ci == a.Cin) { ci = 0; ++tap; if (++kx == 3) { kx = 0; ++ky; } }
                     }
                     uint32_t w4[4];
 #pragma unroll
@@ -114,7 +161,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const ConvTcArgs a) {
                         const __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
                         w4[i] = *reinterpret_cast<const uint32_t*>(&b2);
                     }
-                    *reinterpret_cast<uint4*>(my_row + (size_t)kc * 16 * 128) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                    *reinterpret_cast<uint4*>(my_row + (size_t)kc * 2048) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
                 }
             }
             fence_async_smem();
@@ -232,19 +279,25 @@ size_t conv_tc_work_bytes(const cumind_net_desc& d, int chunk) {
 }
 
 static cudaError_t run_conv_tc(ConvTcArgs a, int sm_count, cudaStream_t st) {
-    a.KCH = a.Kpad < 384 ? a.Kpad : 384;
+    const bool cin32 = a.in_bf16 && a.Cin == 32 && a.Kpad == 288;
+    a.KCH = cin32 ? 96 : (a.Kpad < 384 ? a.Kpad : 384);
     const size_t smem = ((a.w_bytes + 127) & ~127) + (size_t)128 * a.KCH * 2 + 64;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long long n_pix = (long long)a.n_img * a.Ho * a.Wo;
     const long long tiles = (n_pix + 127) / 128;
     int per_sm = (int)((227 * 1024) / smem);
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 6) per_sm = 6;
     const long long cap = (long long)sm_count * per_sm;
     const int grid = (int)(tiles < cap ? tiles : cap);
-    conv_tc_kernel<<<grid, 128, smem, st>>>(a);
+    if (cin32)
+        conv_tc_kernel<true><<<grid, 128, smem, st>>>(a);
+    else
+        conv_tc_kernel<false><<<grid, 128, smem, st>>>(a);
     return cudaGetLastError();
 }
 

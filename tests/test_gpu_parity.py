@@ -294,6 +294,7 @@ def test_tensor_core_search_agrees_with_exact_search():
     h = (0.3 * rng.standard_normal((B, H))).astype(np.float32)
     noise = rng.dirichlet([0.3] * A, size=B)
     m_exact, m_tc = MCTS(exact, _Cfg(S, A)), MCTS(tc, _Cfg(S, A))
+    m_tc.stepwise = True   # one launch per phase: the expansion runs on the tcgen05 kernel
     p_exact, v_exact = m_exact.search_batch(h, noise=noise)
     p_tc, v_tc = m_tc.search_batch(h, noise=noise)
     assert np.all(v_tc.sum(axis=1) == S - A) and np.allclose(p_tc.sum(axis=1), 1.0)
