@@ -219,6 +219,150 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const ConvTcArgs a) {
     if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stride-1 layers (the residual blocks): NO im2col copy.  The M tile is an 8 (x) by 16 (y) block of
+// output pixels; the CTA stages the 18 x 10 input halo once, laid out [yy][k-chunk][xx][8 ch] so that
+// the 8 pixels of a UMMA core matrix are 8 consecutive x of one image row.  A tap (ky,kx) is then just
+// a shifted view of the same tile: descriptor start = base + ((ky*NJ + 2ks)*10 + kx)*16 B with
+// SBO = one halo row (NJ*160 B) and LBO = one k-chunk (160 B), so the 9*Cin/16 MMAs of a tile read
+// shared memory that was written once (6.4x less gather traffic than materialising im2col rows).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) conv_tc_halo_kernel(const ConvTcArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int NJ = a.Cin >> 3;                       // 16-byte k-chunks per pixel
+    const int halo_bytes = 18 * NJ * 10 * 16;
+    unsigned char* w_s = smem;
+    unsigned char* h_s = smem + ((a.w_bytes + 127) & ~127);
+    uint64_t* bar_w = reinterpret_cast<uint64_t*>(h_s + ((halo_bytes + 127) & ~127));
+    uint64_t* bar_mma = bar_w + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < a.Cout) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        tc_mbar_init(bar_w, 1);
+        tc_mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) {
+        tc_mbar_expect_tx(bar_w, (uint32_t)a.w_bytes);
+        const uint32_t CH = 32768;
+        for (uint32_t o = 0; o < (uint32_t)a.w_bytes; o += CH) {
+            const uint32_t n = (uint32_t)a.w_bytes - o < CH ? (uint32_t)a.w_bytes - o : CH;
+            tc_bulk_g2s(w_s + o, a.wpack + o, n, bar_w);
+        }
+    }
+    tc_mbar_wait(bar_w, 0);
+    const float* gain_s = reinterpret_cast<const float*>(w_s + a.gain_off);
+    const float* shift_s = gain_s + a.Cout;
+    const uint32_t h_addr = smem_addr(h_s), w_addr = smem_addr(w_s);
+    const uint32_t idesc = umma_idesc(128, a.Cout);
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t b_lbo = (uint32_t)(a.Cout / 8) * 128;
+    const uint32_t sbo = (uint32_t)NJ * 160;
+    uint32_t mma_phase = 0;
+
+    const int TX = (a.Wo + 7) / 8, TY = (a.Ho + 15) / 16;
+    const int tiles_per_img = TX * TY;
+    const long long n_tiles = (long long)a.n_img * tiles_per_img;
+    const int n_chunks = 18 * 10 * NJ;
+    const int y = tid >> 3, x = tid & 7;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int img = (int)(tile / tiles_per_img);
+        const int trem = (int)(tile - (long long)img * tiles_per_img);
+        const int ty = trem / TX, tx = trem - ty * TX;
+        const int oy0 = ty * 16, ox0 = tx * 8;
+        const __nv_bfloat16* in = a.in_bf16 + (size_t)img * a.Hi * a.Wi * a.Cin;
+        // ---- stage the halo: chunk idx = (yy*10 + xx)*NJ + j (a pixel's channels are contiguous in global) ----
+        for (int base = 0; base < n_chunks; base += 128 * 6) {
+            uint4 v[6];
+            int dst[6];
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const int idx = base + u * 128 + tid;
+                v[u] = make_uint4(0, 0, 0, 0);
+                dst[u] = -1;
+                if (idx < n_chunks) {
+                    const int pixi = idx / NJ, j = idx - pixi * NJ;
+                    const int yy = pixi / 10, xx = pixi - yy * 10;
+                    const int iy = oy0 + yy - 1, ix = ox0 + xx - 1;
+                    dst[u] = ((yy * NJ + j) * 10 + xx) * 16;
+                    if (iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi)
+                        v[u] = *reinterpret_cast<const uint4*>(in + ((size_t)iy * a.Wi + ix) * a.Cin + j * 8);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 6; ++u)
+                if (dst[u] >= 0) *reinterpret_cast<uint4*>(h_s + dst[u]) = v[u];
+        }
+        // prefetch the residual while the MMAs run
+        const int oy = oy0 + y, ox = ox0 + x;
+        const bool live = oy < a.Ho && ox < a.Wo;
+        const size_t opix = ((size_t)img * a.Ho + oy) * a.Wo + ox;
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            bool first = true;
+            for (int tap = 0; tap < 9; ++tap) {
+                const int ky = tap / 3, kx = tap - ky * 3;
+                for (int ks = 0; ks < NJ / 2; ++ks) {
+                    const uint64_t ad = umma_desc(h_addr + (uint32_t)(((ky * NJ + 2 * ks) * 10 + kx) * 16), 160, sbo);
+                    const uint64_t bd = umma_desc(w_addr + (uint32_t)(tap * NJ + 2 * ks) * b_lbo, b_lbo, 128);
+                    umma_f16(tmem_base, ad, bd, idesc, first ? 0u : 1u);
+                    first = false;
+                }
+            }
+            umma_commit(bar_mma);
+        }
+        tc_mbar_wait(bar_mma, mma_phase);
+        mma_phase ^= 1;
+        tc_fence_after();
+        for (int c0 = 0; c0 < a.Cout; c0 += 16) {
+            float acc[16];
+            tmem_ld16(lane_taddr + c0, acc);
+            if (live) {
+                const size_t o = opix * a.Cout + c0;
+                float r[16];
+                if (a.res) {
+                    const uint4 r0 = *reinterpret_cast<const uint4*>(a.res + o), r1 = *reinterpret_cast<const uint4*>(a.res + o + 8);
+                    const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[i]));
+                        r[2 * i] = f2.x; r[2 * i + 1] = f2.y;
+                    }
+                }
+                uint32_t ow[8];
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    float y0 = acc[i] * gain_s[c0 + i] + shift_s[c0 + i];
+                    float y1 = acc[i + 1] * gain_s[c0 + i + 1] + shift_s[c0 + i + 1];
+                    if (a.res) { y0 += r[i]; y1 += r[i + 1]; }
+                    if (a.relu) { y0 = y0 > 0.f ? y0 : 0.f; y1 = y1 > 0.f ? y1 : 0.f; }
+                    const __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
+                    ow[i / 2] = *reinterpret_cast<const uint32_t*>(&b2);
+                }
+                *reinterpret_cast<uint4*>(a.out + o) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                *reinterpret_cast<uint4*>(a.out + o + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
 // mean over pixels (fp32 accumulation, tree reduction over 8 pixel slices) then final_dense in fp32
 __global__ void __launch_bounds__(256) pool_dense_bf16_kernel(const __nv_bfloat16* __restrict__ x, int npix, int Cc,
                                                              const float* __restrict__ K, const float* __restrict__ b, int H,
@@ -278,7 +422,23 @@ size_t conv_tc_work_bytes(const cumind_net_desc& d, int chunk) {
     return 3 * (((size_t)chunk * npix * d.conv_channels * 2 + 255) & ~(size_t)255);
 }
 
+static cudaError_t run_conv_tc_halo(const ConvTcArgs& a, int sm_count, cudaStream_t st) {
+    const int NJ = a.Cin >> 3;
+    const size_t smem = ((a.w_bytes + 127) & ~127) + ((size_t)(18 * NJ * 10 * 16 + 127) & ~(size_t)127) + 64;
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long tiles = (long long)a.n_img * ((a.Wo + 7) / 8) * ((a.Ho + 15) / 16);
+    int per_sm = (int)((227 * 1024) / smem);
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    const long long cap = (long long)sm_count * per_sm;
+    conv_tc_halo_kernel<<<(int)(tiles < cap ? tiles : cap), 128, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 static cudaError_t run_conv_tc(ConvTcArgs a, int sm_count, cudaStream_t st) {
+    if (a.in_bf16 && a.stride == 1 && (a.Cin & 15) == 0 && a.Cin <= 128 && a.Hi == a.Ho && a.Wi == a.Wo)
+        return run_conv_tc_halo(a, sm_count, st);
     const bool cin32 = a.in_bf16 && a.Cin == 32 && a.Kpad == 288;
     a.KCH = cin32 ? 96 : (a.Kpad < 384 ? a.Kpad : 384);
     const size_t smem = ((a.w_bytes + 127) & ~127) + (size_t)128 * a.KCH * 2 + 64;
