@@ -344,3 +344,28 @@ def test_conv_encoder_exact_at_atari_shape_vs_oracle():
     h, lg, v = lo.initial_inference(lo.make_desc(shape, A, H, L, Cc), blob, obs)
     hg, lgg, vg = net.initial_inference(obs)
     assert hp.bits_equal(hg.cpu().numpy(), h) and hp.bits_equal(lgg.cpu().numpy(), lg) and hp.bits_equal(vg[:, 0].cpu().numpy(), v)
+
+
+def test_agent_with_shipped_checkpoint_reproduces_the_reference_search():
+    """Config from the reference's configuration.json + weights of its shipped CartPole checkpoint:
+    Agent.select_action (eval) returns exactly the probabilities of the verbatim reference search."""
+    from cumind_b200 import Config
+    from cumind_b200 import params as P
+    from cumind_b200.agent import Agent
+
+    flat = {}
+    for section in hp.ckpt_config().values():
+        flat.update(section)
+    config = Config(**flat)
+    config.validate()
+    agent = Agent(config)
+    agent.load_state({"network_state": P.unflatten(hp.ckpt_params(), (4,), 2, 128, 2, 32), "optimizer_state": {"count": 0}})
+    n = 0
+    for case in SEARCH:
+        if case["net"] != "ckpt" or case["noise"]:
+            continue
+        d = hp.search_case_data(case)
+        action, probs = agent.select_action(d["obs"], training=False)
+        assert np.array_equal(probs, d["probs"]) and action == int(np.argmax(d["probs"]))
+        n += 1
+    assert n == 4
