@@ -369,3 +369,57 @@ def test_agent_with_shipped_checkpoint_reproduces_the_reference_search():
         assert np.array_equal(probs, d["probs"]) and action == int(np.argmax(d["probs"]))
         n += 1
     assert n == 4
+
+
+@pytest.mark.parametrize("shape", [(3, 48, 2, 12), (2, 20, 1, 15), (4, 6, 2, 10), (2, 96, 3, 8), (2, 256, 1, 6), (3, 300, 1, 5)],
+                         ids=lambda s: f"A{s[0]}H{s[1]}L{s[2]}")
+def test_odd_hidden_sizes_take_a_valid_path_and_stay_bit_exact(shape):
+    """hidden_dim that is not a power of two (lanes idle in the tile), not a multiple of 4 or beyond 256
+    (automatic fallback to the stepwise kernels): every variant must still equal the oracle bit for bit."""
+    from cumind_b200.mcts import MCTS
+    from oracle import network_np as nn
+
+    A, H, L, S = shape
+    B = 70
+    blob = nn.flatten_params(nn.random_params((4,), A, H, L, 32, 50 + H, bias_scale=0.05), (4,))
+    net = _network((4,), A, H, L, 32, blob)
+    rng = np.random.default_rng(H)
+    h = (0.5 * rng.standard_normal((B, H))).astype(np.float32)
+    noise = rng.dirichlet([0.3] * A, size=B)
+    o = lo.search(lo.make_desc((4,), A, H, L), blob, h, S, A, 1.0, 0.25, noise)
+    mcts = MCTS(net, _Cfg(S, A, c_puct=1.0))
+    probs, visits = mcts.search_batch(h, noise=noise)
+    plan = mcts.plan(B)
+    # fused needs H % 4 == 0, H <= 256 and the packed parameters within shared memory (H=256: 262 kB, too big)
+    assert plan["fused"] == {48: 1, 20: 1, 6: 0, 96: 1, 256: 0, 300: 0}[H]
+    _assert_trees_equal(mcts, o, S, A)
+    assert np.array_equal(probs, o["out_probs"])
+    nx, rw, lg, v = net.recurrent_inference(h, rng.integers(0, A, size=B).astype(np.int32))
+    assert tuple(nx.shape) == (B, H)
+
+
+def test_error_paths_raise_python_exceptions():
+    import torch
+
+    from cumind_b200 import _native
+    from cumind_b200.mcts import MCTS
+    from oracle import network_np as nn
+
+    blob = nn.flatten_params(nn.random_params((4,), 2, 16, 2, 32, 1), (4,))
+    net = _network((4,), 2, 16, 2, 32, blob)
+    m = MCTS(net, _Cfg(0, 2))
+    with pytest.raises(ValueError, match="num_simulations must be positive"):
+        m.search_batch(np.zeros((3, 16), np.float32))
+    m = MCTS(net, _Cfg(5, 2))
+    with pytest.raises(ValueError, match="expected root_hidden"):
+        m.search_batch(np.zeros((3, 8), np.float32))
+    with pytest.raises(ValueError, match="expected noise"):
+        m.search_batch(np.zeros((3, 16), np.float32), noise=np.zeros((3, 5)))
+    with pytest.raises(ValueError, match="expected shape"):
+        net.initial_inference(np.zeros((2, 5), np.float32))
+    with pytest.raises((KeyError, ValueError)):
+        net.load_state({"representation_network": {}})
+    # Philox noise path and training-mode sampling run end to end
+    probs, visits = m.search_batch(np.zeros((9, 16), np.float32), philox_seed=5)
+    assert np.allclose(probs.sum(axis=1), 1.0)
+    assert torch.cuda.is_available() and _native.launch_count() > 0
