@@ -271,6 +271,19 @@ CM_DEVICE double ucb_score_tab(int32_t n, double W, double prior, double sqrtN, 
     return __dadd_rn(div_small(W, (double)n, recip[n]), explo);
 }
 
+// Branch-free variant for the fused select: an unvisited child divides by 1 (recip[1] == 1.0 exactly)
+// and the +inf is selected at the end, so the level has no divergent branch.
+CM_DEVICE double ucb_score_tab_nobranch(int32_t n, double W, double prior, double sqrtN, double c_puct,
+                                        const double* __restrict__ recip) {
+    const bool unvisited = n == 0;
+    const int nn = unvisited ? 1 : n;
+    const double num = __dmul_rn(__dmul_rn(c_puct, prior), sqrtN);
+    const double explo = div_small(num, (double)(1 + n), recip[1 + n]);
+    const double q = div_small(unvisited ? 0.0 : W, (double)nn, recip[nn]);
+    const double s = __dadd_rn(q, explo);
+    return unvisited ? __longlong_as_double(0x7FF0000000000000LL) : s;
+}
+
 // The compiler if-converts the n == 0 case, so the divisions always execute: feed them 1/1 then
 // (0/0 would take the slow special-case path of the IEEE division routine on every unvisited child).
 CM_DEVICE double ucb_score(int32_t n, double W, double prior, double sqrtN, double c_puct) {

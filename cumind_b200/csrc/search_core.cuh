@@ -141,15 +141,81 @@ CM_DEVICE int select_leaf(const Node* __restrict__ nodes, const int32_t* __restr
                                              active, plen_out, parent_e_out, action_out);
 }
 
+// Fused-kernel selection for A <= G: one child per lane, SPAN = pow2 >= A lanes in the butterfly,
+// no divergent branch inside a level (lanes without a child and trees that already reached their
+// leaf alias valid records and are masked out of the arg-max), table-driven exact division.
+template <int G, int SPAN>
+CM_DEVICE int select_leaf_fast(const Node* __restrict__ nodes, const int32_t* __restrict__ eidx,
+                               const double* __restrict__ root_prior, const double* __restrict__ sqrt_tab,
+                               const double* __restrict__ recip, int A, double c_puct, int root_visits,
+                               int* __restrict__ path, int g, bool active, int& plen_out, int& parent_e_out, int& action_out) {
+    int node = 0, e = 0, n_parent = root_visits, plen = 0, action = 0, parent_e = 0;
+    int walking = active ? 1 : 0;
+    const bool has_child = g < A;
+    const int cg = has_child ? g : 0;
+    const Node* my_nodes = nodes + 1 + cg;
+    const int32_t* my_eidx = eidx + 1 + cg;
+    const double my_root_prior = root_prior[cg];
+    while (__any_sync(0xffffffffu, walking != 0)) {
+        const int off = walking ? e * A : 0;
+        const Node nd = load_node(my_nodes + off);
+        const int ce = my_eidx[off];
+        const double p = (node == 0) ? my_root_prior : (double)nd.prior;
+        double s = ucb_score_tab_nobranch(nd.visit, nd.value_sum, p, sqrt_tab[n_parent], c_puct, recip);
+        if (s != s) s = (g == 0) ? dinf() : -dinf();
+        const bool valid = has_child && walking;
+        double best_s = valid ? s : -dinf();
+        unsigned best_ae = valid ? (((unsigned)g << 16) | (unsigned)(ce + 1)) : 0xffffffffu;
+        int best_n = nd.visit;
+#pragma unroll
+        for (int o = SPAN / 2; o > 0; o >>= 1) {
+            const double os = __shfl_xor_sync(0xffffffffu, best_s, o);
+            const unsigned oae = __shfl_xor_sync(0xffffffffu, best_ae, o);
+            const int on = __shfl_xor_sync(0xffffffffu, best_n, o);
+            const bool take = os > best_s || (os == best_s && oae < best_ae);
+            best_s = take ? os : best_s;
+            best_ae = take ? oae : best_ae;
+            best_n = take ? on : best_n;
+        }
+        if constexpr (SPAN < G) {
+            best_ae = __shfl_sync(0xffffffffu, best_ae, 0, G);
+            best_n = __shfl_sync(0xffffffffu, best_n, 0, G);
+        }
+        if (walking && g == 0) path[plen] = node;
+        const int act = (int)(best_ae >> 16);
+        const int ne = (int)(best_ae & 0xffffu) - 1;
+        plen += walking;
+        parent_e = walking ? e : parent_e;
+        action = walking ? act : action;
+        node = walking ? 1 + e * A + act : node;
+        n_parent = walking ? best_n : n_parent;
+        e = walking ? ne : e;
+        walking = (walking && ne >= 0) ? 1 : 0;
+    }
+    plen_out = plen;
+    parent_e_out = parent_e;
+    action_out = action;
+    return node;
+}
+
 // fused kernel: reciprocal-table division
 template <int G>
 CM_DEVICE int select_leaf_tab(const Node* __restrict__ nodes, const int32_t* __restrict__ eidx,
                               const double* __restrict__ root_prior, const double* __restrict__ sqrt_tab,
                               const double* __restrict__ recip, int A, double c_puct, int root_visits,
                               int* __restrict__ path, int g, bool active, int& plen_out, int& parent_e_out, int& action_out) {
-    if (A <= G)
-        return select_leaf_impl<G, true, true>(nodes, eidx, root_prior, sqrt_tab, recip, A, c_puct, root_visits, path, g, active,
-                                               plen_out, parent_e_out, action_out);
+#define CM_SELECT_FAST(SP)                                                                                                   \
+    if constexpr (SP <= G)                                                                                                   \
+        if (A <= SP)                                                                                                         \
+            return select_leaf_fast<G, SP>(nodes, eidx, root_prior, sqrt_tab, recip, A, c_puct, root_visits, path, g, active, \
+                                           plen_out, parent_e_out, action_out);
+    CM_SELECT_FAST(1)
+    CM_SELECT_FAST(2)
+    CM_SELECT_FAST(4)
+    CM_SELECT_FAST(8)
+    CM_SELECT_FAST(16)
+    CM_SELECT_FAST(32)
+#undef CM_SELECT_FAST
     return select_leaf_impl<G, false, true>(nodes, eidx, root_prior, sqrt_tab, recip, A, c_puct, root_visits, path, g, active,
                                             plen_out, parent_e_out, action_out);
 }
