@@ -118,9 +118,9 @@ static void build_fused_pack(const cumind_net* n, const float* blob, std::vector
         memcpy(&fp[pk.layer_b(l)], b, sizeof(float) * H);
     }
     for (int k = 0; k < H; ++k) {
-        for (int a = 0; a < A; ++a) fp[pk.heads_w + (size_t)a * pk.HS + k] = blob[lo.pol_k + (size_t)k * A + a];
-        fp[pk.heads_w + (size_t)A * pk.HS + k] = blob[lo.val_k + k];
-        fp[pk.heads_w + (size_t)(A + 1) * pk.HS + k] = blob[lo.rew_k + k];
+        for (int a = 0; a < A; ++a) fp[pk.heads_w + (size_t)k * pk.HP + a] = blob[lo.pol_k + (size_t)k * A + a];
+        fp[pk.heads_w + (size_t)k * pk.HP + A] = blob[lo.val_k + k];
+        fp[pk.heads_w + (size_t)k * pk.HP + A + 1] = blob[lo.rew_k + k];
     }
     for (int a = 0; a < A; ++a) fp[pk.heads_b + a] = blob[lo.pol_b + a];
     fp[pk.heads_b + A] = blob[lo.val_b];

@@ -103,8 +103,8 @@ inline int pick_neurons_per_lane(int H) {
 // finds, for every block of 4 consecutive k, its 4*R weights in R 16-byte chunks laid out
 // [k/4][chunk][lane][4] (float index f = (k%4)*R + v -> chunk f/4, slot f%4), so each LDS.128 is
 // conflict-free and all offsets from the lane's base pointer are compile-time constants.
-// Lanes with j0 >= H hold zeros.  Wht is the head matrix transposed (row o = output o, stride
-// HS = H+1 so that rows start in different banks).
+// Lanes with j0 >= H hold zeros.  Wh is the head matrix row-major [H][HP] (HP = round_up(A+2, 4)):
+// a lane that owns an output pair reads its two weights of row k with one LDS.64.
 struct FusedPackLayout {
     int H, L, A, HP, R, HS;
     size_t emb, layers, layer_stride, heads_w, heads_b, total;  // float offsets
@@ -121,14 +121,14 @@ inline FusedPackLayout make_fused_pack_layout(int H, int L, int A) {
     p.H = H; p.L = L; p.A = A;
     p.HP = (A + 2 + 3) & ~3;
     p.R = pick_neurons_per_lane(H);
-    p.HS = H + 1;
+    p.HS = p.HP;
     auto al = [](size_t x) { return (x + 3) & ~(size_t)3; };
     const int R = p.R > 0 ? p.R : 1;
     size_t o = 0;
     p.emb = o;     o = al(o + (size_t)A * H);
     p.layer_stride = al((size_t)32 * R * H + H);
     p.layers = o;  o = al(o + (size_t)L * p.layer_stride);
-    p.heads_w = o; o = al(o + (size_t)p.HP * p.HS);
+    p.heads_w = o; o = al(o + (size_t)H * p.HP);
     p.heads_b = o; o = al(o + (size_t)p.HP);
     p.total = o;
     return p;

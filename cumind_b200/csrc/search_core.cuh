@@ -451,23 +451,30 @@ CM_DEVICE void warp_layer(const float* __restrict__ Wb, const float* __restrict_
     }
 }
 
-// heads for the warp's TW trees: lane <-> (tree t, output o); out[t*HP + o] = x[:,t] @ Wht[o,:] + bh[o]
-// Wht is transposed (row o, stride HS) so the k loop walks both operands with constant offsets.
+// heads for the warp's TW trees: lane <-> (tree t, output pair q); out[t*HP + 2q..2q+1] = x[:,t] @ Wh[:,2q..2q+1] + bh
+// Wh is row-major [H][HP]: one LDS.64 fetches the pair's weights of row k, one FFMA2 advances both chains.
 template <int TW>
-CM_DEVICE void warp_heads(const float* __restrict__ Wht /*[HP][HS]*/, const float* __restrict__ bh, const float* __restrict__ x,
-                          int H, int HS, int HP, int n_out, float* __restrict__ out, int lane) {
-    for (int idx = lane; idx < TW * n_out; idx += 32) {
-        const int t = idx / n_out, o = idx - t * n_out;
+CM_DEVICE void warp_heads(const float* __restrict__ Wh /*[H][HP]*/, const float* __restrict__ bh, const float* __restrict__ x,
+                          int H, int HP, int n_out, float* __restrict__ out, int lane) {
+    const int n_pairs = (n_out + 1) >> 1;  // HP is a multiple of 4 >= n_out, so a pair never leaves the row
+    for (int idx = lane; idx < TW * n_pairs; idx += 32) {
+        const int t = idx / n_pairs, q = idx - t * n_pairs;
         const float* xp = x + t;
-        const float* wp = Wht + (size_t)o * HS;
-        float acc = 0.0f;
+        const float* wp = Wh + 2 * q;
+        float2 acc = make_float2(0.0f, 0.0f);
 #pragma unroll 1
         for (int kb = 0; kb < H; kb += 8) {
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk)
-                if (kk < 4 || kb + kk < H) acc = ffma(xp[(size_t)(kb + kk) * TW], wp[kb + kk], acc);
+            for (int kk = 0; kk < 8; ++kk) {
+                if (kk < 4 || kb + kk < H) {
+                    const float2 w = *reinterpret_cast<const float2*>(wp + (size_t)(kb + kk) * HP);
+                    acc = ffma2(xp[(size_t)(kb + kk) * TW], w, acc);
+                }
+            }
         }
-        out[t * HP + o] = fadd(acc, bh[o]);
+        const float2 bb = *reinterpret_cast<const float2*>(bh + 2 * q);
+        out[t * HP + 2 * q] = fadd(acc.x, bb.x);
+        out[t * HP + 2 * q + 1] = fadd(acc.y, bb.y);
     }
 }
 

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(512, 1) search_fused_kernel(const FusedParams 
     const int g = lane & (GS - 1);   // lane within the tree's sub-group
     const int tw = lane / GS;        // tree within the warp
     const int TPB = (blockDim.x >> 5) * TW;
-    const int H = p.pk.H, L = p.pk.L, HP = p.pk.HP, HS = p.pk.HS, A = p.tv.A, A_net = p.A_net;
+    const int H = p.pk.H, L = p.pk.L, HP = p.pk.HP, A = p.tv.A, A_net = p.A_net;
 
     // ---- stage parameters (TMA bulk) + sqrt table -------------------------------------------
     if (tid == 0) mbar_init(bar, 1);
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(512, 1) search_fused_kernel(const FusedParams 
             }
         }
         __syncwarp();
-        warp_heads<TW>(wh_s, bh_s, x0, H, HS, HP, A_net, lg_w, lane);
+        warp_heads<TW>(wh_s, bh_s, x0, H, HP, A_net, lg_w, lane);
         if (active && p.noise_mode == 2 && g == 0)
             dirichlet_row(rprior, A, p.alpha, p.seed, p.tree_base + (unsigned long long)t);
         __syncwarp();
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(512, 1) search_fused_kernel(const FusedParams 
                     }
                 }
             }
-            warp_heads<TW>(wh_s, bh_s, cur, H, HS, HP, A_net + 1, lg_w, lane);
+            warp_heads<TW>(wh_s, bh_s, cur, H, HP, A_net + 1, lg_w, lane);
             __syncwarp();
             const float ssum = softmax_prepare<GS>(lg, eb, A_net, g, active);
             if (active) {
