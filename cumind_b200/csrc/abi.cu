@@ -499,14 +499,17 @@ static int plan_fused(const cumind_tree* t, const cumind_net* n, const cumind_se
     pl.R = n->fpk.R;
     if (pl.R <= 0) { why = "hidden_dim has no lane mapping"; return 1; }
     if (t->tv.A > 65535 || t->tv.S_max > 65533) { why = "tree too large for the packed select payload"; return 1; }
-    int want = c->lanes_per_tree;
-    if (want <= 0) {
-        // lanes per tree so that the batch fills ~8 warps per SM (latency hiding), at least 4 lanes
+    // lanes per tree: measured optimum on B200 at H=64 (profiles/README.md, sweep over B x G):
+    // <= 16 trees per SM -> 16 lanes, <= 64 -> 8, more -> 4 (enough warps to hide the per-tree
+    // dependency chain without paying the per-warp select overhead for too few trees).
+    int G;
+    if (c->lanes_per_tree > 0) {
+        G = 4;
+        while (G * 2 <= c->lanes_per_tree && G < 32) G *= 2;
+    } else {
         const int tps = (B + sm - 1) / sm;
-        want = 256 / (tps > 0 ? tps : 1);
+        G = tps <= 16 ? 16 : (tps <= 64 ? 8 : 4);
     }
-    int G = 4;
-    while (G * 2 <= want && G < 32) G *= 2;
     pl.G = G;
     const int TW = 32 / G;
     const FusedPackLayout& pk = n->fpk;
