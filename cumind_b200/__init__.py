@@ -9,7 +9,7 @@ from .config import Config
 from .prng import Rngs, key
 
 __version__ = "0.1.0"
-__all__ = ["Agent", "Config", "MCTS", "Node", "CuMindNetwork", "Rngs", "key", "__version__"]
+__all__ = ["Agent", "Trainer", "Config", "MCTS", "Node", "CuMindNetwork", "Rngs", "key", "__version__"]
 
 
 def __getattr__(name):  # torch / the CUDA library are only imported when the compute classes are used
@@ -19,6 +19,9 @@ def __getattr__(name):  # torch / the CUDA library are only imported when the co
     if name in ("MCTS", "Node"):
         from . import mcts
         return getattr(mcts, name)
+    if name == "Trainer":
+        from .trainer import Trainer
+        return Trainer
     if name == "CuMindNetwork":
         from .network import CuMindNetwork
         return CuMindNetwork

@@ -680,6 +680,27 @@ extern "C" int cumind_dirichlet(double* d_noise, int32_t B, int32_t A, double al
     return 0;
 }
 
+// optax.adamw step over a flat device blob (agent.py:48, trainer.py:97-100); see train.cu.
+extern "C" int cumind_adamw_step(float* d_params, const float* d_grads, float* d_m, float* d_v, const uint8_t* d_mask, size_t n,
+                                 float lr, float b1, float b2, float eps, float weight_decay, int64_t step, float grad_scale,
+                                 void* stream) {
+    if (!d_params || !d_grads || !d_m || !d_v || step < 1) return fail("cumind_adamw_step: bad argument");
+    CM_CUDA(launch_adamw(d_params, d_grads, d_m, d_v, d_mask, n, lr, b1, b2, eps, weight_decay, step, grad_scale, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+// nnx.update(network, params) from a DEVICE blob (after an optimiser step on the GPU): copies it to the
+// host, rebuilds the kernel-side layouts and uploads them.  Synchronises `stream`.
+extern "C" int cumind_net_update_params_device(cumind_net* n, const float* d_params, size_t n_params, void* stream) {
+    if (!n || !d_params) return fail("cumind_net_update_params_device: NULL argument");
+    if (n_params != n->n_params) return fail("cumind_net_update_params_device: parameter blob has the wrong size");
+    std::vector<float> host(n_params);
+    CM_CUDA(cudaMemcpyAsync(host.data(), d_params, sizeof(float) * n_params, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return cumind_net_update_params(n, host.data(), n_params, stream);
+}
+
 extern "C" int cumind_selftest_division(uint64_t n_per_thread, uint64_t seed, int32_t max_divisor, uint64_t* d_counts2,
                                         void* stream) {
     if (!d_counts2 || max_divisor <= 0) return fail("cumind_selftest_division: bad argument");

@@ -71,6 +71,10 @@ size_t conv_tc_work_bytes(const cumind_net_desc& d, int chunk);
 cudaError_t launch_conv_encoder_tc(const NetView& nv, const unsigned char* cpack, const ConvTcPackLayout& cpk, int sm_count,
                                    const float* obs, int B, float* hidden, unsigned char* work, int chunk, cudaStream_t st);
 
+// train.cu — fused AdamW over the flat parameter blob
+cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, const unsigned char* mask, size_t n, float lr, float b1,
+                         float b2, float eps, float wd, long long step, float grad_scale, cudaStream_t st);
+
 // conv_fp32.cu — image encoder, fp32-exact (ConvEncoder, network.py:111-147)
 size_t conv_encoder_work_bytes(const cumind_net_desc& d, int chunk);
 cudaError_t launch_conv_encoder(const NetView& nv, const float* obs, int B, float* hidden, float* work, int chunk,

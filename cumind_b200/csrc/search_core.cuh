@@ -237,13 +237,10 @@ CM_DEVICE void backup_path(Node* __restrict__ nodes, const int* __restrict__ pat
 }
 
 // ------------------------------------------------------------------------------------------------
-// Network, fp32-exact mode.  Lane g of the group owns output chunks c = g + G*i (i < R/V) of V
-// consecutive neurons; each dot product is a sequential-k chain of IEEE fused multiply-adds,
-// exactly as oracle/cumind_oracle.c::cmo_linear (issued two per instruction as FFMA2 where a lane
-// owns an even number of outputs).  x lives in shared memory (one row per tree).
+// Network, fp32-exact mode: every dot product is a sequential-k chain of IEEE fused multiply-adds,
+// exactly as oracle/cumind_oracle.c::cmo_linear.  Per-tree helpers (stepwise kernels) first, then the
+// warp-cooperative tile of the fused kernel.
 // ------------------------------------------------------------------------------------------------
-template <int R> struct VecW { static constexpr int V = R >= 4 ? 4 : R; };
-
 template <int V> CM_DEVICE void load_vec(const float* p, float (&w)[V]);
 template <> CM_DEVICE void load_vec<1>(const float* p, float (&w)[1]) { w[0] = p[0]; }
 template <> CM_DEVICE void load_vec<2>(const float* p, float (&w)[2]) {
@@ -264,100 +261,6 @@ template <> CM_DEVICE void store_vec<8>(float* p, const float (&w)[8]) {
 template <> CM_DEVICE void store_vec<1>(float* p, const float (&w)[1]) { p[0] = w[0]; }
 template <> CM_DEVICE void store_vec<2>(float* p, const float (&w)[2]) { *reinterpret_cast<float2*>(p) = make_float2(w[0], w[1]); }
 template <> CM_DEVICE void store_vec<4>(float* p, const float (&w)[4]) { *reinterpret_cast<float4*>(p) = make_float4(w[0], w[1], w[2], w[3]); }
-
-// acc[R] = fma-chain over k of x[k] * W[k][own outputs]   (sequential k)
-template <int G, int R>
-CM_DEVICE void dot_rows(const float* __restrict__ W /*[H][H]*/, const float* __restrict__ x /*[H]*/, int H, int g,
-                        float (&acc)[R]) {
-    constexpr int V = VecW<R>::V;
-    constexpr int NCH = R / V;
-    if constexpr (R == 1) {
-        acc[0] = 0.0f;
-        if (g < H) {
-            for (int k = 0; k < H; ++k) acc[0] = ffma(x[k], W[(size_t)k * H + g], acc[0]);
-        }
-    } else {
-        float2 a2[R / 2];
-#pragma unroll
-        for (int i = 0; i < R / 2; ++i) a2[i] = make_float2(0.0f, 0.0f);
-#pragma unroll 2
-        for (int k4 = 0; k4 < H; k4 += 4) {
-            float xv[4];
-            load_vec<4>(x + k4, xv);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const float* wrow = W + (size_t)(k4 + kk) * H;
-#pragma unroll
-                for (int i = 0; i < NCH; ++i) {
-                    float w[V];
-                    load_vec<V>(wrow + (g + G * i) * V, w);
-#pragma unroll
-                    for (int v = 0; v < V; v += 2)
-                        a2[(i * V + v) / 2] = ffma2(xv[kk], make_float2(w[v], w[v + 1]), a2[(i * V + v) / 2]);
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < R / 2; ++i) { acc[2 * i] = a2[i].x; acc[2 * i + 1] = a2[i].y; }
-    }
-}
-
-// x_out = relu(x_in @ K + b) + x_in   (one dynamics layer, network.py:230-233)
-template <int G, int R>
-CM_DEVICE void dyn_layer(const float* __restrict__ K, const float* __restrict__ b, const float* __restrict__ xin,
-                         float* __restrict__ xout, int H, int g) {
-    constexpr int V = VecW<R>::V;
-    constexpr int NCH = R / V;
-    float acc[R];
-    dot_rows<G, R>(K, xin, H, g, acc);
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-        const int j0 = (g + G * i) * V;
-        if (R > 1 || j0 < H) {
-            float bb[V], xo[V], y[V];
-            load_vec<V>(b + j0, bb);
-            load_vec<V>(xin + j0, xo);
-#pragma unroll
-            for (int v = 0; v < V; ++v) y[v] = fadd(frelu(fadd(acc[i * V + v], bb[v])), xo[v]);
-            store_vec<V>(xout + j0, y);
-        }
-    }
-}
-
-// x = h + Emb[action]   (network.py:226-227)
-template <int G, int R>
-CM_DEVICE void embed_add(const float* __restrict__ h /*global*/, const float* __restrict__ emb_row /*smem*/,
-                         float* __restrict__ xout, int H, int g) {
-    constexpr int V = VecW<R>::V;
-    constexpr int NCH = R / V;
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-        const int j0 = (g + G * i) * V;
-        if (R > 1 || j0 < H) {
-            float hv[V], ev[V], y[V];
-            load_vec<V>(h + j0, hv);
-            load_vec<V>(emb_row + j0, ev);
-#pragma unroll
-            for (int v = 0; v < V; ++v) y[v] = fadd(hv[v], ev[v]);
-            store_vec<V>(xout + j0, y);
-        }
-    }
-}
-
-template <int G, int R>
-CM_DEVICE void copy_row(const float* __restrict__ src, float* __restrict__ dst, int H, int g) {
-    constexpr int V = VecW<R>::V;
-    constexpr int NCH = R / V;
-#pragma unroll
-    for (int i = 0; i < NCH; ++i) {
-        const int j0 = (g + G * i) * V;
-        if (R > 1 || j0 < H) {
-            float t[V];
-            load_vec<V>(src + j0, t);
-            store_vec<V>(dst + j0, t);
-        }
-    }
-}
 
 // Heads: out[o] = x @ Wh[:,o] + bh[o] for o < n_out (columns: policy 0..A-1, value A, reward A+1).
 template <int G>

@@ -1,0 +1,247 @@
+"""Train step on the GPU behind the reference's `Trainer` surface
+(src/cumind/agent/trainer.py:23-219).
+
+  Trainer.train_step()            trainer.py:83-107   sample -> prepare -> loss + grad -> AdamW -> update
+  Trainer._prepare_batch()        trainer.py:118-153  first observation / policy, K actions / rewards (zero padded)
+  n-step value targets            trainer.py:155-170  ONE batched target-network inference instead of one
+                                                      batch-1 call per sampled item
+  Trainer.compute_losses()        trainer.py:172-205  value MSE, policy CE, reward MSE over a K-step unroll,
+                                                      same value / policy target at every step, /(K+1), /K
+The unrolled forward/backward is dense library GEMM work (torch autograd over views of ONE flat fp32
+parameter tensor in the blob layout of include/cumind_b200.h); what is hand-written is the optimiser:
+`cumind_adamw_step` = optax.adamw fused with the 1/world scaling of the gradient, after one NCCL
+all-reduce of the flat gradient (the only collective in the product).  The updated blob is pushed to
+the search kernels with `cumind_net_update_params_device`.
+"""
+
+from __future__ import annotations
+
+import collections
+import ctypes as C
+import os
+import random
+from datetime import datetime
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _native, params as P
+from .checkpoint import load_checkpoint, save_checkpoint
+from .network import _stream_ptr
+
+
+class MemoryBuffer:
+    """Uniform replay of whole trajectories (src/cumind/data/memory.py:88-113, the buffer runner.train uses)."""
+
+    def __init__(self, capacity: int):
+        self.capacity = int(capacity)
+        self.buffer: collections.deque = collections.deque(maxlen=self.capacity)
+
+    def add(self, sample: Any) -> None:
+        self.buffer.append(sample)
+
+    def sample(self, batch_size: int) -> List[Any]:
+        if batch_size > len(self.buffer):
+            raise ValueError(f"Cannot sample {batch_size} items from buffer of size {len(self.buffer)}")
+        return random.sample(list(self.buffer), batch_size)
+
+    def __len__(self) -> int:
+        return len(self.buffer)
+
+    def get_pct(self) -> float:
+        return 100.0 * len(self.buffer) / self.capacity
+
+    def is_ready(self, min_size: int, min_pct: float = 0.0) -> bool:
+        return len(self.buffer) >= min_size and len(self.buffer) / self.capacity >= min_pct
+
+
+class _ParamViews:
+    """Views of a flat parameter tensor, addressed by the reference's parameter paths."""
+
+    def __init__(self, flat: torch.Tensor, dims):
+        self.leaf: Dict[Tuple[Any, ...], torch.Tensor] = {}
+        o = 0
+        for path, shape in P._schema(*dims):
+            n = int(np.prod(shape))
+            self.leaf[path] = flat[o:o + n].view(*shape)
+            o += n
+        assert o == flat.numel()
+
+    def __call__(self, *path):
+        return self.leaf[tuple(path)]
+
+
+def trainable_mask(dims) -> np.ndarray:
+    """1 for nnx.Param leaves, 0 for BatchNorm running statistics (nnx.BatchStat; never trained, trainer.py:92)."""
+    parts = []
+    for path, shape in P._schema(*dims):
+        parts.append(np.full(int(np.prod(shape)), 0 if path[-1] in ("mean", "var") else 1, dtype=np.uint8))
+    return np.concatenate(parts)
+
+
+def forward_losses(flat: torch.Tensor, dims, observations: torch.Tensor, actions: torch.Tensor, targets: Dict[str, torch.Tensor],
+                   num_unroll_steps: int) -> Dict[str, torch.Tensor]:
+    """trainer.py:172-205 as differentiable torch ops over `flat`."""
+    obs_shape, A, H, L, Cc = dims
+    w = _ParamViews(flat, dims)
+    enc = ("representation_network", "encoder")
+
+    def representation(obs):
+        x = obs
+        if len(obs_shape) == 1:
+            for i in range(L):
+                x = x @ w(*enc, "layers", i, "kernel") + w(*enc, "layers", i, "bias")
+                if i < L - 1:
+                    x = F.relu(x)
+            return x
+
+        def conv(x, name, stride):
+            k = w(*name, "kernel").permute(3, 2, 0, 1)
+            return F.conv2d(x, k, w(*name, "bias"), stride=stride, padding=1)
+
+        def bn(x, name):
+            g = w(*name, "scale") / torch.sqrt(w(*name, "var") + 1e-5)
+            return (x - w(*name, "mean")[None, :, None, None]) * g[None, :, None, None] + w(*name, "bias")[None, :, None, None]
+
+        x = F.relu(conv(obs.permute(0, 3, 1, 2), enc + ("initial_conv",), 2))
+        for i in range(L):
+            blk = enc + ("residual_blocks", i)
+            t = F.relu(bn(conv(x, blk + ("conv1",), 1), blk + ("bn1",)))
+            t = bn(conv(t, blk + ("conv2",), 1), blk + ("bn2",))
+            x = F.relu(t + x)
+        pooled = x.mean(dim=(2, 3))
+        return pooled @ w(*enc, "final_dense", "kernel") + w(*enc, "final_dense", "bias")
+
+    def prediction(h):
+        logits = h @ w("prediction_network", "policy_head", "kernel") + w("prediction_network", "policy_head", "bias")
+        value = h @ w("prediction_network", "value_head", "kernel") + w("prediction_network", "value_head", "bias")
+        return logits, value[:, 0]
+
+    def dynamics(h, a):
+        x = h + w("dynamics_network", "action_embedding", "embedding")[a]
+        for l in range(L):
+            x = F.relu(x @ w("dynamics_network", "layers", l, "kernel") + w("dynamics_network", "layers", l, "bias")) + x
+        reward = x @ w("dynamics_network", "reward_head", "kernel") + w("dynamics_network", "reward_head", "bias")
+        return x, reward[:, 0]
+
+    tv, tp, tr = targets["values"], targets["policies"], targets["rewards"]
+    h = representation(observations)
+    logits, value = prediction(h)
+    value_loss = torch.mean((value - tv) ** 2)
+    policy_loss = -torch.mean(torch.sum(tp * F.log_softmax(logits, dim=-1), dim=-1))
+    reward_loss = torch.zeros((), dtype=flat.dtype, device=flat.device)
+    K = int(num_unroll_steps)
+    for step in range(K):
+        h, reward = dynamics(h, actions[:, step].long())
+        logits, value = prediction(h)
+        reward_loss = reward_loss + torch.mean((reward - tr[:, step]) ** 2)
+        value_loss = value_loss + torch.mean((value - tv) ** 2)          # same target at every step (trainer.py:193)
+        policy_loss = policy_loss + -torch.mean(torch.sum(tp * F.log_softmax(logits, dim=-1), dim=-1))
+    if K > 0:
+        reward_loss = reward_loss / K
+        value_loss = value_loss / (K + 1)
+        policy_loss = policy_loss / (K + 1)
+    return {"value_loss": value_loss, "policy_loss": policy_loss, "reward_loss": reward_loss}
+
+
+class Trainer:
+    def __init__(self, agent, memory, config):
+        self.agent, self.memory, self.config = agent, memory, config
+        timestamp = datetime.now().strftime("%Y%m%d-%H%M%S")
+        self.checkpoint_dir = f"{config.checkpoint_root_dir}/{config.env_name}/{timestamp}"
+        self.train_step_count = 0
+        net = agent.network
+        self._dims = net._dims
+        self._lib = _native.load()
+        dev = net.device
+        self._flat = torch.as_tensor(net.blob.copy()).to(dev).requires_grad_(True)
+        st = agent.optimizer_state if isinstance(agent.optimizer_state, dict) else {}
+        self._m = torch.as_tensor(np.asarray(st["mu"], np.float32)).to(dev) if st.get("mu") is not None and np.size(st["mu"]) == self._flat.numel() else torch.zeros_like(self._flat, requires_grad=False)
+        self._v = torch.as_tensor(np.asarray(st["nu"], np.float32)).to(dev) if st.get("nu") is not None and np.size(st["nu"]) == self._flat.numel() else torch.zeros_like(self._flat, requires_grad=False)
+        self._count = int(st.get("count", 0) or 0)
+        self._mask = torch.as_tensor(trainable_mask(self._dims)).to(dev)
+
+    # ---- batch preparation (trainer.py:118-170) --------------------------------------------------
+    def _n_step_returns(self, batch: Sequence[List[Dict[str, Any]]]) -> np.ndarray:
+        n, g = self.config.td_steps, self.config.discount
+        out = np.zeros(len(batch), dtype=np.float64)
+        boot_idx, boot_obs = [], []
+        for b, item in enumerate(batch):
+            for i in range(min(len(item), n)):
+                out[b] += item[i]["reward"] * (g ** i)
+            if len(item) > n:
+                boot_idx.append(b)
+                boot_obs.append(np.asarray(item[n]["observation"], dtype=np.float32))
+        if boot_idx:  # one batched target-network call instead of one per item
+            _, _, value = self.agent.target_network.initial_inference(np.stack(boot_obs))
+            out[boot_idx] += (g ** n) * value[:, 0].double().cpu().numpy()
+        return out
+
+    def _prepare_batch(self, batch: Sequence[List[Dict[str, Any]]]):
+        K = self.config.num_unroll_steps
+        for item in batch:
+            if not item:
+                raise RuntimeError("Encountered empty item in batch.")
+        values = self._n_step_returns(batch)
+        obs = np.stack([np.asarray(item[0]["observation"], dtype=np.float32) for item in batch])
+        policies = np.stack([np.asarray(item[0]["policy"], dtype=np.float32) for item in batch])
+        actions = np.zeros((len(batch), K), dtype=np.int32)
+        rewards = np.zeros((len(batch), K), dtype=np.float32)
+        for b, item in enumerate(batch):
+            for s, step in enumerate(item[:K]):
+                actions[b, s], rewards[b, s] = step["action"], step["reward"]
+        return obs, actions, {"values": values.astype(np.float32), "rewards": rewards, "policies": policies}
+
+    # ---- the step -----------------------------------------------------------------------------------
+    def compute_losses(self, observations, actions, targets) -> Dict[str, torch.Tensor]:
+        dev = self._flat.device
+        t = {k: torch.as_tensor(np.asarray(v)).to(dev) for k, v in targets.items()}
+        return forward_losses(self._flat, self._dims, torch.as_tensor(np.asarray(observations, np.float32)).to(dev),
+                              torch.as_tensor(np.asarray(actions)).to(dev), t, self.config.num_unroll_steps)
+
+    def train_step(self, batch: Optional[Tuple[Any, Any, Dict[str, Any]]] = None) -> Dict[str, float]:
+        """One optimiser step.  `batch` = (observations, actions [B,K], targets) skips the replay sampling."""
+        if batch is None:
+            if not self.memory.is_ready(self.config.min_memory_size, self.config.min_memory_pct):
+                return {}
+            batch = self._prepare_batch(self.memory.sample(self.config.batch_size))
+        observations, actions, targets = batch
+        self._flat.grad = None
+        losses = self.compute_losses(observations, actions, targets)
+        total = losses["value_loss"] + losses["policy_loss"] + losses["reward_loss"]
+        total.backward()
+        grad = self._flat.grad
+        world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size()
+            torch.distributed.all_reduce(grad)            # one flat bucket over NCCL / NVLink
+        self._count += 1
+        opt = self.agent.optimizer
+        with torch.no_grad():
+            _native.check(self._lib.cumind_adamw_step(
+                C.c_void_p(self._flat.data_ptr()), C.c_void_p(grad.data_ptr()), C.c_void_p(self._m.data_ptr()),
+                C.c_void_p(self._v.data_ptr()), C.c_void_p(self._mask.data_ptr()), self._flat.numel(), opt.learning_rate, opt.b1,
+                opt.b2, opt.eps, opt.weight_decay, self._count, 1.0 / world, _stream_ptr()))
+            net = self.agent.network
+            _native.check(self._lib.cumind_net_update_params_device(net._handle, C.c_void_p(self._flat.data_ptr()), self._flat.numel(),
+                                                                    _stream_ptr()))
+            net._blob = self._flat.detach().cpu().numpy().copy()
+            net.params = P.unflatten(net._blob, *self._dims)
+        self.agent.optimizer_state = {"count": self._count, "mu": self._m.cpu().numpy(), "nu": self._v.cpu().numpy()}
+        self.train_step_count += 1
+        out = {f"train/{k}": float(v.detach()) for k, v in losses.items()}
+        out["total_loss"] = float(total.detach())
+        return out
+
+    # ---- checkpoints (trainer.py:207-219) ------------------------------------------------------------
+    def save_checkpoint(self, episode: int) -> str:
+        os.makedirs(self.checkpoint_dir, exist_ok=True)
+        path = f"{self.checkpoint_dir}/episode_{episode:05d}.pkl"
+        save_checkpoint(self.agent.save_state(), path)
+        return path
+
+    def load_checkpoint(self, path: str) -> None:
+        self.agent.load_state(load_checkpoint(path))
+        self._flat.data.copy_(torch.as_tensor(self.agent.network.blob).to(self._flat.device))

@@ -220,6 +220,16 @@ int cumind_finalize(cumind_tree* tree, const cumind_search_cfg* cfg, int32_t* d_
 int cumind_dirichlet(double* d_noise, int32_t B, int32_t A, double alpha, uint64_t seed,
                      uint64_t tree_index_base, void* stream);
 
+/* Train-step support (trainer.py:97-100, agent.py:48).
+ * cumind_adamw_step: optax.adamw over a flat fp32 device blob, fused with the 1/world scaling of an
+ *   all-reduced gradient (grad_scale); d_mask (uint8, may be NULL) is 0 for leaves that are not
+ *   trained (BatchNorm running statistics).  `step` counts from 1.
+ * cumind_net_update_params_device: nnx.update(network, params) from a device blob. */
+int cumind_adamw_step(float* d_params, const float* d_grads, float* d_m, float* d_v, const uint8_t* d_mask,
+                      size_t n, float lr, float b1, float b2, float eps, float weight_decay, int64_t step,
+                      float grad_scale, void* stream);
+int cumind_net_update_params_device(cumind_net* net, const float* d_params, size_t n_params, void* stream);
+
 /* Diagnostic: checks the table-driven small-divisor division used by the fused select kernel
  * (a/d from RN(1/d) with two FMA residual corrections) against the IEEE division on the device,
  * bitwise, over 148*4*256*n_per_thread random and structured numerators and divisors 1..max_divisor.

@@ -1,0 +1,138 @@
+"""Train step: the NumPy oracle's hand-written backward pass against finite differences (CPU),
+and the GPU step (torch autograd over the flat blob + cumind_adamw_step) against the oracle.
+Tolerances: gradients rtol 1e-4 (fp32 GEMM reductions vs float64), AdamW update rtol 1e-5."""
+
+import numpy as np
+import pytest
+
+from oracle import network_np as nn
+from oracle import train_np as tn
+
+
+def _problem(B=24, A=3, H=16, L=2, K=3, D=5, seed=0):
+    rng = np.random.default_rng(seed)
+    params = nn.random_params((D,), A, H, L, 32, seed, bias_scale=0.1)
+    obs = rng.standard_normal((B, D)).astype(np.float32)
+    actions = rng.integers(0, A, size=(B, K)).astype(np.int32)
+    pol = rng.dirichlet([0.5] * A, size=B).astype(np.float32)
+    targets = {"values": rng.standard_normal(B).astype(np.float32), "rewards": rng.standard_normal((B, K)).astype(np.float32), "policies": pol}
+    return params, obs, actions, targets, (D, A, H, L, K)
+
+
+def test_oracle_backward_matches_finite_differences():
+    params, obs, actions, targets, (D, A, H, L, K) = _problem()
+    total, losses, grads = tn.loss_and_grad(params, obs, actions, targets, K)
+    assert abs(total - sum(losses.values())) < 1e-12
+    flat = nn.flatten_params(params, (D,)).astype(np.float64)
+    gflat = nn.flatten_params(grads, (D,)) if False else np.concatenate([np.asarray(a, np.float64).reshape(-1) for a in _leaves(grads, (D,))])
+    rng = np.random.default_rng(1)
+    from cumind_b200 import params as P
+
+    for idx in rng.choice(flat.size, size=40, replace=False):
+        def loss_at(delta):
+            f2 = flat.copy()
+            f2[idx] += delta
+            tree = P.unflatten(f2.astype(np.float32), (D,), A, H, L, 32)
+            tree = _as64(tree, f2, (D,), A, H, L)
+            return tn.loss_and_grad(tree, obs, actions, targets, K)[0]
+        eps = 1e-5
+        fd = (loss_at(eps) - loss_at(-eps)) / (2 * eps)
+        assert abs(fd - gflat[idx]) <= 1e-6 + 1e-4 * abs(fd), (idx, fd, gflat[idx])
+
+
+def _leaves(tree, obs_shape):
+    from cumind_b200 import params as P
+
+    A, H = tree["dynamics_network"]["action_embedding"]["embedding"].shape
+    L = len(tree["dynamics_network"]["layers"])
+    return [P._get(tree, path) for path, _ in P._schema(obs_shape, A, H, L, 32)]
+
+
+def _as64(tree, flat64, obs_shape, A, H, L):
+    """Parameter tree whose leaves are float64 views of flat64 (so a 1e-5 perturbation is not rounded away)."""
+    from cumind_b200 import params as P
+
+    out, o = {}, 0
+    for path, shape in P._schema(obs_shape, A, H, L, 32):
+        n = int(np.prod(shape))
+        P._set(out, path, flat64[o:o + n].reshape(shape))
+        o += n
+    return out
+
+
+@pytest.mark.gpu
+def test_gpu_train_step_matches_the_oracle():
+    import torch
+
+    from cumind_b200 import Agent, Config
+    from cumind_b200 import params as P
+    from cumind_b200.trainer import MemoryBuffer, Trainer
+
+    params, obs, actions, targets, (D, A, H, L, K) = _problem(B=64, A=2, H=32, L=2, K=5, D=4, seed=3)
+    cfg = Config(hidden_dim=H, num_blocks=L, action_space_size=A, observation_shape=(D,), num_unroll_steps=K, learning_rate=1e-2,
+                 weight_decay=1e-4, num_simulations=5)
+    agent = Agent(cfg)
+    agent.load_state({"network_state": params, "optimizer_state": {"count": 0}})
+    trainer = Trainer(agent, MemoryBuffer(10), cfg)
+    want_total, want_losses, want_grads = tn.loss_and_grad(params, obs, actions, targets, K)
+    losses = trainer.compute_losses(obs, actions, targets)
+    for k in want_losses:
+        assert abs(float(losses[k].detach()) - want_losses[k]) <= 1e-5 * max(1.0, abs(want_losses[k])), k
+    before = agent.network.blob.copy()
+    info = trainer.train_step((obs, actions, targets))
+    assert abs(info["total_loss"] - want_total) <= 1e-5 * max(1.0, abs(want_total))
+    g_gpu = trainer._flat.grad.cpu().numpy().astype(np.float64)
+    g_ref = np.concatenate([np.asarray(a, np.float64).reshape(-1) for a in _leaves(want_grads, (D,))])
+    scale = np.abs(g_ref).max()
+    assert np.all(np.abs(g_gpu - g_ref) <= 1e-4 * np.abs(g_ref) + 1e-6 * scale)
+    want_p, _, _ = tn.adamw(before.astype(np.float64), g_ref, np.zeros_like(g_ref), np.zeros_like(g_ref), 1, cfg.learning_rate, cfg.weight_decay)
+    after = agent.network.blob.astype(np.float64)
+    assert np.all(np.abs(after - want_p) <= 1e-5 * np.abs(want_p) + 1e-6)
+    assert not np.array_equal(after, before)
+    # the search kernels see the new parameters
+    h_new, _, _ = agent.network.initial_inference(obs[:4])
+    net2 = agent.network.clone()
+    assert np.array_equal(net2.initial_inference(obs[:4])[0].cpu().numpy(), h_new.cpu().numpy())
+    # a few more steps reduce the loss on the same batch
+    first = info["total_loss"]
+    for _ in range(30):
+        info = trainer.train_step((obs, actions, targets))
+    assert info["total_loss"] < first
+    assert agent.optimizer_state["count"] == 31
+
+
+@pytest.mark.gpu
+def test_trainer_runs_from_replay_with_bootstrapped_targets_and_image_observations():
+    from cumind_b200 import Agent, Config
+    from cumind_b200.envs import CartPoleVec
+    from cumind_b200.self_play import SelfPlay
+    from cumind_b200.trainer import MemoryBuffer, Trainer
+
+    cfg = Config(hidden_dim=32, num_simulations=6, batch_size=16, td_steps=3, num_unroll_steps=3, min_memory_size=4)
+    agent = Agent(cfg)
+    memory = MemoryBuffer(200)
+    per_env = SelfPlay(agent, memory).run_batch(CartPoleVec(32, seed=2), num_steps=25, philox_seed=4)
+    for eps in per_env:                       # unfinished tails are trajectories too
+        for ep in eps:
+            if len(ep) > 1:
+                memory.add(ep)
+    trainer = Trainer(agent, memory, cfg)
+    info = trainer.train_step()
+    assert np.isfinite(info["total_loss"]) and set(info) >= {"total_loss", "train/value_loss", "train/policy_loss", "train/reward_loss"}
+    # image observations: conv trunk + BatchNorm (running statistics stay fixed)
+    icfg = Config(hidden_dim=16, observation_shape=(12, 12, 3), action_space_size=3, conv_channels=8, num_unroll_steps=2, num_simulations=4)
+    iagent = Agent(icfg)
+    itr = Trainer(iagent, MemoryBuffer(4), icfg)
+    rng = np.random.default_rng(0)
+    batch = (rng.random((8, 12, 12, 3)).astype(np.float32), rng.integers(0, 3, size=(8, 2)).astype(np.int32),
+             {"values": rng.standard_normal(8).astype(np.float32), "rewards": rng.standard_normal((8, 2)).astype(np.float32),
+              "policies": rng.dirichlet([1.0] * 3, size=8).astype(np.float32)})
+    before = iagent.network.blob.copy()
+    l0 = itr.train_step(batch)["total_loss"]
+    for _ in range(20):
+        l1 = itr.train_step(batch)["total_loss"]
+    assert np.isfinite(l1) and l1 < l0
+    from cumind_b200.trainer import trainable_mask
+    mask = trainable_mask(iagent.network._dims).astype(bool)
+    after = iagent.network.blob
+    assert np.array_equal(after[~mask], before[~mask]) and not np.array_equal(after[mask], before[mask])
