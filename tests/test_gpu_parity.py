@@ -423,3 +423,44 @@ def test_error_paths_raise_python_exceptions():
     probs, visits = m.search_batch(np.zeros((9, 16), np.float32), philox_seed=5)
     assert np.allclose(probs.sum(axis=1), 1.0)
     assert torch.cuda.is_available() and _native.launch_count() > 0
+
+
+def test_fine_grained_phase_entry_points_compose_to_the_search():
+    """cumind_tree_init_root / _select / _expand / _backup / _finalize called one by one through the C ABI
+    (the way ncu attributes time per phase) give the oracle's trees and outputs."""
+    import ctypes as C
+
+    import torch
+
+    from cumind_b200 import _native
+    from cumind_b200.mcts import MCTS, _TreeSlab
+    from oracle import network_np as nn
+
+    A, H, S, B = 3, 32, 9, 77
+    blob = nn.flatten_params(nn.random_params((4,), A, H, 2, 32, 13, bias_scale=0.05), (4,))
+    net = _network((4,), A, H, 2, 32, blob)
+    rng = np.random.default_rng(4)
+    h = rng.standard_normal((B, H)).astype(np.float32)
+    noise = rng.dirichlet([0.3] * A, size=B)
+    o = lo.search(lo.make_desc((4,), A, H, 2), blob, h, S, A, 1.25, 0.25, noise)
+    lib = _native.load()
+    mcts = MCTS(net, _Cfg(S, A))
+    tree = mcts._tree(B, S, A)
+    cfg = mcts._cfg(1)
+    dev = net.device
+    d_h, d_noise = torch.as_tensor(h).to(dev), torch.as_tensor(noise).to(dev)
+    leaf_value = torch.empty(B, dtype=torch.float32, device=dev)
+    visits = torch.empty((B, A), dtype=torch.int32, device=dev)
+    probs = torch.empty((B, A), dtype=torch.float64, device=dev)
+    rootv = torch.empty(B, dtype=torch.float64, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    _native.check(lib.cumind_tree_init_root(tree.handle, net._handle, p(d_h), C.byref(cfg), p(d_noise), None))
+    for s in range(S):
+        _native.check(lib.cumind_select(tree.handle, C.byref(cfg), None))
+        _native.check(lib.cumind_expand(tree.handle, net._handle, C.byref(cfg), p(leaf_value), None))
+        _native.check(lib.cumind_backup(tree.handle, p(leaf_value), None))
+    _native.check(lib.cumind_finalize(tree.handle, C.byref(cfg), p(visits), p(probs), p(rootv), None))
+    torch.cuda.synchronize()
+    _assert_trees_equal(mcts, o, S, A)
+    assert np.array_equal(visits.cpu().numpy(), o["out_visits"]) and np.array_equal(probs.cpu().numpy(), o["out_probs"])
+    assert hp.bits_equal(rootv.cpu().numpy(), o["out_root_value"])
