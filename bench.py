@@ -360,7 +360,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
         traffic = json.load(open(tpath)).get("search_fused_dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "search_fused_kernel", "kernel_ms": kern_ms_mean, "algorithmic_bytes_per_sim": algorithmic_bytes_per_sim(dbar),
-                "mean_path_length": dbar, "peak_source": peak_src}
+                "mean_path_length": dbar, "peak_source": peak_src, "encoder_ms": enc_ms_mean}
     if WORKLOAD != "cartpole":
         # image workload: the conv trunk dominates and is tensor-pipe bound
         tf_peak = float(json.load(open(peaks_path)).get("bf16_tflops", 1590.0)) if os.path.exists(peaks_path) else 1590.0

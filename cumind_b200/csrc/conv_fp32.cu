@@ -120,6 +120,7 @@ __global__ void pool_dense_kernel(const float* __restrict__ x, int npix, int Cc,
     __syncthreads();
     for (int j = threadIdx.x; j < H; j += blockDim.x) {
         float acc = 0.0f;
+#pragma unroll 8
         for (int k = 0; k < Cc; ++k) acc = ffma(pooled[k], K[(size_t)k * H + j], acc);
         hidden[(size_t)img * H + j] = fadd(acc, b[j]);
     }

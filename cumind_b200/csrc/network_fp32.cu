@@ -17,9 +17,84 @@ CM_DEVICE void linear_any(const float* __restrict__ K, const float* __restrict__
                           int out, float* __restrict__ y, bool relu, int lane) {
     for (int j = lane; j < out; j += 32) {
         float acc = 0.0f;
+#pragma unroll 8
         for (int k = 0; k < in; ++k) acc = ffma(x[k], K[(size_t)k * out + j], acc);
         const float v = fadd(acc, b[j]);
         y[j] = relu ? frelu(v) : v;
+    }
+}
+
+// VectorEncoder for 4 rows per warp with the fused kernel's FFMA2 tile: all layer parameters staged in
+// shared memory once per CTA (row-major [in][H]), activations k-major with the 4 rows interleaved, lane
+// owns R consecutive neurons of every row; persistent CTAs loop over row quads.  Same sequential-k FMA
+// chain per (row, neuron) as cmo_linear, so the result is bit-identical to the warp-per-row kernel.
+template <int R>
+__global__ void __launch_bounds__(256) vector_encoder_tile_kernel(const float* __restrict__ enc, int n_enc, int D, int H, int L,
+                                                                   const float* __restrict__ obs, int B, float* __restrict__ hidden) {
+    constexpr int TW = 4;
+    extern __shared__ __align__(16) float sm[];
+    float* w_s = sm;                                           // encoder parameters
+    const int M = D > H ? D : H;
+    float* xbuf = sm + ((n_enc + 3) & ~3) + (size_t)(threadIdx.x >> 5) * 2 * M * TW;
+    for (int i = threadIdx.x; i < n_enc; i += blockDim.x) w_s[i] = enc[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int j0 = lane * R;
+    const int n_quads = (B + TW - 1) / TW;
+    for (int q = blockIdx.x * nwarps + warp; q < n_quads; q += gridDim.x * nwarps) {
+        float* a = xbuf;
+        float* c = xbuf + (size_t)M * TW;
+        for (int idx = lane; idx < D * TW; idx += 32) {          // a[k][t] = obs[row t][k]
+            const int k = idx / TW, t = idx - k * TW;
+            const int r = q * TW + t;
+            a[idx] = r < B ? obs[(size_t)r * D + k] : 0.0f;
+        }
+        __syncwarp();
+        const float* p = w_s;
+        int in = D;
+        for (int i = 0; i < L; ++i) {
+            if (j0 < H) {
+                WarpAcc<TW, R> acc;
+                acc.zero();
+#pragma unroll 4
+                for (int k = 0; k < in; ++k) {
+                    float xk[TW], w[R];
+                    load_vec<TW>(a + (size_t)k * TW, xk);
+                    load_vec<R>(p + (size_t)k * H + j0, w);
+                    if constexpr (R >= 2) {
+#pragma unroll
+                        for (int t = 0; t < TW; ++t)
+#pragma unroll
+                            for (int v = 0; v < R; v += 2)
+                                acc.v[t * (R / 2) + v / 2] = ffma2(xk[t], make_float2(w[v], w[v + 1]), acc.v[t * (R / 2) + v / 2]);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < TW; t += 2) acc.v[t / 2] = ffma2(w[0], make_float2(xk[t], xk[t + 1]), acc.v[t / 2]);
+                    }
+                }
+                const float* bias = p + (size_t)in * H;
+#pragma unroll
+                for (int v = 0; v < R; ++v) {
+                    float y[TW];
+#pragma unroll
+                    for (int t = 0; t < TW; ++t) {
+                        const float z = fadd(acc.get(t, v), bias[j0 + v]);
+                        y[t] = (i < L - 1) ? frelu(z) : z;
+                    }
+                    store_vec<TW>(c + (size_t)(j0 + v) * TW, y);
+                }
+            }
+            __syncwarp();
+            p += (size_t)in * H + H;
+            in = H;
+            float* tmp = a; a = c; c = tmp;
+        }
+        for (int idx = lane; idx < H * TW; idx += 32) {          // hidden[row t][j] = a[j][t]
+            const int t = idx / H, j = idx - t * H;
+            const int r = q * TW + t;
+            if (r < B) hidden[(size_t)r * H + j] = a[(size_t)j * TW + t];
+        }
+        __syncwarp();
     }
 }
 
@@ -84,6 +159,7 @@ __global__ void __launch_bounds__(kWarps * 32) recurrent_kernel(const float* __r
                 const float* b = pack + pk.layer_b(l);
                 for (int j = lane; j < H; j += 32) {
                     float acc = 0.0f;
+#pragma unroll 8
                     for (int k = 0; k < H; ++k) acc = ffma(cur[k], K[(size_t)k * H + j], acc);
                     nxt[j] = fadd(frelu(fadd(acc, b[j])), cur[j]);
                 }
@@ -129,9 +205,34 @@ static cudaError_t set_smem(const void* fn, size_t smem) {
     return cudaSuccess;
 }
 
+template <int R>
+static cudaError_t launch_encoder_tile(const NetView& nv, const float* obs, int B, float* hidden, size_t smem, int n_enc, cudaStream_t st) {
+    const int D = nv.desc.obs_shape[0], H = nv.desc.hidden_dim, L = nv.desc.num_blocks;
+    cudaError_t e = cudaFuncSetAttribute(vector_encoder_tile_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int quads = (B + 3) / 4;
+    int grid = (quads + 7) / 8;
+    if (grid > 148 * 2) grid = 148 * 2;
+    vector_encoder_tile_kernel<R><<<grid, 256, smem, st>>>(nv.blob + nv.lo.enc, n_enc, D, H, L, obs, B, hidden);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_vector_encoder(const NetView& nv, const float* obs, int B, float* hidden, cudaStream_t st) {
     const int D = nv.desc.obs_shape[0], H = nv.desc.hidden_dim, L = nv.desc.num_blocks;
     const int M = D > H ? D : H;
+    {   // tile kernel when the parameters fit shared memory and H maps onto R neurons per lane
+        const int n_enc = (int)((size_t)D * H + H + (size_t)(L - 1) * ((size_t)H * H + H));
+        const size_t smem_t = ((size_t)((n_enc + 3) & ~3) + (size_t)8 * 2 * M * 4) * sizeof(float);
+        const int R = pick_neurons_per_lane(H);
+        if (R > 0 && smem_t <= 200 * 1024 && B >= 64) {
+            switch (R) {
+                case 1: return launch_encoder_tile<1>(nv, obs, B, hidden, smem_t, n_enc, st);
+                case 2: return launch_encoder_tile<2>(nv, obs, B, hidden, smem_t, n_enc, st);
+                case 4: return launch_encoder_tile<4>(nv, obs, B, hidden, smem_t, n_enc, st);
+                case 8: return launch_encoder_tile<8>(nv, obs, B, hidden, smem_t, n_enc, st);
+            }
+        }
+    }
     const size_t smem = (size_t)kWarps * 2 * M * sizeof(float);
     cudaError_t e = set_smem((const void*)vector_encoder_kernel, smem);
     if (e != cudaSuccess) return e;

@@ -8,10 +8,10 @@
 // advances through its S simulations independently of all others.
 //
 // Reference semantics reproduced here (src/cumind/core/mcts.py):
-//   select_leaf   <- MCTS._simulate selection loop 165-171, Node.select_child 67-76, ucb_score 51-65
-//   dyn_layer ... <- DynamicsNetwork.__call__ network.py:217-236, PredictionNetwork.__call__ 254-266
-//   expand_leaf   <- Node.expand 78-89 (children get the fp32 softmax priors)
-//   backup_path   <- mcts.py:199-203 (parents only; the root a second time)
+//   select_leaf*            <- MCTS._simulate selection loop 165-171, Node.select_child 67-76, ucb_score 51-65
+//   warp_layer / warp_heads <- DynamicsNetwork.__call__ network.py:217-236, PredictionNetwork.__call__ 254-266
+//   softmax_prepare         <- jax.nn.softmax mcts.py:128,191 (children get the fp32 priors, Node.expand 78-89)
+//   backup_path             <- mcts.py:199-203 (parents only; the root a second time)
 #pragma once
 
 #include "common.cuh"
@@ -268,6 +268,7 @@ CM_DEVICE void heads(const float* __restrict__ Wh /*[H][HP]*/, const float* __re
                      int H, int HP, int n_out, float* __restrict__ out, int g) {
     for (int o = g; o < n_out; o += G) {
         float acc = 0.0f;
+#pragma unroll 8
         for (int k = 0; k < H; ++k) acc = ffma(x[k], Wh[(size_t)k * HP + o], acc);
         out[o] = fadd(acc, bh[o]);
     }

@@ -18,6 +18,7 @@ CM_DEVICE void dyn_layer_any(const float* __restrict__ K, const float* __restric
                              float* __restrict__ xout, int H, int lane) {
     for (int j = lane; j < H; j += 32) {
         float acc = 0.0f;
+#pragma unroll 8
         for (int k = 0; k < H; ++k) acc = ffma(xin[k], K[(size_t)k * H + j], acc);
         xout[j] = fadd(frelu(fadd(acc, b[j])), xin[j]);
     }
