@@ -20,7 +20,7 @@ EXPORTS = [
     "cumind_tree_bytes", "cumind_tree_create", "cumind_tree_destroy", "cumind_tree_get_view", "cumind_search",
     "cumind_search_plan", "cumind_search_stepwise", "cumind_select_actions_work_bytes", "cumind_select_actions_host",
     "cumind_tree_init_root", "cumind_select", "cumind_expand", "cumind_backup", "cumind_finalize", "cumind_dirichlet",
-    "cumind_launch_count", "cumind_selftest_division", "cumind_adamw_step", "cumind_net_update_params_device",
+    "cumind_launch_count", "cumind_selftest_division", "cumind_adamw_step", "cumind_adamw_step_dev", "cumind_net_update_params_device",
 ]
 
 NET_FP32_EXACT = 0
@@ -105,6 +105,7 @@ def load():
     lib.cumind_selftest_division.argtypes = [u64, u64, i32, vp, vp]
     f32 = C.c_float
     lib.cumind_adamw_step.argtypes = [vp, vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, C.c_int64, f32, vp]
+    lib.cumind_adamw_step_dev.argtypes = [vp, vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, vp, f32, vp]
     lib.cumind_net_update_params_device.argtypes = [vp, vp, sz, vp]
     _lib = lib
     return lib

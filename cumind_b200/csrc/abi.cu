@@ -33,8 +33,9 @@ struct cumind_net {
     FusedPackLayout fpk;
     float* d_work;        // activation workspace of the image encoder (lazily sized, grow-only)
     size_t work_bytes;
-    std::vector<float> h_pack, h_fpack;
-    std::vector<unsigned char> h_tcpack, h_cpack;
+    int *d_pack_map, *d_fpack_map, *d_tc_half_map, *d_tc_f32_map, *d_c_half_map;
+    BnFold* d_folds;
+    int n_folds;
 };
 
 struct cumind_tree {
@@ -79,131 +80,146 @@ static NetView view_of(const cumind_net* n) {
     return v;
 }
 
-// canonical blob -> PackLayout (emb | layers | heads [H][HP] | head biases)
-static void build_pack(const cumind_net* n, const float* blob, std::vector<float>& pack) {
+// ------------------------------------------------------------------------------------------------
+// Kernel-side parameter layouts are rebuilt ON THE DEVICE from the canonical blob: at create time the
+// host only computes index maps (destination element -> blob index, -1 = zero padding, -2 = leave
+// alone) and BatchNorm-fold records; every parameter update is then a blob copy plus a few gather
+// kernels on the caller's stream (no host round trip, capturable in a CUDA graph).
+// ------------------------------------------------------------------------------------------------
+static void build_pack_map(const cumind_net* n, std::vector<int>& m) {
     const PackLayout& pk = n->pk;
     const BlobLayout& lo = n->lo;
     const int H = pk.H, L = pk.L, A = pk.A, HP = pk.HP;
-    pack.assign(pk.total, 0.0f);
-    memcpy(&pack[pk.emb], blob + lo.emb, sizeof(float) * (size_t)A * H);
-    memcpy(&pack[pk.layers], blob + lo.dyn, sizeof(float) * (size_t)L * ((size_t)H * H + H));
+    m.assign(pk.total, -1);
+    for (size_t i = 0; i < (size_t)A * H; ++i) m[pk.emb + i] = (int)(lo.emb + i);
+    for (size_t i = 0; i < (size_t)L * ((size_t)H * H + H); ++i) m[pk.layers + i] = (int)(lo.dyn + i);
     for (int k = 0; k < H; ++k) {
-        for (int a = 0; a < A; ++a) pack[pk.heads_w + (size_t)k * HP + a] = blob[lo.pol_k + (size_t)k * A + a];
-        pack[pk.heads_w + (size_t)k * HP + A] = blob[lo.val_k + k];
-        pack[pk.heads_w + (size_t)k * HP + A + 1] = blob[lo.rew_k + k];
+        for (int a = 0; a < A; ++a) m[pk.heads_w + (size_t)k * HP + a] = (int)(lo.pol_k + (size_t)k * A + a);
+        m[pk.heads_w + (size_t)k * HP + A] = (int)(lo.val_k + k);
+        m[pk.heads_w + (size_t)k * HP + A + 1] = (int)(lo.rew_k + k);
     }
-    for (int a = 0; a < A; ++a) pack[pk.heads_b + a] = blob[lo.pol_b + a];
-    pack[pk.heads_b + A] = blob[lo.val_b];
-    pack[pk.heads_b + A + 1] = blob[lo.rew_b];
+    for (int a = 0; a < A; ++a) m[pk.heads_b + a] = (int)(lo.pol_b + a);
+    m[pk.heads_b + A] = (int)lo.val_b;
+    m[pk.heads_b + A + 1] = (int)lo.rew_b;
 }
 
-// canonical blob -> FusedPackLayout (lane-blocked layer kernels, transposed heads)
-static void build_fused_pack(const cumind_net* n, const float* blob, std::vector<float>& fp) {
+// FusedPackLayout: lane-blocked layer kernels, row-major heads
+static void build_fused_map(const cumind_net* n, std::vector<int>& m) {
     const FusedPackLayout& pk = n->fpk;
     const BlobLayout& lo = n->lo;
     const int H = pk.H, L = pk.L, A = pk.A, R = pk.R > 0 ? pk.R : 1;
-    fp.assign(pk.total, 0.0f);
-    memcpy(&fp[pk.emb], blob + lo.emb, sizeof(float) * (size_t)A * H);
+    m.assign(pk.total, -1);
+    for (size_t i = 0; i < (size_t)A * H; ++i) m[pk.emb + i] = (int)(lo.emb + i);
     for (int l = 0; l < L; ++l) {
-        const float* K = blob + lo.dyn + (size_t)l * ((size_t)H * H + H);
-        const float* b = K + (size_t)H * H;
+        const size_t K = lo.dyn + (size_t)l * ((size_t)H * H + H);
         if (pk.R > 0) {
             for (int k = 0; k < H; ++k)
                 for (int lane = 0; lane < 32; ++lane)
                     for (int v = 0; v < R; ++v) {
                         const int j = lane * R + v;
-                        if (j < H) fp[pk.layer_w(l) + FusedPackLayout::w_index(k, lane, v, R)] = K[(size_t)k * H + j];
+                        if (j < H) m[pk.layer_w(l) + FusedPackLayout::w_index(k, lane, v, R)] = (int)(K + (size_t)k * H + j);
                     }
         }
-        memcpy(&fp[pk.layer_b(l)], b, sizeof(float) * H);
+        for (int j = 0; j < H; ++j) m[pk.layer_b(l) + j] = (int)(K + (size_t)H * H + j);
     }
     for (int k = 0; k < H; ++k) {
-        for (int a = 0; a < A; ++a) fp[pk.heads_w + (size_t)k * pk.HP + a] = blob[lo.pol_k + (size_t)k * A + a];
-        fp[pk.heads_w + (size_t)k * pk.HP + A] = blob[lo.val_k + k];
-        fp[pk.heads_w + (size_t)k * pk.HP + A + 1] = blob[lo.rew_k + k];
+        for (int a = 0; a < A; ++a) m[pk.heads_w + (size_t)k * pk.HP + a] = (int)(lo.pol_k + (size_t)k * A + a);
+        m[pk.heads_w + (size_t)k * pk.HP + A] = (int)(lo.val_k + k);
+        m[pk.heads_w + (size_t)k * pk.HP + A + 1] = (int)(lo.rew_k + k);
     }
-    for (int a = 0; a < A; ++a) fp[pk.heads_b + a] = blob[lo.pol_b + a];
-    fp[pk.heads_b + A] = blob[lo.val_b];
-    fp[pk.heads_b + A + 1] = blob[lo.rew_b];
+    for (int a = 0; a < A; ++a) m[pk.heads_b + a] = (int)(lo.pol_b + a);
+    m[pk.heads_b + A] = (int)lo.val_b;
+    m[pk.heads_b + A + 1] = (int)lo.rew_b;
 }
 
-// fp32 -> bf16, round to nearest even (NaN kept quiet)
-static inline uint16_t to_bf16(float f) {
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
-    const uint32_t lsb = (u >> 16) & 1u;
-    u += 0x7fffu + lsb;
-    return (uint16_t)(u >> 16);
-}
-
-// canonical blob -> TcPackLayout
-static void build_tc_pack(const cumind_net* n, const float* blob, std::vector<unsigned char>& tp) {
+// TcPackLayout: bf16 tiles over [0, bias_off) (map in 2-byte units), fp32 over [bias_off, total) (4-byte units)
+static void build_tc_maps(const cumind_net* n, std::vector<int>& half_map, std::vector<int>& f32_map) {
     const TcPackLayout& pk = n->tpk;
     const BlobLayout& lo = n->lo;
     const int H = pk.H, L = pk.L, A = pk.A, NP = pk.NP;
-    tp.assign(pk.total_bytes, 0);
+    half_map.assign(pk.bias_off / 2, -1);
+    f32_map.assign((pk.total_bytes - pk.bias_off) / 4, -1);
+    auto f32_at = [&](size_t byte_off) -> int& { return f32_map[(byte_off - pk.bias_off) / 4]; };
     for (int l = 0; l < L; ++l) {
-        const float* K = blob + lo.dyn + (size_t)l * ((size_t)H * H + H);
-        unsigned char* tile = tp.data() + pk.layer_off + (size_t)l * H * H * 2;
+        const size_t K = lo.dyn + (size_t)l * ((size_t)H * H + H);
+        const size_t tile = pk.layer_off + (size_t)l * H * H * 2;
         for (int k = 0; k < H; ++k)
-            for (int j = 0; j < H; ++j) {
-                const uint16_t v = to_bf16(K[(size_t)k * H + j]);
-                memcpy(tile + tc_tile_offset_host(j, k, H), &v, 2);
-            }
-        memcpy(tp.data() + pk.bias_off + (size_t)l * H * 4, K + (size_t)H * H, (size_t)H * 4);
+            for (int j = 0; j < H; ++j) half_map[(tile + tc_tile_offset_host(j, k, H)) / 2] = (int)(K + (size_t)k * H + j);
+        for (int j = 0; j < H; ++j) f32_at(pk.bias_off + ((size_t)l * H + j) * 4) = (int)(K + (size_t)H * H + j);
     }
-    unsigned char* ht = tp.data() + pk.heads_off;
-    float* bh = reinterpret_cast<float*>(tp.data() + pk.bh_off);
     for (int k = 0; k < H; ++k) {
-        for (int a = 0; a < A; ++a) { const uint16_t v = to_bf16(blob[lo.pol_k + (size_t)k * A + a]); memcpy(ht + tc_tile_offset_host(a, k, NP), &v, 2); }
-        const uint16_t vv = to_bf16(blob[lo.val_k + k]), vr = to_bf16(blob[lo.rew_k + k]);
-        memcpy(ht + tc_tile_offset_host(A, k, NP), &vv, 2);
-        memcpy(ht + tc_tile_offset_host(A + 1, k, NP), &vr, 2);
+        for (int a = 0; a < A; ++a) half_map[(pk.heads_off + tc_tile_offset_host(a, k, NP)) / 2] = (int)(lo.pol_k + (size_t)k * A + a);
+        half_map[(pk.heads_off + tc_tile_offset_host(A, k, NP)) / 2] = (int)(lo.val_k + k);
+        half_map[(pk.heads_off + tc_tile_offset_host(A + 1, k, NP)) / 2] = (int)(lo.rew_k + k);
     }
-    for (int a = 0; a < A; ++a) bh[a] = blob[lo.pol_b + a];
-    bh[A] = blob[lo.val_b];
-    bh[A + 1] = blob[lo.rew_b];
-    memcpy(tp.data() + pk.emb_off, blob + lo.emb, (size_t)A * H * 4);
+    for (int a = 0; a < A; ++a) f32_at(pk.bh_off + (size_t)a * 4) = (int)(lo.pol_b + a);
+    f32_at(pk.bh_off + (size_t)A * 4) = (int)lo.val_b;
+    f32_at(pk.bh_off + (size_t)(A + 1) * 4) = (int)lo.rew_b;
+    for (size_t i = 0; i < (size_t)A * H; ++i) f32_at(pk.emb_off + i * 4) = (int)(lo.emb + i);
 }
 
-// canonical blob -> ConvTcPackLayout (bias + inference BatchNorm folded into gain / shift)
-static void build_conv_tc_pack(const cumind_net* n, const float* blob, std::vector<unsigned char>& cp) {
+// ConvTcPackLayout: bf16 tiles (map in 2-byte units over the whole pack, -2 over the fp32 gain/shift
+// regions) + one BatchNorm-fold record per output channel of every conv layer
+static void build_conv_maps(const cumind_net* n, std::vector<int>& half_map, std::vector<BnFold>& folds) {
     const ConvTcPackLayout& pk = n->cpk;
     const int C = n->desc.obs_shape[2], Cc = n->desc.conv_channels, L = n->desc.num_blocks;
-    cp.assign(pk.total_bytes, 0);
-    const float* p = blob + n->lo.enc;
-    auto emit = [&](int i, const float* K, const float* bias, const float* bn, int cin) {
-        unsigned char* tile = cp.data() + pk.off[i];
+    half_map.assign(pk.total_bytes / 2, -1);
+    folds.clear();
+    size_t p = n->lo.enc;
+    auto emit = [&](int i, size_t K, size_t bias, long long bn, int cin) {
+        const size_t tile = pk.off[i];
         for (int k = 0; k < 9 * cin; ++k)
-            for (int co = 0; co < Cc; ++co) {
-                const uint16_t v = to_bf16(K[(size_t)k * Cc + co]);
-                memcpy(tile + tc_tile_offset_host(co, k, Cc), &v, 2);
-            }
-        float* gain = reinterpret_cast<float*>(tile + pk.gain_off[i]);
-        float* shift = gain + Cc;
+            for (int co = 0; co < Cc; ++co) half_map[(tile + tc_tile_offset_host(co, k, Cc)) / 2] = (int)(K + (size_t)k * Cc + co);
+        const size_t goff = tile + pk.gain_off[i];
+        for (size_t h = goff / 2; h < (goff + (size_t)2 * Cc * 4) / 2; ++h) half_map[h] = -2;
         for (int co = 0; co < Cc; ++co) {
-            if (bn) {
-                const float g = bn[co] / sqrtf(bn[3 * Cc + co] + 1e-5f);
-                gain[co] = g;
-                shift[co] = (bias[co] - bn[2 * Cc + co]) * g + bn[Cc + co];
-            } else {
-                gain[co] = 1.0f;
-                shift[co] = bias[co];
-            }
+            BnFold f;
+            f.gain_dst = (int)((goff + (size_t)co * 4) / 4);
+            f.shift_dst = (int)((goff + (size_t)(Cc + co) * 4) / 4);
+            f.bias = (int)(bias + co);
+            f.scale = bn >= 0 ? (int)(bn + co) : -1;
+            f.beta = bn >= 0 ? (int)(bn + Cc + co) : -1;
+            f.mean = bn >= 0 ? (int)(bn + 2 * Cc + co) : -1;
+            f.var = bn >= 0 ? (int)(bn + 3 * Cc + co) : -1;
+            folds.push_back(f);
         }
     };
-    emit(0, p, p + (size_t)9 * C * Cc, nullptr, C);
+    emit(0, p, p + (size_t)9 * C * Cc, -1, C);
     p += (size_t)9 * C * Cc + Cc;
     for (int l = 0; l < L; ++l) {
-        const float* k1 = p;           const float* b1 = k1 + (size_t)9 * Cc * Cc;
-        const float* bn1 = b1 + Cc;    const float* k2 = bn1 + 4 * Cc;
-        const float* b2 = k2 + (size_t)9 * Cc * Cc;
-        const float* bn2 = b2 + Cc;
-        emit(1 + 2 * l, k1, b1, bn1, Cc);
-        emit(2 + 2 * l, k2, b2, bn2, Cc);
+        const size_t k1 = p, b1 = k1 + (size_t)9 * Cc * Cc, bn1 = b1 + Cc, k2 = bn1 + 4 * Cc, b2 = k2 + (size_t)9 * Cc * Cc, bn2 = b2 + Cc;
+        emit(1 + 2 * l, k1, b1, (long long)bn1, Cc);
+        emit(2 + 2 * l, k2, b2, (long long)bn2, Cc);
         p = bn2 + 4 * Cc;
     }
+}
+
+template <class T>
+static cudaError_t upload(const std::vector<T>& v, T** d) {
+    *d = nullptr;
+    if (v.empty()) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void**)d, v.size() * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+// rebuild every kernel-side layout from n->d_blob on `st`
+static int repack_device(cumind_net* n, cudaStream_t st) {
+    CM_CUDA(launch_repack_f32(n->d_blob, n->d_pack_map, n->d_pack, n->pk.total, st));
+    CM_CUDA(launch_repack_f32(n->d_blob, n->d_fpack_map, n->d_fpack, n->fpk.total, st));
+    g_launches += 2;
+    if (n->tc_ok) {
+        CM_CUDA(launch_repack_bf16(n->d_blob, n->d_tc_half_map, n->d_tcpack, n->tpk.bias_off / 2, st));
+        CM_CUDA(launch_repack_f32(n->d_blob, n->d_tc_f32_map, reinterpret_cast<float*>(n->d_tcpack + n->tpk.bias_off),
+                                  (n->tpk.total_bytes - n->tpk.bias_off) / 4, st));
+        g_launches += 2;
+    }
+    if (n->conv_tc_ok) {
+        CM_CUDA(launch_repack_bf16(n->d_blob, n->d_c_half_map, n->d_cpack, n->cpk.total_bytes / 2, st));
+        CM_CUDA(launch_bn_fold(n->d_blob, n->d_folds, n->n_folds, reinterpret_cast<float*>(n->d_cpack), st));
+        g_launches += 2;
+    }
+    return 0;
 }
 
 extern "C" int cumind_net_create(const cumind_net_desc* desc, const float* h_params, size_t n_params, cumind_net** out) {
@@ -243,6 +259,33 @@ extern "C" int cumind_net_create(const cumind_net_desc* desc, const float* h_par
         delete n;
         return fail_cuda("cumind_net_create", e);
     }
+    {
+        std::vector<int> m;
+        n->d_pack_map = n->d_fpack_map = n->d_tc_half_map = n->d_tc_f32_map = n->d_c_half_map = nullptr;
+        n->d_folds = nullptr;
+        n->n_folds = 0;
+        build_pack_map(n, m);
+        if ((e = upload(m, &n->d_pack_map)) != cudaSuccess) { cumind_net_destroy(n); return fail_cuda("cumind_net_create", e); }
+        build_fused_map(n, m);
+        if ((e = upload(m, &n->d_fpack_map)) != cudaSuccess) { cumind_net_destroy(n); return fail_cuda("cumind_net_create", e); }
+        if (n->tc_ok) {
+            std::vector<int> f;
+            build_tc_maps(n, m, f);
+            if ((e = upload(m, &n->d_tc_half_map)) != cudaSuccess || (e = upload(f, &n->d_tc_f32_map)) != cudaSuccess) {
+                cumind_net_destroy(n);
+                return fail_cuda("cumind_net_create", e);
+            }
+        }
+        if (n->conv_tc_ok) {
+            std::vector<BnFold> folds;
+            build_conv_maps(n, m, folds);
+            n->n_folds = (int)folds.size();
+            if ((e = upload(m, &n->d_c_half_map)) != cudaSuccess || (e = upload(folds, &n->d_folds)) != cudaSuccess) {
+                cumind_net_destroy(n);
+                return fail_cuda("cumind_net_create", e);
+            }
+        }
+    }
     *out = n;
     int rc = cumind_net_update_params(n, h_params, n_params, nullptr);
     if (rc != 0) { cumind_net_destroy(n); *out = nullptr; return rc; }
@@ -254,20 +297,9 @@ extern "C" int cumind_net_update_params(cumind_net* n, const float* h_params, si
     if (!n || !h_params) return fail("cumind_net_update_params: NULL argument");
     if (n_params != n->n_params) return fail("cumind_net_update_params: parameter blob has the wrong size");
     cudaStream_t st = (cudaStream_t)stream;
-    build_pack(n, h_params, n->h_pack);
-    build_fused_pack(n, h_params, n->h_fpack);
-    if (n->conv_tc_ok) {
-        build_conv_tc_pack(n, h_params, n->h_cpack);
-        CM_CUDA(cudaMemcpyAsync(n->d_cpack, n->h_cpack.data(), n->cpk.total_bytes, cudaMemcpyHostToDevice, st));
-    }
-    if (n->tc_ok) {
-        build_tc_pack(n, h_params, n->h_tcpack);
-        CM_CUDA(cudaMemcpyAsync(n->d_tcpack, n->h_tcpack.data(), n->tpk.total_bytes, cudaMemcpyHostToDevice, st));
-    }
-    CM_CUDA(cudaMemcpyAsync(n->d_fpack, n->h_fpack.data(), sizeof(float) * n->fpk.total, cudaMemcpyHostToDevice, st));
     CM_CUDA(cudaMemcpyAsync(n->d_blob, h_params, sizeof(float) * n_params, cudaMemcpyHostToDevice, st));
-    CM_CUDA(cudaMemcpyAsync(n->d_pack, n->h_pack.data(), sizeof(float) * n->pk.total, cudaMemcpyHostToDevice, st));
-    CM_CUDA(cudaStreamSynchronize(st));  // h_pack is reused by the next update
+    if (repack_device(n, st)) return 1;
+    CM_CUDA(cudaStreamSynchronize(st));  // the caller may reuse h_params right away
     return 0;
 }
 
@@ -278,6 +310,8 @@ extern "C" int cumind_net_destroy(cumind_net* n) {
     cudaFree(n->d_fpack);
     cudaFree(n->d_tcpack);
     cudaFree(n->d_cpack);
+    cudaFree(n->d_pack_map); cudaFree(n->d_fpack_map); cudaFree(n->d_tc_half_map); cudaFree(n->d_tc_f32_map);
+    cudaFree(n->d_c_half_map); cudaFree(n->d_folds);
     cudaFree(n->d_work);
     delete n;
     return 0;
@@ -690,15 +724,27 @@ extern "C" int cumind_adamw_step(float* d_params, const float* d_grads, float* d
     return 0;
 }
 
-// nnx.update(network, params) from a DEVICE blob (after an optimiser step on the GPU): copies it to the
-// host, rebuilds the kernel-side layouts and uploads them.  Synchronises `stream`.
+// Same step with the counter on the device (d_step is incremented first): the launch arguments do not
+// change between steps, so the whole train step can be replayed from a CUDA graph.
+extern "C" int cumind_adamw_step_dev(float* d_params, const float* d_grads, float* d_m, float* d_v, const uint8_t* d_mask, size_t n,
+                                     float lr, float b1, float b2, float eps, float weight_decay, int64_t* d_step, float grad_scale,
+                                     void* stream) {
+    if (!d_params || !d_grads || !d_m || !d_v || !d_step) return fail("cumind_adamw_step_dev: bad argument");
+    CM_CUDA(launch_adamw_dev_step(d_params, d_grads, d_m, d_v, d_mask, n, lr, b1, b2, eps, weight_decay, (long long*)d_step, grad_scale,
+                                  (cudaStream_t)stream));
+    g_launches += 2;
+    return 0;
+}
+
+// nnx.update(network, params) from a DEVICE blob (after an optimiser step on the GPU): one device copy
+// and the gather kernels on `stream`; asynchronous, no host round trip.
 extern "C" int cumind_net_update_params_device(cumind_net* n, const float* d_params, size_t n_params, void* stream) {
     if (!n || !d_params) return fail("cumind_net_update_params_device: NULL argument");
     if (n_params != n->n_params) return fail("cumind_net_update_params_device: parameter blob has the wrong size");
-    std::vector<float> host(n_params);
-    CM_CUDA(cudaMemcpyAsync(host.data(), d_params, sizeof(float) * n_params, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    CM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-    return cumind_net_update_params(n, host.data(), n_params, stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_params != n->d_blob)
+        CM_CUDA(cudaMemcpyAsync(n->d_blob, d_params, sizeof(float) * n_params, cudaMemcpyDeviceToDevice, st));
+    return repack_device(n, st);
 }
 
 extern "C" int cumind_selftest_division(uint64_t n_per_thread, uint64_t seed, int32_t max_divisor, uint64_t* d_counts2,

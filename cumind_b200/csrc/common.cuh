@@ -160,6 +160,12 @@ inline TcPackLayout make_tc_pack_layout(int H, int L, int A) {
 // Per-layer sections of the tensor-core conv pack: bf16 weight tile [Kpad/8][Cout/8][8][8]
 // (row = output channel, k = (ky*3+kx)*Cin + ci, zero padded to Kpad), then fp32 gain[Cout] and
 // shift[Cout] (conv bias and inference BatchNorm folded: y = acc*gain + shift).
+// one record per conv output channel: where gain / shift go (4-byte units inside the conv pack) and
+// which blob entries they are folded from (scale = -1: layer without BatchNorm)
+struct BnFold {
+    int gain_dst, shift_dst, bias, scale, beta, mean, var;
+};
+
 struct ConvTcPackLayout {
     static constexpr int kMaxLayers = 17;  // 1 + 2*L, L <= 8
     int n_layers;

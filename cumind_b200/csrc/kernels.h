@@ -71,7 +71,12 @@ size_t conv_tc_work_bytes(const cumind_net_desc& d, int chunk);
 cudaError_t launch_conv_encoder_tc(const NetView& nv, const unsigned char* cpack, const ConvTcPackLayout& cpk, int sm_count,
                                    const float* obs, int B, float* hidden, unsigned char* work, int chunk, cudaStream_t st);
 
-// train.cu — fused AdamW over the flat parameter blob
+// train.cu — parameter re-layout on the device (gather maps) and fused AdamW over the flat parameter blob
+cudaError_t launch_repack_f32(const float* blob, const int* map, float* dst, size_t n, cudaStream_t st);
+cudaError_t launch_repack_bf16(const float* blob, const int* map, unsigned char* dst, size_t n, cudaStream_t st);
+cudaError_t launch_bn_fold(const float* blob, const BnFold* folds, int n, float* cpack_f32, cudaStream_t st);
+cudaError_t launch_adamw_dev_step(float* p, const float* g, float* m, float* v, const unsigned char* mask, size_t n, float lr, float b1,
+                                  float b2, float eps, float wd, long long* d_step, float grad_scale, cudaStream_t st);
 cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, const unsigned char* mask, size_t n, float lr, float b1,
                          float b2, float eps, float wd, long long step, float grad_scale, cudaStream_t st);
 

@@ -114,8 +114,17 @@ class CuMindNetwork:
         self.params = P.unflatten(blob, *self._dims)
         self._blob = blob
 
+    def _refresh_host(self) -> None:
+        """After a device-side optimiser step the host copy is stale: pull it back on demand."""
+        src = getattr(self, "_device_source", None)
+        if src is not None and getattr(self, "_host_stale", False):
+            self._blob = src.detach().cpu().numpy().copy()
+            self.params = P.unflatten(self._blob, *self._dims)
+            self._host_stale = False
+
     def state(self) -> Dict[str, Any]:
         """The parameter tree (NumPy arrays, reference naming) — what nnx.state(network) holds."""
+        self._refresh_host()
         return P.unflatten(self._blob, *self._dims)
 
     def load_state(self, params: Dict[str, Any]) -> None:
@@ -124,13 +133,21 @@ class CuMindNetwork:
             _native.check(self._lib.cumind_net_update_params(self._handle, blob.ctypes.data_as(C.c_void_p), blob.size, _stream_ptr()))
         self._blob = blob
         self.params = P.unflatten(blob, *self._dims)
+        self._host_stale = False
 
     def clone(self) -> "CuMindNetwork":
         return CuMindNetwork(*self._dims, params=self.state(), device=self.device, net_mode=self.net_mode)
 
     @property
     def blob(self) -> np.ndarray:
+        self._refresh_host()
         return self._blob
+
+    def update_from_device(self, flat: "torch.Tensor") -> None:
+        """nnx.update(network, params) from a flat device tensor (blob layout): asynchronous, stays on the GPU."""
+        with torch.cuda.device(self.device):
+            _native.check(self._lib.cumind_net_update_params_device(self._handle, C.c_void_p(flat.data_ptr()), flat.numel(), _stream_ptr()))
+        self._device_source, self._host_stale = flat, True
 
     def __del__(self):
         try:

@@ -156,12 +156,17 @@ class Trainer:
         self._dims = net._dims
         self._lib = _native.load()
         dev = net.device
-        self._flat = torch.as_tensor(net.blob.copy()).to(dev).requires_grad_(True)
+        self._flat = torch.as_tensor(net.blob.copy()).to(dev)      # parameters (blob layout); leaves alias it per step
+        self.last_grad: Optional[torch.Tensor] = None
         st = agent.optimizer_state if isinstance(agent.optimizer_state, dict) else {}
         self._m = torch.as_tensor(np.asarray(st["mu"], np.float32)).to(dev) if st.get("mu") is not None and np.size(st["mu"]) == self._flat.numel() else torch.zeros_like(self._flat, requires_grad=False)
         self._v = torch.as_tensor(np.asarray(st["nu"], np.float32)).to(dev) if st.get("nu") is not None and np.size(st["nu"]) == self._flat.numel() else torch.zeros_like(self._flat, requires_grad=False)
         self._count = int(st.get("count", 0) or 0)
+        self._step_dev = torch.tensor([self._count], dtype=torch.int64, device=dev)
         self._mask = torch.as_tensor(trainable_mask(self._dims)).to(dev)
+        self.use_cuda_graph = True
+        self._graph, self._graph_key, self._graph_out, self._static = None, None, None, None
+        self._state_stale = False
 
     # ---- batch preparation (trainer.py:118-170) --------------------------------------------------
     def _n_step_returns(self, batch: Sequence[List[Dict[str, Any]]]) -> np.ndarray:
@@ -198,8 +203,61 @@ class Trainer:
     def compute_losses(self, observations, actions, targets) -> Dict[str, torch.Tensor]:
         dev = self._flat.device
         t = {k: torch.as_tensor(np.asarray(v)).to(dev) for k, v in targets.items()}
-        return forward_losses(self._flat, self._dims, torch.as_tensor(np.asarray(observations, np.float32)).to(dev),
-                              torch.as_tensor(np.asarray(actions)).to(dev), t, self.config.num_unroll_steps)
+        with torch.no_grad():
+            return forward_losses(self._flat, self._dims, torch.as_tensor(np.asarray(observations, np.float32)).to(dev),
+                                  torch.as_tensor(np.asarray(actions)).to(dev), t, self.config.num_unroll_steps)
+
+    def _eager_step(self, observations, actions, targets) -> Dict[str, torch.Tensor]:
+        """loss -> grad -> (all-reduce) -> AdamW -> push parameters; every launch on the current stream."""
+        leaf = self._flat.detach().requires_grad_(True)   # fresh autograd leaf over the same storage
+        losses = forward_losses(leaf, self._dims, observations, actions, targets, self.config.num_unroll_steps)
+        total = losses["value_loss"] + losses["policy_loss"] + losses["reward_loss"]
+        total.backward()
+        grad = leaf.grad
+        self.last_grad = grad
+        losses = {k: v.detach() for k, v in losses.items()}
+        total = total.detach()
+        world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size()
+            torch.distributed.all_reduce(grad)            # one flat bucket over NCCL / NVLink
+        opt = self.agent.optimizer
+        with torch.no_grad():
+            _native.check(self._lib.cumind_adamw_step_dev(
+                C.c_void_p(self._flat.data_ptr()), C.c_void_p(grad.data_ptr()), C.c_void_p(self._m.data_ptr()),
+                C.c_void_p(self._v.data_ptr()), C.c_void_p(self._mask.data_ptr()), self._flat.numel(), opt.learning_rate, opt.b1,
+                opt.b2, opt.eps, opt.weight_decay, C.c_void_p(self._step_dev.data_ptr()), 1.0 / world, _stream_ptr()))
+            self.agent.network.update_from_device(self._flat)
+        return {**losses, "total_loss": total}
+
+    def _graph_step(self, observations, actions, targets) -> Dict[str, torch.Tensor]:
+        """Replay the whole step from one CUDA graph (static shapes; single process)."""
+        key = (tuple(observations.shape), tuple(actions.shape))
+        if self._graph is None or self._graph_key != key:
+            self._static = (observations.clone(), actions.clone(), {k: v.clone() for k, v in targets.items()})
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            state = (self._flat.detach().clone(), self._m.clone(), self._v.clone(), self._step_dev.clone())
+            with torch.cuda.stream(side):
+                for _ in range(3):                       # warm-up outside the capture (allocator, cuBLAS handles)
+                    self._eager_step(*self._static)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            with torch.no_grad():                        # undo the warm-up updates
+                self._flat.copy_(state[0]); self._m.copy_(state[1]); self._v.copy_(state[2]); self._step_dev.copy_(state[3])
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._graph_out = self._eager_step(*self._static)
+            with torch.no_grad():                        # capture does not execute: state is unchanged, but be explicit
+                self._flat.copy_(state[0]); self._m.copy_(state[1]); self._v.copy_(state[2]); self._step_dev.copy_(state[3])
+            self.agent.network.update_from_device(self._flat)
+            self._graph_key = key
+        so, sa, st = self._static
+        so.copy_(observations); sa.copy_(actions)
+        for k in st:
+            st[k].copy_(targets[k])
+        self._graph.replay()
+        return self._graph_out
 
     def train_step(self, batch: Optional[Tuple[Any, Any, Dict[str, Any]]] = None) -> Dict[str, float]:
         """One optimiser step.  `batch` = (observations, actions [B,K], targets) skips the replay sampling."""
@@ -207,36 +265,30 @@ class Trainer:
             if not self.memory.is_ready(self.config.min_memory_size, self.config.min_memory_pct):
                 return {}
             batch = self._prepare_batch(self.memory.sample(self.config.batch_size))
-        observations, actions, targets = batch
-        self._flat.grad = None
-        losses = self.compute_losses(observations, actions, targets)
-        total = losses["value_loss"] + losses["policy_loss"] + losses["reward_loss"]
-        total.backward()
-        grad = self._flat.grad
-        world = 1
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            world = torch.distributed.get_world_size()
-            torch.distributed.all_reduce(grad)            # one flat bucket over NCCL / NVLink
+        dev = self._flat.device
+        observations = torch.as_tensor(np.asarray(batch[0], np.float32)).to(dev)
+        actions = torch.as_tensor(np.asarray(batch[1])).to(dev)
+        targets = {k: torch.as_tensor(np.asarray(v)).to(dev) for k, v in batch[2].items()}
+        distributed = torch.distributed.is_available() and torch.distributed.is_initialized()
+        if self.use_cuda_graph and not distributed:
+            out = self._graph_step(observations, actions, targets)
+        else:
+            out = self._eager_step(observations, actions, targets)
         self._count += 1
-        opt = self.agent.optimizer
-        with torch.no_grad():
-            _native.check(self._lib.cumind_adamw_step(
-                C.c_void_p(self._flat.data_ptr()), C.c_void_p(grad.data_ptr()), C.c_void_p(self._m.data_ptr()),
-                C.c_void_p(self._v.data_ptr()), C.c_void_p(self._mask.data_ptr()), self._flat.numel(), opt.learning_rate, opt.b1,
-                opt.b2, opt.eps, opt.weight_decay, self._count, 1.0 / world, _stream_ptr()))
-            net = self.agent.network
-            _native.check(self._lib.cumind_net_update_params_device(net._handle, C.c_void_p(self._flat.data_ptr()), self._flat.numel(),
-                                                                    _stream_ptr()))
-            net._blob = self._flat.detach().cpu().numpy().copy()
-            net.params = P.unflatten(net._blob, *self._dims)
-        self.agent.optimizer_state = {"count": self._count, "mu": self._m.cpu().numpy(), "nu": self._v.cpu().numpy()}
         self.train_step_count += 1
-        out = {f"train/{k}": float(v.detach()) for k, v in losses.items()}
-        out["total_loss"] = float(total.detach())
-        return out
+        self._state_stale = True
+        res = {f"train/{k}": float(v.detach()) for k, v in out.items() if k != "total_loss"}
+        res["total_loss"] = float(out["total_loss"].detach())
+        return res
+
+    def sync_optimizer_state(self) -> None:
+        """Copy the AdamW moments back into agent.optimizer_state (for save_state / checkpoints)."""
+        self.agent.optimizer_state = {"count": self._count, "mu": self._m.cpu().numpy(), "nu": self._v.cpu().numpy()}
+        self._state_stale = False
 
     # ---- checkpoints (trainer.py:207-219) ------------------------------------------------------------
     def save_checkpoint(self, episode: int) -> str:
+        self.sync_optimizer_state()
         os.makedirs(self.checkpoint_dir, exist_ok=True)
         path = f"{self.checkpoint_dir}/episode_{episode:05d}.pkl"
         save_checkpoint(self.agent.save_state(), path)
@@ -244,4 +296,4 @@ class Trainer:
 
     def load_checkpoint(self, path: str) -> None:
         self.agent.load_state(load_checkpoint(path))
-        self._flat.data.copy_(torch.as_tensor(self.agent.network.blob).to(self._flat.device))
+        self._flat.copy_(torch.as_tensor(self.agent.network.blob).to(self._flat.device))

@@ -224,10 +224,15 @@ int cumind_dirichlet(double* d_noise, int32_t B, int32_t A, double alpha, uint64
  * cumind_adamw_step: optax.adamw over a flat fp32 device blob, fused with the 1/world scaling of an
  *   all-reduced gradient (grad_scale); d_mask (uint8, may be NULL) is 0 for leaves that are not
  *   trained (BatchNorm running statistics).  `step` counts from 1.
- * cumind_net_update_params_device: nnx.update(network, params) from a device blob. */
+ * cumind_adamw_step_dev: the same with the step counter in device memory (CUDA-graph replayable).
+ * cumind_net_update_params_device: nnx.update(network, params) from a device blob; asynchronous
+ *   (one device copy + gather kernels that rebuild the kernel-side layouts), no host round trip. */
 int cumind_adamw_step(float* d_params, const float* d_grads, float* d_m, float* d_v, const uint8_t* d_mask,
                       size_t n, float lr, float b1, float b2, float eps, float weight_decay, int64_t step,
                       float grad_scale, void* stream);
+int cumind_adamw_step_dev(float* d_params, const float* d_grads, float* d_m, float* d_v, const uint8_t* d_mask,
+                          size_t n, float lr, float b1, float b2, float eps, float weight_decay,
+                          int64_t* d_step /* device counter, incremented first */, float grad_scale, void* stream);
 int cumind_net_update_params_device(cumind_net* net, const float* d_params, size_t n_params, void* stream);
 
 /* Diagnostic: checks the table-driven small-divisor division used by the fused select kernel

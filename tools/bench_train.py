@@ -45,6 +45,7 @@ def main():
         torch.distributed.barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
+    dev_batch = (torch.as_tensor(batch[0]).cuda(), torch.as_tensor(batch[1]).cuda(), {k: torch.as_tensor(v).cuda() for k, v in batch[2].items()})
     for _ in range(args.steps):
         info = trainer.train_step(batch)
     t1.record()
