@@ -273,6 +273,8 @@ def run_native(args, rank: int, world: int, local_rank: int):
     agent.network.load_state(P.unflatten(blob, OBS_SHAPE, A, H, L, CC))
     agent.update_target_network()
     agent.mcts.lanes_per_tree = args.lanes
+    agent.mcts.schedule = {"auto": 0, "warp": 1, "team": 2}[args.schedule]
+    agent.mcts.teams_per_cta, agent.mcts.net_warps_per_team, agent.mcts.trees_per_team = args.teams, args.net_warps, args.trees_per_team
     net, mcts = agent.network, agent.mcts
     dev = torch.device("cuda", local_rank)
     d_obs = torch.as_tensor(obs).to(dev)
@@ -294,6 +296,10 @@ def run_native(args, rank: int, world: int, local_rank: int):
         step_dev()
         flush_l2(1)
     torch.cuda.synchronize()
+    if args.phase_clocks:
+        if rank == 0:
+            print(json.dumps(phase_clocks(mcts, net.representation_network(d_obs), d_noise, tree_base, S)), flush=True)
+        return
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -366,7 +372,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("search_fused_dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "search_fused_kernel", "kernel_ms": kern_ms_mean, "algorithmic_bytes_per_sim": algorithmic_bytes_per_sim(dbar),
+                "kernel": "search_team_kernel" if mcts.plan(B)["schedule"] == "team" else "search_fused_kernel", "kernel_ms": kern_ms_mean, "algorithmic_bytes_per_sim": algorithmic_bytes_per_sim(dbar),
                 "mean_path_length": dbar, "peak_source": peak_src, "encoder_ms": enc_ms_mean}
     if WORKLOAD != "cartpole":
         # image workload: the conv trunk dominates and is tensor-pipe bound
@@ -394,6 +400,38 @@ def run_native(args, rank: int, world: int, local_rank: int):
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def phase_clocks(mcts, hidden, d_noise, tree_index_base, S):
+    """cumind_search_phase_clocks: SM cycles per phase of the team kernel (tree warp 0 / network warp 0 of
+    team 0 in every CTA), averaged over the CTAs and divided by the number of simulations."""
+    import ctypes as C
+
+    import torch
+
+    from cumind_b200 import _native
+    from cumind_b200.network import _ptr, _stream_ptr
+
+    net = mcts.network
+    B = hidden.shape[0]
+    A_cfg = int(mcts.config.action_space_size)
+    tree = mcts._tree(B, int(mcts.config.num_simulations), min(A_cfg, net.action_space_size))
+    cfg = mcts._cfg(1, 0, tree_index_base)
+    plan = mcts.plan(B)
+    visits = torch.empty((B, A_cfg), dtype=torch.int32, device=net.device)
+    probs = torch.empty((B, A_cfg), dtype=torch.float64, device=net.device)
+    clk = torch.zeros((plan["grid"], 16), dtype=torch.int64, device=net.device)
+    _native.check(mcts._lib.cumind_search_phase_clocks(tree.handle, net._handle, _ptr(hidden), C.byref(cfg), _ptr(d_noise), _ptr(visits),
+                                                       _ptr(probs), None, _ptr(clk), _stream_ptr()))
+    torch.cuda.synchronize()
+    c = clk.cpu().numpy().astype(np.float64)
+    names = ["tree.select", "tree.wait_network", "tree.softmax_expand_backup", "tree.root_and_final",
+             "net.gather", "net.layer_barriers", "net.heads", "net.wait_trees", "net.layer_compute"]
+    cols = [0, 1, 2, 3, 8, 9, 10, 11, 12]
+    out = {"plan": plan, "cycles_per_simulation_mean": {n: float(c[:, k].mean()) / S for n, k in zip(names, cols)},
+           "cycles_per_simulation_max": {n: float(c[:, k].max()) / S for n, k in zip(names, cols)}}
+    out["tree_total_per_sim"] = sum(out["cycles_per_simulation_mean"][n] for n in names[:4])
+    return out
 
 
 def _search_device(mcts, hidden, d_noise, tree_index_base):
@@ -430,6 +468,11 @@ def main():
                     help="global batch sharded across the ranks (strong scaling; BASELINE configs[3] uses 65536)")
     ap.add_argument("--sims", type=int, default=50)
     ap.add_argument("--lanes", type=int, default=0, help="lanes per tree (0 = auto)")
+    ap.add_argument("--schedule", default="auto", choices=["auto", "warp", "team"], help="cumind_search_cfg.schedule")
+    ap.add_argument("--teams", type=int, default=0, help="team schedule: teams per CTA (0 = auto)")
+    ap.add_argument("--net-warps", type=int, default=0, help="team schedule: network warps per team (0 = auto)")
+    ap.add_argument("--trees-per-team", type=int, default=0, help="team schedule: tree slots per team (0 = auto)")
+    ap.add_argument("--phase-clocks", action="store_true", help="print the team kernel's per-phase SM cycles and exit")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--workload", default="cartpole", choices=["cartpole", "atari", "atari-literal"],

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcumind_b200.so")
-SOURCES = ["abi.cu", "search_fused.cu", "tree_steps.cu", "network_fp32.cu", "conv_fp32.cu", "network_tc.cu", "conv_tc.cu", "train.cu"]
+SOURCES = ["abi.cu", "search_fused.cu", "search_team.cu", "tree_steps.cu", "network_fp32.cu", "conv_fp32.cu", "network_tc.cu", "conv_tc.cu", "train.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
 
@@ -37,18 +37,44 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _stale_obj(src: str, obj: str, headers: List[str]) -> bool:
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    return any(os.path.getmtime(d) > t for d in [src] + headers)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """One object per .cu (compiled in parallel, only the stale ones), then one link step."""
     if not force and not is_stale():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
+
     os.makedirs(LIB_DIR, exist_ok=True)
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(os.path.dirname(HERE), "include", "cumind_b200.h"))
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src: str):
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        if not force and not _stale_obj(src, obj, headers):
+            return obj, ""
+        r = subprocess.run([_nvcc()] + cflags + ["-c", "-o", obj, src], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s%s" % (src, r.stdout, r.stderr))
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, sources()))
     tmp = LIB_PATH + ".tmp"
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + sources()
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    r = subprocess.run([_nvcc()] + NVCC_FLAGS + ["-o", tmp] + [o for o, _ in results], capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
     os.replace(tmp, LIB_PATH)
     if verbose:
-        sys.stderr.write(r.stderr)
+        sys.stderr.write("".join(log for _, log in results))
     return LIB_PATH
 
 

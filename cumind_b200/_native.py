@@ -18,7 +18,7 @@ EXPORTS = [
     "cumind_last_error", "cumind_abi_version", "cumind_param_count", "cumind_net_create", "cumind_net_update_params",
     "cumind_net_destroy", "cumind_initial_inference", "cumind_recurrent_inference", "cumind_prediction", "cumind_softmax",
     "cumind_tree_bytes", "cumind_tree_create", "cumind_tree_destroy", "cumind_tree_get_view", "cumind_search",
-    "cumind_search_plan", "cumind_search_stepwise", "cumind_select_actions_work_bytes", "cumind_select_actions_host",
+    "cumind_search_plan", "cumind_search_phase_clocks", "cumind_search_stepwise", "cumind_select_actions_work_bytes", "cumind_select_actions_host",
     "cumind_tree_init_root", "cumind_select", "cumind_expand", "cumind_backup", "cumind_finalize", "cumind_dirichlet",
     "cumind_launch_count", "cumind_selftest_division", "cumind_adamw_step", "cumind_adamw_step_dev", "cumind_net_update_params_device",
 ]
@@ -26,6 +26,7 @@ EXPORTS = [
 NET_FP32_EXACT = 0
 NET_BF16_TC = 1
 TREE_REFERENCE = 0
+SCHED_AUTO, SCHED_WARP, SCHED_TEAM = 0, 1, 2
 
 
 class NetDesc(C.Structure):
@@ -37,7 +38,8 @@ class SearchCfg(C.Structure):
     _fields_ = [("num_simulations", C.c_int32), ("action_space_size", C.c_int32), ("c_puct", C.c_double),
                 ("exploration_fraction", C.c_double), ("dirichlet_alpha", C.c_double), ("noise_mode", C.c_int32),
                 ("net_mode", C.c_int32), ("tree_mode", C.c_int32), ("lanes_per_tree", C.c_int32), ("seed", C.c_uint64),
-                ("tree_index_base", C.c_uint64)]
+                ("tree_index_base", C.c_uint64), ("schedule", C.c_int32), ("teams_per_cta", C.c_int32),
+                ("net_warps_per_team", C.c_int32), ("trees_per_team", C.c_int32)]
 
 
 class TreeView(C.Structure):
@@ -94,7 +96,8 @@ def load():
     search_args = [vp, vp, vp, C.POINTER(SearchCfg), vp, vp, vp, vp, vp]
     lib.cumind_search.argtypes = search_args
     lib.cumind_search_stepwise.argtypes = search_args
-    lib.cumind_search_plan.argtypes = [vp, vp, C.POINTER(SearchCfg), C.POINTER(i32 * 6)]
+    lib.cumind_search_phase_clocks.argtypes = search_args[:-1] + [vp, vp]
+    lib.cumind_search_plan.argtypes = [vp, vp, C.POINTER(SearchCfg), C.POINTER(i32 * 8)]
     lib.cumind_select_actions_host.argtypes = [vp, vp, vp, C.POINTER(SearchCfg), vp, vp, vp, vp, sz, vp]
     lib.cumind_tree_init_root.argtypes = [vp, vp, vp, C.POINTER(SearchCfg), vp, vp]
     lib.cumind_select.argtypes = [vp, C.POINTER(SearchCfg), vp]

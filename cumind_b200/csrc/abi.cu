@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -22,6 +23,9 @@ struct cumind_net {
     float* d_blob;
     float* d_pack;
     float* d_fpack;       // FusedPackLayout copy for the fused search kernel
+    float* d_team_pack;   // TeamPackLayout copy for the team search kernel
+    TeamPackLayout team_pk;
+    int* d_team_map;
     unsigned char* d_tcpack;  // TcPackLayout (bf16 tiles) for the tensor-core kernels, or null
     TcPackLayout tpk;
     bool tc_ok;
@@ -132,6 +136,35 @@ static void build_fused_map(const cumind_net* n, std::vector<int>& m) {
     m[pk.heads_b + A + 1] = (int)lo.rew_b;
 }
 
+// TeamPackLayout: k-major layer kernels padded to Hp output columns, every weight stored twice when dup
+static void build_team_map(const cumind_net* n, std::vector<int>& m) {
+    const TeamPackLayout& pk = n->team_pk;
+    const BlobLayout& lo = n->lo;
+    const int H = pk.H, L = pk.L, A = pk.A, Hp = pk.Hp, rep = pk.dup ? 2 : 1;
+    m.assign(pk.total, -1);
+    for (size_t i = 0; i < (size_t)A * H; ++i) m[pk.emb + i] = (int)(lo.emb + i);
+    for (int l = 0; l < L; ++l) {
+        const size_t K = lo.dyn + (size_t)l * ((size_t)H * H + H);
+        for (int k = 0; k < H; ++k)
+            for (int j = 0; j < H; ++j)
+                for (int r = 0; r < rep; ++r) m[pk.layer_w(l) + ((size_t)k * Hp + j) * rep + r] = (int)(K + (size_t)k * H + j);
+        for (int j = 0; j < H; ++j) m[pk.layer_b(l) + j] = (int)(K + (size_t)H * H + j);
+    }
+    for (int k = 0; k < H; ++k) {
+        for (int a = 0; a < A; ++a) m[pk.heads_w + (size_t)k * pk.HP + a] = (int)(lo.pol_k + (size_t)k * A + a);
+        m[pk.heads_w + (size_t)k * pk.HP + A] = (int)(lo.val_k + k);
+        m[pk.heads_w + (size_t)k * pk.HP + A + 1] = (int)(lo.rew_k + k);
+    }
+    for (int a = 0; a < A; ++a) m[pk.heads_b + a] = (int)(lo.pol_b + a);
+    m[pk.heads_b + A] = (int)lo.val_b;
+    m[pk.heads_b + A + 1] = (int)lo.rew_b;
+    for (int k = 0; k < H; ++k) {
+        for (int a = 0; a < A; ++a) m[pk.heads_wt + (size_t)a * H + k] = (int)(lo.pol_k + (size_t)k * A + a);
+        m[pk.heads_wt + (size_t)A * H + k] = (int)(lo.val_k + k);
+        m[pk.heads_wt + (size_t)(A + 1) * H + k] = (int)(lo.rew_k + k);
+    }
+}
+
 // TcPackLayout: bf16 tiles over [0, bias_off) (map in 2-byte units), fp32 over [bias_off, total) (4-byte units)
 static void build_tc_maps(const cumind_net* n, std::vector<int>& half_map, std::vector<int>& f32_map) {
     const TcPackLayout& pk = n->tpk;
@@ -207,7 +240,8 @@ static cudaError_t upload(const std::vector<T>& v, T** d) {
 static int repack_device(cumind_net* n, cudaStream_t st) {
     CM_CUDA(launch_repack_f32(n->d_blob, n->d_pack_map, n->d_pack, n->pk.total, st));
     CM_CUDA(launch_repack_f32(n->d_blob, n->d_fpack_map, n->d_fpack, n->fpk.total, st));
-    g_launches += 2;
+    CM_CUDA(launch_repack_f32(n->d_blob, n->d_team_map, n->d_team_pack, n->team_pk.total, st));
+    g_launches += 3;
     if (n->tc_ok) {
         CM_CUDA(launch_repack_bf16(n->d_blob, n->d_tc_half_map, n->d_tcpack, n->tpk.bias_off / 2, st));
         CM_CUDA(launch_repack_f32(n->d_blob, n->d_tc_f32_map, reinterpret_cast<float*>(n->d_tcpack + n->tpk.bias_off),
@@ -238,7 +272,12 @@ extern "C" int cumind_net_create(const cumind_net_desc* desc, const float* h_par
     n->lo = lo;
     n->pk = make_pack_layout(desc->hidden_dim, desc->num_blocks, desc->action_space_size);
     n->fpk = make_fused_pack_layout(desc->hidden_dim, desc->num_blocks, desc->action_space_size);
+    {
+        n->team_pk = make_team_pack_layout(desc->hidden_dim, desc->num_blocks, desc->action_space_size, 0);
+    }
     n->n_params = n_params;
+    n->d_team_pack = nullptr;
+    n->d_team_map = nullptr;
     n->d_blob = n->d_pack = n->d_fpack = n->d_work = nullptr;
     n->d_tcpack = nullptr;
     n->d_cpack = nullptr;
@@ -253,9 +292,10 @@ extern "C" int cumind_net_create(const cumind_net_desc* desc, const float* h_par
         (e = cudaMalloc(&n->d_blob, sizeof(float) * lo.total)) != cudaSuccess ||
         (e = cudaMalloc(&n->d_pack, sizeof(float) * n->pk.total)) != cudaSuccess ||
         (e = cudaMalloc(&n->d_fpack, sizeof(float) * n->fpk.total)) != cudaSuccess ||
+        (e = cudaMalloc(&n->d_team_pack, sizeof(float) * n->team_pk.total)) != cudaSuccess ||
         (n->tc_ok && (e = cudaMalloc(&n->d_tcpack, n->tpk.total_bytes)) != cudaSuccess) ||
         (n->conv_tc_ok && (e = cudaMalloc(&n->d_cpack, n->cpk.total_bytes)) != cudaSuccess)) {
-        cudaFree(n->d_blob); cudaFree(n->d_pack); cudaFree(n->d_fpack);
+        cudaFree(n->d_blob); cudaFree(n->d_pack); cudaFree(n->d_fpack); cudaFree(n->d_team_pack);
         delete n;
         return fail_cuda("cumind_net_create", e);
     }
@@ -268,6 +308,8 @@ extern "C" int cumind_net_create(const cumind_net_desc* desc, const float* h_par
         if ((e = upload(m, &n->d_pack_map)) != cudaSuccess) { cumind_net_destroy(n); return fail_cuda("cumind_net_create", e); }
         build_fused_map(n, m);
         if ((e = upload(m, &n->d_fpack_map)) != cudaSuccess) { cumind_net_destroy(n); return fail_cuda("cumind_net_create", e); }
+        build_team_map(n, m);
+        if ((e = upload(m, &n->d_team_map)) != cudaSuccess) { cumind_net_destroy(n); return fail_cuda("cumind_net_create", e); }
         if (n->tc_ok) {
             std::vector<int> f;
             build_tc_maps(n, m, f);
@@ -308,6 +350,8 @@ extern "C" int cumind_net_destroy(cumind_net* n) {
     cudaFree(n->d_blob);
     cudaFree(n->d_pack);
     cudaFree(n->d_fpack);
+    cudaFree(n->d_team_pack);
+    cudaFree(n->d_team_map);
     cudaFree(n->d_tcpack);
     cudaFree(n->d_cpack);
     cudaFree(n->d_pack_map); cudaFree(n->d_fpack_map); cudaFree(n->d_tc_half_map); cudaFree(n->d_tc_f32_map);
@@ -600,6 +644,110 @@ static int plan_fused(const cumind_tree* t, const cumind_net* n, const cumind_se
     return 0;
 }
 
+struct TeamPlan { int G, grid, block; size_t smem; TeamParams p; };
+
+// Team schedule (search_team.cu): G = pow2 >= A lanes per tree, TT tree slots per team (8 or 16), ntw tree
+// warps + nmw network warps per team, n_team teams per CTA, one CTA per SM.  The tree statistics of the
+// trees in flight live in shared memory (40 bytes per node), which bounds the trees per team.
+static int plan_team(const cumind_tree* t, const cumind_net* n, const cumind_search_cfg* c, TeamPlan& pl, std::string& why) {
+    const int H = n->desc.hidden_dim, B = t->tv.B, A = t->tv.A, S_max = t->tv.S_max, N = t->tv.N;
+    const int sm = n->sm_count;
+    if (H % 4 != 0) { why = "hidden_dim is not a multiple of 4"; return 1; }
+    if (A > 65535 || S_max > 65533) { why = "tree too large for the packed select payload"; return 1; }
+    int G = 2;
+    while (G < A && G < 32) G *= 2;
+    if (c->lanes_per_tree > 0) {  // explicit lanes per tree: round down to a power of two in [2, 32]
+        G = 2;
+        while (G * 2 <= c->lanes_per_tree && G < 32) G *= 2;
+    }
+    const int TPW = 32 / G;
+    const int tps = (B + sm - 1) / sm;  // trees per SM
+    int TT = (G <= 8 && tps > 8) ? 16 : 8;
+    if (c->trees_per_team > 0) TT = (c->trees_per_team > 8 && G <= 8) ? 16 : 8;
+    if (!team_variant_ok(G, TT)) { why = "no team kernel for this lane mapping"; return 1; }
+    const int ntw = (TT + TPW - 1) / TPW;
+    int nmw = c->net_warps_per_team > 0 ? c->net_warps_per_team : 4;
+    if (nmw > 8) nmw = 8;
+    const int team_warps = ntw + nmw;
+    const int XS = TT + 4;
+    const TeamPackLayout& pk = n->team_pk;
+    const size_t pack_bytes = pk.total * sizeof(float);
+    const int n_sqrt = 2 * S_max + 4;
+    auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t off_sqrt = al16(pack_bytes);
+    const size_t off_recip = al16(off_sqrt + (size_t)n_sqrt * sizeof(double));
+    const size_t off_teams = (off_recip + (size_t)n_sqrt * sizeof(double) + 127) & ~(size_t)127;
+    const size_t team_base = al16((size_t)(2 * H * XS + TT * (H + 4) + 2 * TT * pk.HP + 3 * TT) * 4);
+    const size_t per_tree = (size_t)(S_max + 2) * sizeof(int) + (size_t)N * 40;  // path + hot W + hot records
+    const size_t kMax = 227 * 1024;
+    if (off_teams + team_base + per_tree + 256 > kMax) { why = "one tree does not fit the team kernel's shared memory"; return 1; }
+    int n_team = c->teams_per_cta > 0 ? c->teams_per_cta : (tps + TT - 1) / TT;
+    if (n_team < 1) n_team = 1;
+    if (n_team > 7) n_team = 7;
+    // the automatic choice keeps the CTA at <= 512 threads (128 registers per thread)
+    const int max_threads = c->teams_per_cta > 0 ? 1024 : 512;
+    while (n_team > 1 && n_team * team_warps * 32 > max_threads) --n_team;
+    if (n_team * team_warps * 32 > 1024) { why = "team does not fit a CTA"; return 1; }
+    // trees per batch: spread the SM's trees evenly over its teams, within TT and within shared memory
+    int tpt = 0;
+    for (;; --n_team) {
+        const size_t budget = (kMax - 64 - off_teams) / n_team;
+        const long long cap = budget > team_base + 512 ? (long long)((budget - team_base - 512) / per_tree) : 0;
+        tpt = (tps + n_team - 1) / n_team;
+        if (tpt > TT) tpt = TT;
+        if (c->trees_per_team > 0 && c->trees_per_team < tpt) tpt = c->trees_per_team;
+        if (cap >= 1) {
+            if (tpt > cap) tpt = (int)cap;
+            break;
+        }
+        if (n_team == 1) { why = "one tree does not fit the team kernel's shared memory"; return 1; }
+    }
+    if (tpt < 1) tpt = 1;
+    const size_t off_path = team_base;
+    const size_t off_hotw = al16(off_path + (size_t)tpt * (S_max + 2) * sizeof(int));
+    const size_t off_hot = al16(off_hotw + (size_t)tpt * N * sizeof(double));
+    const size_t team_bytes = (off_hot + (size_t)tpt * N * 32 + 127) & ~(size_t)127;
+    const size_t total = off_teams + (size_t)n_team * team_bytes + 16;
+    if (total > kMax) { why = "internal: team scratch exceeds shared memory"; return 1; }
+    const int n_batches = (B + tpt - 1) / tpt;
+    int grid = (n_batches + n_team - 1) / n_team;
+    if (grid > sm) grid = sm;
+    pl.G = G;
+    pl.grid = grid;
+    pl.block = n_team * team_warps * 32;
+    pl.smem = total;
+    TeamParams& p = pl.p;
+    p.tv = t->tv;
+    p.pack = n->d_team_pack;
+    p.pk = pk;
+    p.S = c->num_simulations;
+    p.A_cfg = c->action_space_size;
+    p.A_net = n->desc.action_space_size;
+    p.c_puct = c->c_puct;
+    p.frac = c->exploration_fraction;
+    p.one_minus_frac = 1.0 - c->exploration_fraction;
+    p.alpha = c->dirichlet_alpha;
+    p.noise_mode = c->noise_mode;
+    p.seed = c->seed;
+    p.tree_base = c->tree_index_base;
+    p.n_team = n_team; p.ntw = ntw; p.nmw = nmw; p.TT = TT; p.tpt = tpt; p.n_batches = n_batches;
+    p.off_sqrt = (unsigned)off_sqrt;
+    p.off_recip = (unsigned)off_recip;
+    p.off_teams = (unsigned)off_teams;
+    p.team_bytes = (unsigned)team_bytes;
+    p.off_path = (unsigned)off_path;
+    p.off_hotw = (unsigned)off_hotw;
+    p.off_hot = (unsigned)off_hot;
+    p.off_bar = (unsigned)((off_teams + (size_t)n_team * team_bytes + 7) & ~(size_t)7);
+    p.n_sqrt = n_sqrt;
+    p.clk = nullptr;
+    p.tile = 0;
+    p.stagger = 0;
+    if (const char* e = getenv("CUMIND_TEAM_TILE")) p.tile = atoi(e);        // tuning only
+    if (const char* e = getenv("CUMIND_TEAM_STAGGER")) p.stagger = atoi(e);  // tuning only
+    return 0;
+}
+
 extern "C" int cumind_search_stepwise(cumind_tree* t, const cumind_net* n, const float* d_root_hidden, const cumind_search_cfg* c,
                                       const double* d_noise, int32_t* d_out_visits, double* d_out_probs, double* d_out_root_value,
                                       void* stream) {
@@ -628,11 +776,25 @@ extern "C" int cumind_search(cumind_tree* t, const cumind_net* n, const float* d
     if (!d_root_hidden || !d_out_visits || !d_out_probs) return fail("cumind_search: NULL device pointer");
     FusedPlan pl;
     std::string why;
-    // The fused kernel computes the in-search MLP in fp32-exact arithmetic.  It is also what
-    // CUMIND_NET_BF16_TC runs when the parameters fit its shared-memory staging: at these layer widths
+    // The fused kernels compute the in-search MLP in fp32-exact arithmetic.  They are also what
+    // CUMIND_NET_BF16_TC runs when the parameters fit their shared-memory staging: at these layer widths
     // one fused launch beats 3 launches per simulation through the tensor-core expansion kernel
     // (measured in profiles/README.md), and it is more accurate.  cumind_search_stepwise always
     // honours net_mode (tcgen05 expansion kernel in bf16 mode).
+    if (c->schedule < 0 || c->schedule > CUMIND_SCHED_TEAM) return fail("unknown schedule");
+    if (c->schedule != CUMIND_SCHED_WARP) {
+        TeamPlan tp;
+        if (plan_team(t, n, c, tp, why) == 0) {
+            tp.p.root_hidden = d_root_hidden;
+            tp.p.noise = d_noise;
+            tp.p.out_visits = d_out_visits;
+            tp.p.out_probs = d_out_probs;
+            tp.p.out_root_value = d_out_root_value;
+            CM_CUDA(launch_search_team(tp.G, tp.p, tp.grid, tp.block, tp.smem, (cudaStream_t)stream));
+            g_launches += 1;
+            return 0;
+        }
+    }
     if (plan_fused(t, n, c, pl, why) != 0)
         return cumind_search_stepwise(t, n, d_root_hidden, c, d_noise, d_out_visits, d_out_probs, d_out_root_value, stream);
     pl.p.root_hidden = d_root_hidden;
@@ -646,12 +808,40 @@ extern "C" int cumind_search(cumind_tree* t, const cumind_net* n, const float* d
 }
 
 // introspection for tests / bench: the launch configuration cumind_search would use
-extern "C" int cumind_search_plan(const cumind_tree* t, const cumind_net* n, const cumind_search_cfg* c, int32_t* out /*[6]*/) {
+extern "C" int cumind_search_plan(const cumind_tree* t, const cumind_net* n, const cumind_search_cfg* c, int32_t* out /*[8]*/) {
     if (!t || !n || !c || !out) return fail("cumind_search_plan: NULL argument");
-    FusedPlan pl;
     std::string why;
-    if (plan_fused(t, n, c, pl, why) != 0) { out[0] = 0; return 0; }
-    out[0] = 1; out[1] = pl.G; out[2] = pl.R; out[3] = pl.grid; out[4] = pl.block; out[5] = (int32_t)pl.smem;
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    if (c->schedule != CUMIND_SCHED_WARP) {
+        TeamPlan tp;
+        if (plan_team(t, n, c, tp, why) == 0) {
+            out[0] = CUMIND_SCHED_TEAM; out[1] = tp.G; out[2] = tp.p.tpt; out[3] = tp.grid; out[4] = tp.block;
+            out[5] = (int32_t)tp.smem; out[6] = tp.p.n_team; out[7] = tp.p.nmw;
+            return 0;
+        }
+    }
+    FusedPlan pl;
+    if (plan_fused(t, n, c, pl, why) != 0) return 0;
+    out[0] = CUMIND_SCHED_WARP; out[1] = pl.G; out[2] = pl.R; out[3] = pl.grid; out[4] = pl.block; out[5] = (int32_t)pl.smem;
+    return 0;
+}
+
+extern "C" int cumind_search_phase_clocks(cumind_tree* t, const cumind_net* n, const float* d_root_hidden, const cumind_search_cfg* c,
+                                          const double* d_noise, int32_t* d_out_visits, double* d_out_probs,
+                                          double* d_out_root_value, int64_t* d_clocks, void* stream) {
+    if (check_search("cumind_search_phase_clocks", t, n, c, d_noise)) return 1;
+    if (!d_root_hidden || !d_out_visits || !d_out_probs || !d_clocks) return fail("cumind_search_phase_clocks: NULL device pointer");
+    TeamPlan tp;
+    std::string why;
+    if (plan_team(t, n, c, tp, why) != 0) return fail("cumind_search_phase_clocks: " + why);
+    tp.p.root_hidden = d_root_hidden;
+    tp.p.noise = d_noise;
+    tp.p.out_visits = d_out_visits;
+    tp.p.out_probs = d_out_probs;
+    tp.p.out_root_value = d_out_root_value;
+    tp.p.clk = (long long*)d_clocks;
+    CM_CUDA(launch_search_team(tp.G, tp.p, tp.grid, tp.block, tp.smem, (cudaStream_t)stream));
+    g_launches += 1;
     return 0;
 }
 

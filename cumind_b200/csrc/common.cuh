@@ -134,6 +134,36 @@ inline FusedPackLayout make_fused_pack_layout(int H, int L, int A) {
     return p;
 }
 
+// Parameters as the TEAM search kernel (search_team.cu) wants them in shared memory ("tpack"):
+//   emb [A][H] | L x ( W_l [H][Hp] | b_l [Hp] ) | Wh [H][HP] | bh [HP] | WhT [HP][H]
+// (WhT = the head matrix transposed: a head chain reads four consecutive k of its column with one LDS.128.)
+// W_l is the layer kernel k-major with the output neurons padded to Hp = round_up(H, 64) (zeros): the
+// lane that owns neurons j..j+NV-1 reads them with one LDS.64/128 per k, conflict-free across the warp.
+// (dup = 1 stores every weight twice, {w,w}: packed-FFMA2 operand form, measured slower on B200 and unused.)
+struct TeamPackLayout {
+    int H, L, A, HP, Hp, dup;
+    size_t emb, layers, layer_stride, heads_w, heads_b, heads_wt, total;  // float offsets
+    CM_HOST_DEVICE size_t layer_w(int l) const { return layers + (size_t)l * layer_stride; }
+    CM_HOST_DEVICE size_t layer_b(int l) const { return layer_w(l) + (size_t)H * Hp * (dup ? 2 : 1); }
+};
+
+inline TeamPackLayout make_team_pack_layout(int H, int L, int A, int dup) {
+    TeamPackLayout p;
+    p.H = H; p.L = L; p.A = A; p.dup = dup;
+    p.HP = (A + 2 + 3) & ~3;
+    p.Hp = (H + 63) & ~63;
+    auto al = [](size_t x) { return (x + 3) & ~(size_t)3; };
+    size_t o = 0;
+    p.emb = o;     o = al(o + (size_t)A * H);
+    p.layer_stride = al((size_t)H * p.Hp * (dup ? 2 : 1) + p.Hp);
+    p.layers = o;  o = al(o + (size_t)L * p.layer_stride);
+    p.heads_w = o; o = al(o + (size_t)H * p.HP);
+    p.heads_b = o; o = al(o + (size_t)p.HP);
+    p.heads_wt = o; o = al(o + (size_t)p.HP * H);
+    p.total = o;
+    return p;
+}
+
 // Parameters for the tensor-core (bf16) network kernel: bf16 weight tiles in the UMMA K-major
 // core-matrix layout ([k/8][n/8][n%8][k%8], one tile per layer with rows n = output neuron, then the
 // head tile with NP = 16 rows: policy 0..A-1, value A, reward A+1, zero padded), followed by the
@@ -222,6 +252,17 @@ CM_DEVICE float2 ffma2(float x, float2 w, float2 acc) {
     asm("mov.b64 %0, {%1, %2};" : "=l"(ww) : "f"(w.x), "f"(w.y));
     asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(acc.x), "f"(acc.y));
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(dd) : "l"(xx), "l"(ww), "l"(aa));
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(dd));
+    return r;
+}
+// Fully packed form: d.{x,y} = fma(a.{x,y}, b.{x,y}, c.{x,y}).
+CM_DEVICE float2 ffma2v(float2 a, float2 b, float2 c) {
+    unsigned long long aa, bb, cc, dd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(dd) : "l"(aa), "l"(bb), "l"(cc));
     float2 r;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(dd));
     return r;

@@ -27,6 +27,34 @@ struct FusedParams {
 // search_fused.cu
 cudaError_t launch_search_fused(int G, int R, const FusedParams& p, int grid, int block, size_t smem, cudaStream_t st);
 
+// search_team.cu — the same search with warp-specialised teams (tree warps + network warps)
+struct TeamParams {
+    TreeView tv;
+    const float* pack;      // device, TeamPackLayout order
+    TeamPackLayout pk;
+    const float* root_hidden;  // [B][H]
+    const double* noise;       // [B][A] or nullptr
+    int32_t* out_visits;       // [B][A_cfg]
+    double* out_probs;         // [B][A_cfg]
+    double* out_root_value;    // [B] or nullptr
+    int S, A_cfg, A_net;
+    double c_puct, frac, one_minus_frac, alpha;
+    int noise_mode;
+    unsigned long long seed, tree_base;
+    int path_in_smem;
+    // team geometry: n_team teams per CTA, each ntw tree warps + nmw network warps; TT tree slots per
+    // team (compile-time in the kernel: 8 or 16), of which tpt are used per batch
+    int n_team, ntw, nmw, TT, tpt, n_batches;
+    int tile;                  // lane tile of the network warps (0 = default; see launch_search_team)
+    int stagger;               // SM cycles between the starts of the teams of one CTA
+    // shared-memory carve-up (bytes); off_path / off_hotw / off_hot are relative to the team's scratch
+    unsigned off_sqrt, off_recip, off_teams, team_bytes, off_bar, off_path, off_hotw, off_hot;
+    int n_sqrt;
+    long long* clk;            // [grid][16] phase clocks (diagnostic) or nullptr
+};
+bool team_variant_ok(int G, int TT);
+cudaError_t launch_search_team(int G, const TeamParams& p, int grid, int block, size_t smem, cudaStream_t st);
+
 // tree_steps.cu — one launch per phase (warp per tree, any H / A)
 struct StepParams {
     TreeView tv;

@@ -45,9 +45,6 @@ CM_DEVICE void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes
 
 // GS = lanes per tree in the select / expand / backup phases (TW = 32/GS trees per warp);
 // R = neurons per lane in the warp-cooperative network tile (32*R >= H).
-// e / s of the softmax; a saturated softmax produces exact zeros, which would send the IEEE
-// division down its slow special-case path: 0 / s == 0 exactly for the finite s >= 1 of a softmax.
-CM_DEVICE float prior_div(float e, float s) { return (e == 0.0f && s >= 1.0f) ? 0.0f : __fdiv_rn(e, s); }
 
 template <int GS, int R>
 __global__ void __launch_bounds__(512, 1) search_fused_kernel(const FusedParams p) {

@@ -116,6 +116,10 @@ class MCTS:
         self._lib = _native.load()
         self._slab: Optional[_TreeSlab] = None
         self.lanes_per_tree = 0          # 0 = auto
+        self.schedule = _native.SCHED_AUTO   # launch tuning (no effect on results): see cumind_search_cfg
+        self.teams_per_cta = 0
+        self.net_warps_per_team = 0
+        self.trees_per_team = 0
         self.stepwise = False            # True: one launch per phase (cumind_search_stepwise)
         self.last_cfg: Optional[_native.SearchCfg] = None
 
@@ -141,6 +145,10 @@ class MCTS:
         cfg.net_mode = self.network.net_mode
         cfg.tree_mode = _native.TREE_REFERENCE
         cfg.lanes_per_tree = int(self.lanes_per_tree)
+        cfg.schedule = int(self.schedule)
+        cfg.teams_per_cta = int(self.teams_per_cta)
+        cfg.net_warps_per_team = int(self.net_warps_per_team)
+        cfg.trees_per_team = int(self.trees_per_team)
         cfg.seed = int(seed) & (2**64 - 1)
         cfg.tree_index_base = int(tree_index_base)
         return cfg
@@ -203,10 +211,17 @@ class MCTS:
         """Launch configuration cumind_search would use for B trees with the current config."""
         A = min(int(self.config.action_space_size), self.network.action_space_size)
         tree = self._tree(B, int(self.config.num_simulations), A)
-        out = (C.c_int32 * 6)()
+        out = (C.c_int32 * 8)()
         cfg = self._cfg(0)
         _native.check(self._lib.cumind_search_plan(tree.handle, self.network._handle, C.byref(cfg), C.byref(out)))
-        return dict(zip(("fused", "lanes_per_tree", "outputs_per_lane", "grid", "block", "smem_bytes"), (int(x) for x in out)))
+        v = [int(x) for x in out]
+        plan = {"fused": 1 if v[0] else 0, "schedule": {0: "stepwise", 1: "warp", 2: "team"}[v[0]], "lanes_per_tree": v[1],
+                "grid": v[3], "block": v[4], "smem_bytes": v[5]}
+        if v[0] == _native.SCHED_TEAM:
+            plan.update(trees_per_team=v[2], teams_per_cta=v[6], net_warps_per_team=v[7])
+        else:
+            plan.update(outputs_per_lane=v[2])
+        return plan
 
     # ---- inspection ----------------------------------------------------------------------------
     def dump_trees(self) -> Dict[str, np.ndarray]:

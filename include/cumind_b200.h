@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CUMIND_ABI_VERSION 1
+#define CUMIND_ABI_VERSION 2
 
 /* ------------------------------------------------------------------------------------------
  * Network descriptor + flat parameter blob.
@@ -87,7 +87,19 @@ typedef struct cumind_search_cfg {
     uint64_t seed;                /* Philox key for noise_mode 2                             */
     uint64_t tree_index_base;     /* global index of local tree 0 (multi-GPU sharding: results
                                      do not depend on the GPU count)                         */
+    /* launch tuning of cumind_search; none of these changes a result bit */
+    int32_t schedule;             /* CUMIND_SCHED_*: 0 = auto                                */
+    int32_t teams_per_cta;        /* team schedule: 0 = auto, else 1..7                      */
+    int32_t net_warps_per_team;   /* team schedule: 0 = auto (4), else 1..8                  */
+    int32_t trees_per_team;       /* team schedule: 0 = auto, else tree slots used per batch */
 } cumind_search_cfg;
+
+/* How cumind_search maps the work onto the GPU (all produce identical results):
+ *   WARP  search_fused.cu: every group of `lanes_per_tree` lanes runs the whole search of one tree
+ *   TEAM  search_team.cu : warp-specialised teams (tree-walk warps + network warps), see DESIGN.md */
+#define CUMIND_SCHED_AUTO 0
+#define CUMIND_SCHED_WARP 1
+#define CUMIND_SCHED_TEAM 2
 
 typedef struct cumind_net  cumind_net;   /* opaque: packed parameters on one device  */
 typedef struct cumind_tree cumind_tree;  /* opaque: view over a caller-owned SoA slab */
@@ -178,10 +190,21 @@ int cumind_search(cumind_tree* tree, const cumind_net* net, const float* d_root_
                   int32_t* d_out_visits, double* d_out_probs, double* d_out_root_value,
                   void* stream);
 
-/* The launch configuration cumind_search would use: out = {fused(0/1), lanes per tree G,
- * outputs per lane R, grid, block, dynamic shared memory bytes}. */
+/* The launch configuration cumind_search would use: out = {schedule (0 = stepwise fallback,
+ * CUMIND_SCHED_WARP, CUMIND_SCHED_TEAM), lanes per tree G, WARP: outputs per lane R / TEAM: trees
+ * per team batch, grid, block, dynamic shared memory bytes, TEAM: teams per CTA, TEAM: network
+ * warps per team}. */
 int cumind_search_plan(const cumind_tree* tree, const cumind_net* net, const cumind_search_cfg* cfg,
-                       int32_t* out6);
+                       int32_t* out8);
+
+/* Diagnostic: cumind_search on the TEAM schedule with phase clocks.  d_clocks is a zero-initialised
+ * device int64[grid*16] (grid from cumind_search_plan): per CTA, SM cycles spent by tree warp 0 of
+ * team 0 in {select, waiting for the network, softmax+expand+backup, root+final} and by network
+ * warp 0 in {gather, layers, heads, waiting for the tree warps}. */
+int cumind_search_phase_clocks(cumind_tree* tree, const cumind_net* net, const float* d_root_hidden,
+                               const cumind_search_cfg* cfg, const double* d_noise,
+                               int32_t* d_out_visits, double* d_out_probs, double* d_out_root_value,
+                               int64_t* d_clocks, void* stream);
 
 /* Same search issued as separate kernels per phase (the fine-grained entry points below);
  * used by the tests to cross-check the fused kernel and by ncu to attribute time per phase. */

@@ -67,15 +67,17 @@ def test_network_bit_exact_vs_golden(case):
     assert hp.bits_equal(net.representation_network(d["obs"]).cpu().numpy(), d["h"])
 
 
-@pytest.mark.parametrize("stepwise", [False, True], ids=["fused", "stepwise"])
+@pytest.mark.parametrize("path", ["team", "warp", "stepwise"])
 @pytest.mark.parametrize("case", SEARCH, ids=[c["id"] for c in SEARCH])
-def test_search_matches_reference_trees(case, stepwise):
+def test_search_matches_reference_trees(case, path):
+    from cumind_b200 import _native
     from cumind_b200.mcts import MCTS
 
     d = hp.search_case_data(case)
     net = _network(case["obs_shape"], case["A_net"], case["H"], case["L"], 32, d["params"])
     mcts = MCTS(net, _Cfg(case["S"], case["A_cfg"], case["c_puct"], case["alpha"], case["frac"]))
-    mcts.stepwise = stepwise
+    mcts.stepwise = path == "stepwise"
+    mcts.schedule = {"team": _native.SCHED_TEAM, "warp": _native.SCHED_WARP, "stepwise": _native.SCHED_AUTO}[path]
     noise = None if d["noise"] is None else d["noise"][None]
     probs, visits = mcts.search_batch(d["root_h"][None], noise=noise)
     A = min(case["A_net"], case["A_cfg"])
@@ -91,6 +93,7 @@ def test_search_matches_reference_trees(case, stepwise):
 @pytest.mark.parametrize("shape", [(2, 64, 50), (4, 64, 50), (18, 32, 25), (3, 16, 30), (2, 128, 25), (5, 24, 20)],
                          ids=lambda s: f"A{s[0]}H{s[1]}S{s[2]}")
 def test_fused_search_vs_oracle_all_lane_mappings(shape, lanes):
+    from cumind_b200 import _native
     from cumind_b200.mcts import MCTS
     from oracle import network_np as nn
 
@@ -107,9 +110,81 @@ def test_fused_search_vs_oracle_all_lane_mappings(shape, lanes):
     o = lo.search(desc, blob, h, S, A, 1.25, 0.25, noise)
     mcts = MCTS(net, _Cfg(S, A))
     mcts.lanes_per_tree = lanes
+    mcts.schedule = _native.SCHED_WARP
+    assert mcts.plan(B)["schedule"] == "warp"
     probs, visits = mcts.search_batch(h, noise=noise)
     _assert_trees_equal(mcts, o, S, A)
     assert np.array_equal(visits, o["out_visits"]) and np.array_equal(probs, o["out_probs"])
+
+
+_team_cases = {}
+
+
+def _team_case(A, H, S, B):
+    from oracle import network_np as nn
+
+    key = (A, H, S, B)
+    if key not in _team_cases:
+        blob = nn.flatten_params(nn.random_params((4,), A, H, 2, 32, 11 + A, bias_scale=0.05), (4,))
+        rng = np.random.default_rng(A * 1000 + H)
+        obs = rng.standard_normal((B, 4)).astype(np.float32)
+        desc = lo.make_desc((4,), A, H, 2)
+        h, _, _ = lo.initial_inference(desc, blob, obs)
+        noise = rng.dirichlet([0.3] * A, size=B)
+        _team_cases[key] = (lo.search(desc, blob, h, S, A, 1.25, 0.25, noise), h, noise, blob)
+    return _team_cases[key]
+
+
+# (teams per CTA, network warps per team, tree slots per team, lanes per tree); 0 = the planner's choice
+TEAM_GEOMETRIES = [(0, 0, 0, 0), (1, 4, 0, 0), (3, 2, 8, 0), (2, 1, 4, 0), (4, 3, 16, 0), (2, 8, 11, 0), (6, 4, 0, 0), (1, 2, 5, 32), (2, 4, 16, 4)]
+
+
+@pytest.mark.parametrize("geom", TEAM_GEOMETRIES, ids=lambda g: "T%dM%dS%dG%d" % g)
+@pytest.mark.parametrize("shape", [(2, 64, 50), (4, 64, 50), (18, 32, 25), (3, 16, 30), (2, 128, 25), (5, 24, 20), (1, 32, 7)],
+                         ids=lambda s: f"A{s[0]}H{s[1]}S{s[2]}")
+def test_team_search_vs_oracle_all_geometries(shape, geom):
+    """search_team.cu (tree warps + network warps) against the C oracle: every array of every tree, for
+    every team geometry the launch knobs can produce (ragged last batch: B is not a multiple of anything)."""
+    from cumind_b200 import _native
+    from cumind_b200.mcts import MCTS
+
+    A, H, S = shape
+    B = 1237
+    o, h, noise, blob = _team_case(A, H, S, B)
+    net = _network((4,), A, H, 2, 32, blob)
+    mcts = MCTS(net, _Cfg(S, A))
+    mcts.schedule = _native.SCHED_TEAM
+    mcts.teams_per_cta, mcts.net_warps_per_team, mcts.trees_per_team, mcts.lanes_per_tree = geom
+    plan = mcts.plan(B)
+    assert plan["schedule"] == "team", plan
+    probs, visits = mcts.search_batch(h, noise=noise)
+    _assert_trees_equal(mcts, o, S, A)
+    assert np.array_equal(visits, o["out_visits"]) and np.array_equal(probs, o["out_probs"])
+    assert hp.bits_equal(mcts.last_root_value.cpu().numpy(), o["out_root_value"])
+
+
+@pytest.mark.parametrize("c_puct", [1e290, 3e-300, 0.0, float("inf")], ids=["huge", "tiny", "zero", "inf"])
+def test_team_search_leaves_the_bare_division_when_it_is_not_exact(c_puct):
+    """The team kernel's walk divides with the bare Markstein sequence only while c_puct*prior stays in the
+    range where that is the correctly rounded quotient; outside (huge / tiny / infinite c_puct) the trees take
+    the range-checked walk.  Either way: the oracle's trees, bit for bit."""
+    from cumind_b200 import _native
+    from cumind_b200.mcts import MCTS
+    from oracle import network_np as nn
+
+    A, H, S, B = 3, 32, 20, 300
+    blob = nn.flatten_params(nn.random_params((4,), A, H, 2, 32, 21, bias_scale=0.05), (4,))
+    net = _network((4,), A, H, 2, 32, blob)
+    rng = np.random.default_rng(17)
+    h = rng.standard_normal((B, H)).astype(np.float32)
+    noise = rng.dirichlet([0.3] * A, size=B)
+    o = lo.search(lo.make_desc((4,), A, H, 2), blob, h, S, A, c_puct, 0.25, noise)
+    for schedule in (_native.SCHED_TEAM, _native.SCHED_WARP):
+        mcts = MCTS(net, _Cfg(S, A, c_puct=c_puct))
+        mcts.schedule = schedule
+        probs, visits = mcts.search_batch(h, noise=noise)
+        _assert_trees_equal(mcts, o, S, A)
+        assert np.array_equal(visits, o["out_visits"]) and np.array_equal(probs, o["out_probs"])
 
 
 def _assert_trees_equal(mcts, o, S, A):
@@ -128,6 +203,7 @@ def _assert_trees_equal(mcts, o, S, A):
 
 def test_baseline_config2_full_size_bit_exact():
     """BASELINE configs[1]: B=4096 CartPole-shaped trees, 50 simulations, fp32 — every tree bit-exact."""
+    from cumind_b200 import _native
     from cumind_b200.mcts import MCTS
     from oracle import network_np as nn
 
@@ -143,10 +219,12 @@ def test_baseline_config2_full_size_bit_exact():
     h_gpu = net.representation_network(obs)
     assert hp.bits_equal(h_gpu.cpu().numpy(), h)
     o = lo.search(desc, blob, h, S, A, 1.25, 0.25, noise)
-    mcts = MCTS(net, _Cfg(S, A))
-    probs, visits = mcts.search_batch(h_gpu, noise=noise)
-    _assert_trees_equal(mcts, o, S, A)
-    assert np.array_equal(visits, o["out_visits"]) and np.array_equal(probs, o["out_probs"])
+    for schedule in (_native.SCHED_WARP, _native.SCHED_TEAM):
+        mcts = MCTS(net, _Cfg(S, A))
+        mcts.schedule = schedule
+        probs, visits = mcts.search_batch(h_gpu, noise=noise)
+        _assert_trees_equal(mcts, o, S, A)
+        assert np.array_equal(visits, o["out_visits"]) and np.array_equal(probs, o["out_probs"])
     # size-independent properties of the reference semantics
     assert np.all(mcts.dump_trees()["visit"][:, 0] == 2 * S)
     assert np.all(visits.sum(axis=1) == S - A)
