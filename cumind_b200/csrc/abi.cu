@@ -677,7 +677,7 @@ static int plan_team(const cumind_tree* t, const cumind_net* n, const cumind_sea
     const size_t off_sqrt = al16(pack_bytes);
     const size_t off_recip = al16(off_sqrt + (size_t)n_sqrt * sizeof(double));
     const size_t off_teams = (off_recip + (size_t)n_sqrt * sizeof(double) + 127) & ~(size_t)127;
-    const size_t team_base = al16((size_t)(2 * H * XS + TT * (H + 4) + 2 * TT * pk.HP + 3 * TT) * 4);
+    const size_t team_base = al16((size_t)(2 * H * XS + TT * (H + 4) + 2 * TT * pk.HP + 4 * TT) * 4);
     const size_t per_tree = (size_t)(S_max + 2) * sizeof(int) + (size_t)N * 40;  // path + hot W + hot records
     const size_t kMax = 227 * 1024;
     if (off_teams + team_base + per_tree + 256 > kMax) { why = "one tree does not fit the team kernel's shared memory"; return 1; }

@@ -291,6 +291,31 @@ CM_DEVICE double pexp(double d) {
     return __dmul_rn(p, scale);
 }
 
+// pexp without branches (same operations on the same values, the special cases selected at the end): keeps
+// the instruction stream of a latency-bound caller straight.
+CM_DEVICE double pexp_nb(double d) {
+    const bool is_nan = d != d;
+    const bool vanishes = !(d >= -200.0);  // also true for NaN, which is restored below
+    double x = d > 0.0 ? 0.0 : d;
+    x = vanishes ? 0.0 : x;
+    const double LOG2E = 1.4426950408889634;
+    const double LN2_HI = 6.93147180369123816490e-01;
+    const double LN2_LO = 1.90821492927058770002e-10;
+    const double kf = rint(__dmul_rn(x, LOG2E));
+    const double r = __dsub_rn(__dsub_rn(x, __dmul_rn(kf, LN2_HI)), __dmul_rn(kf, LN2_LO));
+    const double C[14] = {1.0, 1.0, 0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0,
+                          1.0 / 40320.0, 1.0 / 362880.0, 1.0 / 3628800.0, 1.0 / 39916800.0,
+                          1.0 / 479001600.0, 1.0 / 6227020800.0};
+    double p = C[13];
+#pragma unroll
+    for (int i = 12; i >= 0; --i) p = __dadd_rn(__dmul_rn(p, r), C[i]);
+    const int k = __double2int_rn(kf);  // integral, -289 <= k <= 0
+    const double scale = __hiloint2double((k + 1023) << 20, 0);
+    double res = __dmul_rn(p, scale);
+    res = vanishes ? 0.0 : res;
+    return is_nan ? d : res;
+}
+
 // Node.ucb_score (mcts.py:51-65): inf if n == 0 else W/n + ((c*p)*sqrt(N))/(1+n), float64.
 // `sqrtN` is __dsqrt_rn((double)N_parent) (correctly rounded, same as math.sqrt).
 // a / d for a small positive integer d, correctly rounded, from r = RN(1/d):

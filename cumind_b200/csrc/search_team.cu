@@ -132,10 +132,27 @@ CM_DEVICE void sts32_pred(uint32_t addr, int v, int pred) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.shared.s32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"(pred) : "memory");
 }
 
+CM_DEVICE void sts64_pred(uint32_t addr, double v, int pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.shared.f64 [%0], %1;\n\t}" ::"r"(addr), "d"(v), "r"(pred) : "memory");
+}
+CM_DEVICE void sts128_s(uint32_t addr, int a, int b, int c, int d) {
+    asm volatile("st.shared.v4.s32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+CM_DEVICE int lds32_s(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 // c_puct*prior values for which the bare Markstein division of select_hot_fast is exact
 CM_DEVICE bool cp_is_safe(double cp) {
-    const double m = fabs(cp);
-    return cp == 0.0 || cp != cp || (m >= 1.2114454386347773e-268 /* 2^-890 */ && m <= 8.254601404463519e+267 /* 2^890 */);
+    // 0, NaN, or a biased exponent in [1023-890, 1023+890): integer tests on the high word
+    const unsigned hi = (unsigned)__double2hiint(cp) & 0x7fffffffu;
+    const unsigned lo = (unsigned)__double2loint(cp);
+    const unsigned ex = hi >> 20;
+    const bool zero = (hi | lo) == 0u;
+    const bool nan = hi > 0x7ff00000u || (hi == 0x7ff00000u && lo != 0u);
+    return zero || nan || (ex - 133u) < 1780u;
 }
 
 template <int G, int SPAN>
@@ -277,37 +294,100 @@ CM_DEVICE int select_hot_any(const HotSel* __restrict__ hs, const double* __rest
 
 // Backup on the hot records (mcts.py:199-203): every parent on the path gets n += 1, W += v, the root
 // (path[0]) a second time; the value term q = W/n and RN(1/(1+n)) are refreshed here so that the next
-// walk does not have to.  Up to four path entries per lane are in flight at once.
-template <int G>
-CM_DEVICE void backup_hot(HotSel* __restrict__ hs, double* __restrict__ hw, const int* __restrict__ path, int plen,
-                          float leaf_value, const double* __restrict__ recip, int g) {
+// walk does not have to.  U path entries per lane are processed together with no branch in between (entries
+// past the end of the path stand in as the root and their stores are predicated off), so their dependency
+// chains overlap.  q = W/n is the Markstein sequence of div_small; a value sum outside the range where
+// that is exact (never in practice) is redone with the IEEE division after the block.  A zero sum stays on
+// the sequence (it yields a zero; the sign of a zero value term never reaches a decision: scores are
+// compared with -0 folded into +0, and root values are divided separately).
+template <int G, int U>
+CM_DEVICE void backup_hot(uint32_t hs_addr, uint32_t hw_addr, uint32_t path_addr, int plen, float leaf_value, uint32_t recip_addr,
+                          int g) {
     const double v = (double)leaf_value;
 #pragma unroll 1
-    for (int i0 = g; i0 < plen; i0 += 4 * G) {
-        int nd[4], n[4];
-        double w[4];
+    for (int i0 = g; i0 < plen; i0 += U * G) {
+        int nd[U], n[U], ok[U];
+        double w[U];
+        int slow = 0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int i = i0 + u * G;
-            nd[u] = i < plen ? path[i] : -1;
+            ok[u] = i < plen ? 1 : 0;
+            nd[u] = lds32_s(path_addr + 4u * (uint32_t)(ok[u] ? i : 0));
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (nd[u] >= 0) { w[u] = hw[nd[u]]; n[u] = hs[nd[u]].n; }
+        for (int u = 0; u < U; ++u) {
+            w[u] = lds64_s(hw_addr + 8u * (uint32_t)nd[u]);
+            n[u] = lds32_s(hs_addr + 32u * (uint32_t)nd[u] + 24u);
+        }
+        // the shared-memory accesses are volatile asm and keep their program order: all loads of all entries
+        // first, then the arithmetic, then all stores, or one entry's stores would fence the next entry's loads
+        double ww[U], rn[U], r1[U], q[U], d[U], t[U], e[U];
+        int nn[U];
+        // one operation of every entry at a time: a warp issues in order, so the U dependency chains only
+        // overlap if the instruction stream itself interleaves them
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (nd[u] >= 0) {
-                double ww = __dadd_rn(w[u], v);
-                int nn = n[u] + 1;
-                if (nd[u] == 0) { ww = __dadd_rn(ww, v); nn += 1; }
-                hw[nd[u]] = ww;
-                HotSel* h = hs + nd[u];
-                h->q = div_small(ww, (double)nn, recip[nn]);
-                h->r = recip[1 + nn];
-                h->n = nn;
+        for (int u = 0; u < U; ++u) ww[u] = __dadd_rn(w[u], v);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool root = nd[u] == 0;
+            const double w2 = __dadd_rn(ww[u], v);
+            ww[u] = root ? w2 : ww[u];
+            nn[u] = n[u] + (root ? 2 : 1);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            rn[u] = lds64_s(recip_addr + 8u * (uint32_t)nn[u]);
+            r1[u] = lds64_s(recip_addr + 8u * (uint32_t)nn[u] + 8u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) d[u] = (double)nn[u];
+#pragma unroll
+        for (int u = 0; u < U; ++u) t[u] = __dmul_rn(ww[u], rn[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) e[u] = __fma_rn(-d[u], t[u], ww[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) t[u] = __fma_rn(e[u], rn[u], t[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) e[u] = __fma_rn(-d[u], t[u], ww[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) q[u] = __fma_rn(e[u], rn[u], t[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned hi = (unsigned)__double2hiint(ww[u]) & 0x7fffffffu;
+            const bool exact = ((hi >> 20) - 123u) < 1800u || (hi | (unsigned)__double2loint(ww[u])) == 0u;
+            slow |= (ok[u] && !exact) ? 1 : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t rec = hs_addr + 32u * (uint32_t)nd[u];
+            sts64_pred(hw_addr + 8u * (uint32_t)nd[u], ww[u], ok[u]);
+            sts64_pred(rec, q[u], ok[u]);
+            sts64_pred(rec + 16u, r1[u], ok[u]);
+            sts32_pred(rec + 24u, nn[u], ok[u]);
+        }
+        if (slow) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (ok[u]) sts64_pred(hs_addr + 32u * (uint32_t)nd[u], __ddiv_rn(ww[u], (double)nn[u]), 1);
             }
         }
     }
+}
+
+// softmax over lg[0..A_net) with the pinned exp, straight-line per lane; every lane returns the sum
+template <int G>
+CM_DEVICE float softmax_team(const float* __restrict__ lg, float* __restrict__ e_buf, int A_net, int g, bool active) {
+    float m = lg[0];
+    for (int a = 1; a < A_net; ++a) { const float l = lg[a]; m = l > m ? l : m; }
+    for (int a = g; a < A_net; a += G) {
+        const float e = __double2float_rn(pexp_nb((double)__fsub_rn(lg[a], m)));
+        if (active) e_buf[a] = e;
+    }
+    __syncwarp();
+    float s = 0.0f;
+    for (int a = 0; a < A_net; ++a) s = fadd(s, e_buf[a]);
+    return s;
 }
 
 // ---- network warps -------------------------------------------------------------------------------
@@ -532,15 +612,15 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
     const float* wht_s = w_s + p.pk.heads_wt;
     const float* bh_s = w_s + p.pk.heads_b;
 
-    // team scratch: x0,x1 [H][XS] | xt [TT][H+4] | lg,eb [TT][HP] | sel [3][TT] | path [tpt][S_max+2] | hot W [tpt][N] | hot records [tpt][N]
+    // team scratch: x0,x1 [H][XS] | xt [TT][H+4] | lg,eb [TT][HP] | sel [4][TT] | path [tpt][S_max+2] | hot W [tpt][N] | hot records [tpt][N]
     unsigned char* my = smem + p.off_teams + (size_t)team * p.team_bytes;
     float* x0 = reinterpret_cast<float*>(my);
     float* x1 = x0 + (size_t)H * XS;
     float* xt = x1 + (size_t)H * XS;
     float* lg_t = xt + (size_t)TT * (H + 4);
     float* eb_t = lg_t + TT * HP;
-    int* sel = reinterpret_cast<int*>(eb_t + TT * HP);   // [2][TT] selection, then [TT] "needs the checked walk" flags
-    int* unsafe_t = sel + 2 * TT;
+    int* sel = reinterpret_cast<int*>(eb_t + TT * HP);   // [3][TT] parent_e, action, path length; then [TT] "checked walk" flags
+    int* unsafe_t = sel + 3 * TT;
     int* path_t = reinterpret_cast<int*>(my + p.off_path);
     double* hw_t = reinterpret_cast<double*>(my + p.off_hotw);
     HotSel* hs_t = reinterpret_cast<HotSel*>(my + p.off_hot);
@@ -548,7 +628,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
     const int cnt_team = team_warps * 32, cnt_mlp = p.nmw * 32;
     const size_t hstride = (size_t)(S_max + 1) * H;
     const bool clk_on = p.clk != nullptr && team == 0 && lane == 0 && (wt == 0 || wt == p.ntw);
-    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, tmark = 0;
+    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, tmark = 0;
     if (clk_on) tmark = clock64();
     // Phase clocks (diagnostic).  The clock read sits behind a branch on a value that only exists once the
     // phase is over (a load that follows the barrier, a result of the loop): neither nvcc nor ptxas can
@@ -592,6 +672,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
             HotSel* hs = hs_t + (size_t)tsc * N;
             double* hw = hw_t + (size_t)tsc * N;
             const uint32_t hs_addr = smem_addr(hs), sq_addr = smem_addr(sq_s), path_addr = smem_addr(path);
+            const uint32_t hw_addr = smem_addr(hw), rc_addr = smem_addr(rc_s);
             int* unsafe = unsafe_t + tsc;
 
             // ---- root: softmax of the root logits -> expand -> noise (mcts.py:126-136) -------------
@@ -602,7 +683,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
             if (active && g == 0) *unsafe = 0;
             __syncwarp();
             {
-                const float ssum = softmax_prepare<G>(lg, eb, A_net, g, active);
+                const float ssum = softmax_team<G>(lg, eb, A_net, g, active);
                 if (active) {
                     for (int a = g; a < A; a += G) {
                         const float p32 = prior_div(eb[a], ssum);
@@ -645,29 +726,33 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
                 if (g == 0 && ts < TT) {
                     sel[ts] = active ? parent_e : 0;
                     sel[TT + ts] = active ? action : 0;
+                    sel[2 * TT + ts] = active ? plen : 0;
                 }
                 CM_CLK(c0, plen + leaf)
                 named_bar_sync(bar_team, cnt_team);  // (A) selection published
                 named_bar_sync(bar_team, cnt_team);  // (B) logits + value published
                 CM_CLK(c1, __float_as_int(lg[A_net]))
                 const int k = s + 1;  // expansion index of the leaf
-                const float ssum = softmax_prepare<G>(lg, eb, A_net, g, active);
+                const float ssum = softmax_team<G>(lg, eb, A_net, g, active);
+                CM_CLK(c5, __float_as_int(ssum))   // softmax alone; c6: expansion; c2: the backup that follows
                 if (active) {
                     const float value = lg[A_net];
                     const int cbase = 1 + k * A;
                     for (int a = g; a < A; a += G) {
                         const float p32 = prior_div(eb[a], ssum);
                         store_node(nodes + cbase + a, 0.0, 0, p32);
-                        HotSel h;
-                        h.q = 0.0; h.cp = __dmul_rn(p.c_puct, (double)p32); h.r = 1.0; h.n = 0; h.ce = -1;
-                        hs[cbase + a] = h;
-                        hw[cbase + a] = 0.0;
-                        if (!cp_is_safe(h.cp)) *unsafe = 1;
+                        const double cp = __dmul_rn(p.c_puct, (double)p32);
+                        const uint32_t rec = hs_addr + 32u * (uint32_t)(cbase + a);
+                        sts128_s(rec, 0, 0, __double2loint(cp), __double2hiint(cp));       // q = 0, cp
+                        sts128_s(rec + 16u, 0, 0x3ff00000, 0, -1);                          // r = 1.0, n = 0, ce = -1
+                        sts64_pred(hw_addr + 8u * (uint32_t)(cbase + a), 0.0, 1);
+                        if (!cp_is_safe(cp)) *unsafe = 1;
                     }
                     if (g == 0) { hs[leaf].ce = k; exp_node[k] = leaf; }
-                    backup_hot<G>(hs, hw, path, plen, value, rc_s, g);
                     depth += plen;
                 }
+                CM_CLK(c6, hs[1].n)
+                named_bar_sync(bar_team, cnt_team);  // (C) the network warps have backed the value up
                 __syncwarp();
                 CM_CLK(c2, hs[0].n)
             }
@@ -675,6 +760,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
             // ---- statistics -> canonical records; visit counts -> probabilities (mcts.py:143-155) ---
             if (active) {
                 const int used = 1 + A * (p.S + 1);
+#pragma unroll 4
                 for (int i = g; i < used; i += G) {
                     nodes[i].value_sum = hw[i];
                     nodes[i].visit = hs[i].n;
@@ -753,13 +839,39 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
                 __syncwarp();
                 CM_CLK(c2, __float_as_int(lg_t[0]))
                 named_bar_sync(bar_team, cnt_team);  // (B) logits + value published
+                // Backup (mcts.py:199-203) on the network warps, one path entry per lane, while the tree warps
+                // turn the logits into the new node's children: W += v, n += 1 on every parent of the path, the
+                // root (path[0]) twice; q = W/n and RN(1/(1+n)) refreshed for the next walk.
+                {
+                    const int ts = mlane % TT;
+                    if (ts < n_here) {
+                        const int plen = sel[2 * TT + ts];
+                        const double v = (double)lg_t[ts * HP + A_net];
+                        const int* path = path_t + ts * (S_max + 2);
+                        HotSel* hs = hs_t + (size_t)ts * N;
+                        double* hw = hw_t + (size_t)ts * N;
+                        for (int i = mlane / TT; i < plen; i += nml / TT) {
+                            const int nd = path[i];
+                            const bool root = nd == 0;
+                            const double w1 = __dadd_rn(hw[nd], v);
+                            const double ww = root ? __dadd_rn(w1, v) : w1;
+                            const int nn = hs[nd].n + (root ? 2 : 1);
+                            hw[nd] = ww;
+                            hs[nd].q = div_small(ww, (double)nn, rc_s[nn]);
+                            hs[nd].r = rc_s[1 + nn];
+                            hs[nd].n = nn;
+                        }
+                    }
+                }
+                CM_CLK(c5, hs_t[0].n)
+                named_bar_sync(bar_team, cnt_team);  // (C) statistics updated
             }
         }
     }
 #undef CM_CLK
     if (clk_on) {
         long long* o = p.clk + (size_t)blockIdx.x * 16 + (is_tree ? 0 : 8);
-        o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3; o[4] = c4;
+        o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3; o[4] = c4; o[5] = c5; o[6] = c6;
     }
 }
 
