@@ -809,18 +809,43 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
             for (int s = 0; s < p.S; ++s) {
                 named_bar_sync(bar_team, cnt_team);  // (A) selection published
                 CM_CLK(c3, sel[0])
-                // gather: x0[j][ts] = hidden[ts][parent_e][j] + Emb[action][j]   (network.py:229-230)
-                for (int i = mlane; i < TT * H4; i += nml) {
-                    const int ts = i / H4, c = i - ts * H4;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ts < n_here) {
-                        const int pe = sel[ts], ac = sel[TT + ts];
-                        const float4 hv = *reinterpret_cast<const float4*>(hid0 + (size_t)ts * hstride + (size_t)pe * H + 4 * c);
-                        const float4 ev = *reinterpret_cast<const float4*>(emb_s + (size_t)ac * H + 4 * c);
-                        v.x = fadd(hv.x, ev.x); v.y = fadd(hv.y, ev.y); v.z = fadd(hv.z, ev.z); v.w = fadd(hv.w, ev.w);
+                // gather: x0[j][ts] = hidden[ts][parent_e][j] + Emb[action][j]   (network.py:229-230).
+                // Two items per lane and pass with both global loads in flight before either is used (the
+                // parent rows come from L2); with a compile-time H the item -> (tree, chunk) split is shifts.
+                {
+                    const int H4c = HS > 0 ? HS / 4 : H4;
+                    for (int i0 = mlane; i0 < TT * H4c; i0 += 2 * nml) {
+                        int ts[2], c[2];
+                        bool on[2];
+                        float4 hv[2], ev[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int i = i0 + u * nml;
+                            ts[u] = i / H4c;
+                            c[u] = i - ts[u] * H4c;
+                            on[u] = i < TT * H4c && ts[u] < n_here;
+                            hv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            ev[u] = hv[u];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            if (on[u]) {
+                                const int pe = sel[ts[u]], ac = sel[TT + ts[u]];
+                                hv[u] = *reinterpret_cast<const float4*>(hid0 + (size_t)ts[u] * hstride + (size_t)pe * H + 4 * c[u]);
+                                ev[u] = *reinterpret_cast<const float4*>(emb_s + (size_t)ac * H + 4 * c[u]);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            if (i0 + u * nml < TT * H4c) {
+                                float* xd = x0 + (size_t)(4 * c[u]) * XS + ts[u];
+                                xd[0] = fadd(hv[u].x, ev[u].x);
+                                xd[XS] = fadd(hv[u].y, ev[u].y);
+                                xd[2 * XS] = fadd(hv[u].z, ev[u].z);
+                                xd[3 * XS] = fadd(hv[u].w, ev[u].w);
+                            }
+                        }
                     }
-                    float* xd = x0 + (size_t)(4 * c) * XS + ts;
-                    xd[0] = v.x; xd[XS] = v.y; xd[2 * XS] = v.z; xd[3 * XS] = v.w;
                 }
                 named_bar_sync(bar_mlp, cnt_mlp);
                 CM_CLK(c0, __float_as_int(x0[0]))
