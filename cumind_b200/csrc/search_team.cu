@@ -931,6 +931,8 @@ bool team_variant_ok(int G, int TT) {
 cudaError_t launch_search_team(int G, const TeamParams& p, int grid, int block, size_t smem, cudaStream_t st) {
     if (!team_variant_ok(G, p.TT)) return cudaErrorInvalidValue;
     if (p.tile != 0) {
+        if (p.TT == 16 && p.tile == 2 && G == 2 && p.pk.H == 64 && block <= 640) return launch_one<2, 16, 2, 2, 64, 640>(p, grid, block, smem, st);
+        if (p.TT == 16 && p.tile == 3 && G == 2 && p.pk.H == 64 && block <= 640) return launch_one<2, 16, 4, 1, 64, 640>(p, grid, block, smem, st);
         if (G != 2 || p.pk.H != 64 || block > 512) return cudaErrorInvalidValue;
         if (p.TT == 16 && p.tile == 1) return launch_one<2, 16, 4, 4, 64, 512>(p, grid, block, smem, st);
         if (p.TT == 8 && p.tile == 1) return launch_one<2, 8, 4, 2, 64, 512>(p, grid, block, smem, st);
