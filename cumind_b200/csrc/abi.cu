@@ -648,7 +648,7 @@ struct TeamPlan { int G, grid, block; size_t smem; TeamParams p; };
 
 // Team schedule (search_team.cu): G = pow2 >= A lanes per tree, TT tree slots per team (8 or 16), ntw tree
 // warps + nmw network warps per team, n_team teams per CTA, one CTA per SM.  The tree statistics of the
-// trees in flight live in shared memory (40 bytes per node), which bounds the trees per team.
+// trees in flight live in shared memory (44 bytes per node), which bounds the trees per team.
 static int plan_team(const cumind_tree* t, const cumind_net* n, const cumind_search_cfg* c, TeamPlan& pl, std::string& why) {
     const int H = n->desc.hidden_dim, B = t->tv.B, A = t->tv.A, S_max = t->tv.S_max, N = t->tv.N;
     const int sm = n->sm_count;
@@ -677,8 +677,8 @@ static int plan_team(const cumind_tree* t, const cumind_net* n, const cumind_sea
     const size_t off_sqrt = al16(pack_bytes);
     const size_t off_recip = al16(off_sqrt + (size_t)n_sqrt * sizeof(double));
     const size_t off_teams = (off_recip + (size_t)n_sqrt * sizeof(double) + 127) & ~(size_t)127;
-    const size_t team_base = al16((size_t)(2 * H * XS + TT * (H + 4) + 2 * TT * pk.HP + 4 * TT) * 4);
-    const size_t per_tree = (size_t)(S_max + 2) * sizeof(int) + (size_t)N * 40;  // path + hot W + hot records
+    const size_t team_base = al16((size_t)(2 * H * XS + TT * (H + 4) + 3 * TT * pk.HP + 4 * TT) * 4);
+    const size_t per_tree = (size_t)(S_max + 2) * sizeof(int) + (size_t)N * 44;  // path + selection cache + hot W + hot records
     const size_t kMax = 227 * 1024;
     if (off_teams + team_base + per_tree + 256 > kMax) { why = "one tree does not fit the team kernel's shared memory"; return 1; }
     int n_team = c->teams_per_cta > 0 ? c->teams_per_cta : (tps + TT - 1) / TT;
@@ -704,7 +704,8 @@ static int plan_team(const cumind_tree* t, const cumind_net* n, const cumind_sea
     }
     if (tpt < 1) tpt = 1;
     const size_t off_path = team_base;
-    const size_t off_hotw = al16(off_path + (size_t)tpt * (S_max + 2) * sizeof(int));
+    const size_t off_nxt = al16(off_path + (size_t)tpt * (S_max + 2) * sizeof(int));
+    const size_t off_hotw = al16(off_nxt + (size_t)tpt * N * sizeof(int));
     const size_t off_hot = al16(off_hotw + (size_t)tpt * N * sizeof(double));
     const size_t team_bytes = (off_hot + (size_t)tpt * N * 32 + 127) & ~(size_t)127;
     const size_t total = off_teams + (size_t)n_team * team_bytes + 16;
@@ -736,6 +737,7 @@ static int plan_team(const cumind_tree* t, const cumind_net* n, const cumind_sea
     p.off_teams = (unsigned)off_teams;
     p.team_bytes = (unsigned)team_bytes;
     p.off_path = (unsigned)off_path;
+    p.off_nxt = (unsigned)off_nxt;
     p.off_hotw = (unsigned)off_hotw;
     p.off_hot = (unsigned)off_hot;
     p.off_bar = (unsigned)((off_teams + (size_t)n_team * team_bytes + 7) & ~(size_t)7);

@@ -47,8 +47,8 @@ struct TeamParams {
     int n_team, ntw, nmw, TT, tpt, n_batches;
     int tile;                  // lane tile of the network warps (0 = default; see launch_search_team)
     int stagger;               // SM cycles between the starts of the teams of one CTA
-    // shared-memory carve-up (bytes); off_path / off_hotw / off_hot are relative to the team's scratch
-    unsigned off_sqrt, off_recip, off_teams, team_bytes, off_bar, off_path, off_hotw, off_hot;
+    // shared-memory carve-up (bytes); off_path / off_nxt / off_hotw / off_hot are relative to the team's scratch
+    unsigned off_sqrt, off_recip, off_teams, team_bytes, off_bar, off_path, off_nxt, off_hotw, off_hot;
     int n_sqrt;
     long long* clk;            // [grid][16] phase clocks (diagnostic) or nullptr
 };

@@ -40,86 +40,19 @@ __device__ __noinline__ void dirichlet_row_cold(double* out, int A, double alpha
     dirichlet_row(out, A, alpha, seed, tree);
 }
 
-// What one level of the walk reads for a child (shared memory, 32 bytes, two LDS.128):
+// The statistics of a node while its tree is being searched (shared memory, 32 bytes, two LDS.128):
 //   q  = value_sum / visit_count as Node.value computes it (mcts.py:41-49; 0 while unvisited)
 //   cp = c_puct * prior in float64 (mcts.py:65; root children: the prior after noise mixing)
-//   r  = RN(1 / (1 + n)) for the exact division of the exploration term
-//   n  = visit_count, ce = expansion index of the child's own children (-1: not expanded)
+//   r  = RN(1 / (1 + n)) for the exact table-driven division of the exploration term
+//   n  = visit_count, ce = expansion index of the node's own children (-1: not expanded)
+// value_sum itself lives in a parallel array (hw) and the child select_child would pick in nxt (below).
 struct __align__(16) HotSel {
     double q, cp, r;
     int32_t n, ce;
 };
 static_assert(sizeof(HotSel) == 32, "HotSel must be 32 bytes");
 
-CM_DEVICE void lds_hot(const HotSel* p, int4& a, int4& b) {
-    a = *reinterpret_cast<const int4*>(p);
-    b = *(reinterpret_cast<const int4*>(p) + 1);
-}
-
-// Selection on the hot records, one child per lane (A <= G), SPAN = pow2 >= A lanes in the butterfly.
-// The records of the next level are requested before the warp votes on whether anyone still walks.
-template <int G, int SPAN>
-CM_DEVICE int select_hot(const HotSel* __restrict__ hs, const double* __restrict__ sqrt_tab, int A, int root_visits,
-                         int* __restrict__ path, int g, bool active, int& plen_out, int& parent_e_out, int& action_out) {
-    int node = 0, e = 0, n_parent = root_visits, plen = 0, action = 0, parent_e = 0;
-    int walking = active ? 1 : 0;
-    const bool has_child = g < A;
-    const HotSel* mine = hs + 1 + (has_child ? g : 0);
-    int4 ra, rb;
-    lds_hot(mine, ra, rb);
-    while (true) {
-        const double q = __hiloint2double(ra.y, ra.x), cp = __hiloint2double(ra.w, ra.z), r = __hiloint2double(rb.y, rb.x);
-        const int n = rb.z, ce = rb.w;
-        const double num = __dmul_rn(cp, sqrt_tab[n_parent]);
-        double s = __dadd_rn(q, div_small(num, (double)(1 + n), r));
-        s = (n == 0) ? dinf() : s;
-        if (s != s) s = (g == 0) ? dinf() : -dinf();
-        const bool valid = has_child && walking;
-        double best_s = valid ? s : -dinf();
-        unsigned best_ae = valid ? (((unsigned)g << 16) | (unsigned)(ce + 1)) : 0xffffffffu;
-        int best_n = n;
-#pragma unroll
-        for (int o = SPAN / 2; o > 0; o >>= 1) {
-            const double os = __shfl_xor_sync(0xffffffffu, best_s, o);
-            const unsigned oae = __shfl_xor_sync(0xffffffffu, best_ae, o);
-            const int on = __shfl_xor_sync(0xffffffffu, best_n, o);
-            const bool take = os > best_s || (os == best_s && oae < best_ae);
-            best_s = take ? os : best_s;
-            best_ae = take ? oae : best_ae;
-            best_n = take ? on : best_n;
-        }
-        if constexpr (SPAN < G) {
-            best_ae = __shfl_sync(0xffffffffu, best_ae, 0, G);
-            best_n = __shfl_sync(0xffffffffu, best_n, 0, G);
-        }
-        if (walking && g == 0) path[plen] = node;
-        const int act = (int)(best_ae >> 16);
-        const int ne = (int)(best_ae & 0xffffu) - 1;
-        plen += walking;
-        parent_e = walking ? e : parent_e;
-        action = walking ? act : action;
-        node = walking ? 1 + e * A + act : node;
-        n_parent = walking ? best_n : n_parent;
-        e = walking ? ne : e;
-        walking = (walking && ne >= 0) ? 1 : 0;
-        lds_hot(mine + (walking ? e * A : 0), ra, rb);
-        if (!__any_sync(0xffffffffu, walking != 0)) break;
-    }
-    plen_out = plen;
-    parent_e_out = parent_e;
-    action_out = action;
-    return node;
-}
-
-// ---- the fast walk -------------------------------------------------------------------------------
-// Same selection with everything that is not arithmetic taken off the per-level dependency chain:
-//   * shared memory is addressed through 32-bit window addresses kept in registers (ld.shared / st.shared);
-//   * the division is the bare Markstein sequence: the caller guarantees (per tree, see cp_is_safe) that
-//     the numerator c_puct*prior*sqrt(N) is 0, NaN or within [2^-900, 2^900], where the sequence is the
-//     correctly rounded quotient (0 and NaN come out as 0 and NaN), so no range test and no branch;
-//   * scores are compared as order-preserving 64-bit integer keys (-0 folded into +0, NaN and unvisited
-//     mapped as in select_hot), one ISETP pair instead of three dependent DSETPs;
-//   * sqrt(N_parent) of the next level is requested together with the next records.
+// shared memory through 32-bit window addresses kept in registers (ld.shared / st.shared)
 CM_DEVICE void lds128_s(uint32_t addr, int4& v) {
     asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
 }
@@ -128,249 +61,190 @@ CM_DEVICE double lds64_s(uint32_t addr) {
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
     return v;
 }
-CM_DEVICE void sts32_pred(uint32_t addr, int v, int pred) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.shared.s32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"(pred) : "memory");
-}
-
-CM_DEVICE void sts64_pred(uint32_t addr, double v, int pred) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.shared.f64 [%0], %1;\n\t}" ::"r"(addr), "d"(v), "r"(pred) : "memory");
-}
-CM_DEVICE void sts128_s(uint32_t addr, int a, int b, int c, int d) {
-    asm volatile("st.shared.v4.s32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 CM_DEVICE int lds32_s(uint32_t addr) {
     int v;
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
-
-// c_puct*prior values for which the bare Markstein division of select_hot_fast is exact
-CM_DEVICE bool cp_is_safe(double cp) {
-    // 0, NaN, or a biased exponent in [1023-890, 1023+890): integer tests on the high word
-    const unsigned hi = (unsigned)__double2hiint(cp) & 0x7fffffffu;
-    const unsigned lo = (unsigned)__double2loint(cp);
-    const unsigned ex = hi >> 20;
-    const bool zero = (hi | lo) == 0u;
-    const bool nan = hi > 0x7ff00000u || (hi == 0x7ff00000u && lo != 0u);
-    return zero || nan || (ex - 133u) < 1780u;
+CM_DEVICE void sts32_s(uint32_t addr, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+CM_DEVICE void sts64_s(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+CM_DEVICE void sts128_s(uint32_t addr, int a, int b, int c, int d) {
+    asm volatile("st.shared.v4.s32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <int G, int SPAN>
-CM_DEVICE int select_hot_fast(uint32_t hs_addr, uint32_t sqrt_addr, int A, int root_visits, uint32_t path_addr, int g, bool active,
-                              int& plen_out, int& parent_e_out, int& action_out) {
-    int node = 0, e = 0, plen = 0, action = 0, parent_e = 0;
-    int walking = active ? 1 : 0;
-    const bool has_child = g < A;
-    const uint32_t mine = hs_addr + 32u * (uint32_t)(1 + (has_child ? g : 0));
-    const uint32_t stride = 32u * (uint32_t)A;
-    const unsigned gbits = (unsigned)g << 16;
-    const long long PINF = 0x7ff0000000000000LL, NINF = (long long)0xfff0000000000000ULL;
-    const long long nan_key_src = (g == 0) ? PINF : NINF;
-    int4 ra, rb;
-    lds128_s(mine, ra);
-    lds128_s(mine + 16u, rb);
-    double sq = lds64_s(sqrt_addr + 8u * (uint32_t)root_visits);
-    while (true) {
-        const double q = __hiloint2double(ra.y, ra.x), cp = __hiloint2double(ra.w, ra.z), r = __hiloint2double(rb.y, rb.x);
-        const int n = rb.z, ce = rb.w;
-        const double num = __dmul_rn(cp, sq);
-        const double d = (double)(1 + n);
-        double t = __dmul_rn(num, r);
-        t = __fma_rn(__fma_rn(-d, t, num), r, t);
-        t = __fma_rn(__fma_rn(-d, t, num), r, t);
-        long long b = __double_as_longlong(__dadd_rn(q, t));
-        const long long mag = b & 0x7fffffffffffffffLL;
-        b = mag > PINF ? nan_key_src : (mag == 0 ? 0LL : b);
-        b = (n == 0) ? PINF : b;
-        long long key = b ^ ((b >> 63) & 0x7fffffffffffffffLL);
-        const bool valid = has_child && walking;
-        key = valid ? key : (long long)0x8000000000000000ULL;
-        unsigned ae = valid ? (gbits | (unsigned)(ce + 1)) : 0xffffffffu;
-        int bn = n;
-#pragma unroll
-        for (int o = SPAN / 2; o > 0; o >>= 1) {
-            const long long ok = __shfl_xor_sync(0xffffffffu, key, o);
-            const unsigned oae = __shfl_xor_sync(0xffffffffu, ae, o);
-            const int on = __shfl_xor_sync(0xffffffffu, bn, o);
-            const bool take = ok > key || (ok == key && oae < ae);
-            key = take ? ok : key;
-            ae = take ? oae : ae;
-            bn = take ? on : bn;
-        }
-        if constexpr (SPAN < G) {
-            ae = __shfl_sync(0xffffffffu, ae, 0, G);
-            bn = __shfl_sync(0xffffffffu, bn, 0, G);
-        }
-        sts32_pred(path_addr + 4u * (uint32_t)plen, node, walking && g == 0);
-        const int act = (int)(ae >> 16);
-        const int ne = (int)(ae & 0xffffu) - 1;
-        plen += walking;
-        parent_e = walking ? e : parent_e;
-        action = walking ? act : action;
-        node = walking ? 1 + e * A + act : node;
-        e = walking ? ne : e;
-        walking = (walking && ne >= 0) ? 1 : 0;
-        const uint32_t nxt = mine + (walking ? (uint32_t)e * stride : 0u);
-        lds128_s(nxt, ra);
-        lds128_s(nxt + 16u, rb);
-        // lanes that do not walk (finished, or slots without a tree aliasing another warp's records, which may
-        // be mid-update) must not turn what they loaded into an address
-        sq = lds64_s(sqrt_addr + 8u * (uint32_t)(walking ? bn : 0));
-        if (!__any_sync(0xffffffffu, walking != 0)) break;
-    }
-    plen_out = plen;
-    parent_e_out = parent_e;
-    action_out = action;
-    return node;
-}
-
-template <int G>
-CM_DEVICE int select_hot_fast_any(uint32_t hs_addr, uint32_t sqrt_addr, int A, int root_visits, uint32_t path_addr, int g, bool active,
-                                  int& plen_out, int& parent_e_out, int& action_out) {
-    if constexpr (G >= 4) {
-        if (A <= G / 2)
-            return select_hot_fast<G, G / 2>(hs_addr, sqrt_addr, A, root_visits, path_addr, g, active, plen_out, parent_e_out, action_out);
-    }
-    return select_hot_fast<G, G>(hs_addr, sqrt_addr, A, root_visits, path_addr, g, active, plen_out, parent_e_out, action_out);
-}
-
-// A > G (only with G == 32): every lane scores children g, g+32, ... of the current node.
-template <int G>
-CM_DEVICE int select_hot_loop(const HotSel* __restrict__ hs, const double* __restrict__ sqrt_tab, int A, int root_visits,
-                              int* __restrict__ path, int g, bool active, int& plen_out, int& parent_e_out, int& action_out) {
-    int node = 0, e = 0, n_parent = root_visits, plen = 0, action = 0, parent_e = 0;
-    bool walking = active;
-    while (__any_sync(0xffffffffu, walking)) {
-        double best_s = -dinf();
-        unsigned best_ae = 0xffffffffu;
-        int best_n = 0;
-        if (walking) {
-            const double sq = sqrt_tab[n_parent];
-            for (int a = g; a < A; a += G) {
-                int4 ra, rb;
-                lds_hot(hs + 1 + e * A + a, ra, rb);
-                const double q = __hiloint2double(ra.y, ra.x), cp = __hiloint2double(ra.w, ra.z), r = __hiloint2double(rb.y, rb.x);
-                const int n = rb.z, ce = rb.w;
-                double s = __dadd_rn(q, div_small(__dmul_rn(cp, sq), (double)(1 + n), r));
-                s = (n == 0) ? dinf() : s;
-                if (s != s) s = (a == 0) ? dinf() : -dinf();
-                if (best_ae == 0xffffffffu || s > best_s) { best_s = s; best_ae = ((unsigned)a << 16) | (unsigned)(ce + 1); best_n = n; }
-            }
-        }
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) {
-            const double os = __shfl_xor_sync(0xffffffffu, best_s, o);
-            const unsigned oae = __shfl_xor_sync(0xffffffffu, best_ae, o);
-            const int on = __shfl_xor_sync(0xffffffffu, best_n, o);
-            if (os > best_s || (os == best_s && oae < best_ae)) { best_s = os; best_ae = oae; best_n = on; }
-        }
-        if (walking) {
-            if (g == 0) path[plen] = node;
+// ---- selection as a pointer chase ------------------------------------------------------------------
+// Node.select_child (mcts.py:67-76) is a function of the parent's visit count and its children's
+// statistics, and all of those only change in a simulation whose path goes through the parent: the backup
+// (mcts.py:199-203) touches the parents on the path and nothing else, and a child is on the path only if
+// its parent is.  So the child the NEXT visit of a node will select is known as soon as the backup of
+// the current simulation is done.  backup_rescore (network warps) stores it in nxt[node] for every parent
+// on the path; a freshly expanded node gets nxt = its child 0 (all children unvisited: every score is +inf
+// and max() keeps the first, mcts.py:76); an unexpanded node has nxt = -1.  The walk of mcts.py:165-171 is
+// then one dependent shared-memory load per level.  Returns the leaf; path[0..plen) = the parents.
+CM_DEVICE int select_chase(uint32_t nxt_addr, uint32_t path_addr, int g, bool active, int& plen_out) {
+    int node = 0, plen = 0;
+    if (active) {
+        int nx = lds32_s(nxt_addr);
+        while (nx >= 0) {
+            if (g == 0) sts32_s(path_addr + 4u * (uint32_t)plen, node);
             ++plen;
-            parent_e = e;
-            action = (int)(best_ae >> 16);
-            node = 1 + e * A + action;
-            n_parent = best_n;
-            e = (int)(best_ae & 0xffffu) - 1;
-            walking = e >= 0;
+            node = nx;
+            nx = lds32_s(nxt_addr + 4u * (uint32_t)nx);
         }
     }
+    __syncwarp();
     plen_out = plen;
-    parent_e_out = parent_e;
-    action_out = action;
     return node;
 }
 
-template <int G>
-CM_DEVICE int select_hot_any(const HotSel* __restrict__ hs, const double* __restrict__ sqrt_tab, int A, int root_visits,
-                             int* __restrict__ path, int g, bool active, int& plen_out, int& parent_e_out, int& action_out) {
-    if constexpr (G >= 2) {
-        if (A <= G / 2 && G / 2 >= 1)
-            return select_hot<G, (G / 2 >= 1 ? G / 2 : 1)>(hs, sqrt_tab, A, root_visits, path, g, active, plen_out, parent_e_out, action_out);
+// Node.ucb_score (mcts.py:51-65) of one child as an order-preserving 64-bit integer key:
+//   +inf if n == 0, else q + ((c_puct*prior)*sqrt(N_parent)) / (1 + n) with q = W/n already divided.
+// IEEE: the division is __ddiv_rn; otherwise it is the Markstein sequence of div_small, which is the correctly
+// rounded quotient when the numerator is 0, NaN or within [2^-900, 2^900] (`exact` reports whether it was).
+// -0 is folded into +0 (Python compares them equal), NaN maps to +inf for child 0 and -inf otherwise (max()
+// never replaces its first candidate by a NaN and never replaces a NaN first candidate).
+template <bool IEEE>
+CM_DEVICE long long score_key(double q, double cp, double r, int n, double sq, bool first, bool& exact) {
+    const long long PINF = 0x7ff0000000000000LL, NINF = (long long)0xfff0000000000000ULL;
+    const double num = __dmul_rn(cp, sq);
+    const double d = (double)(1 + n);
+    double t;
+    if constexpr (IEEE) {
+        t = __ddiv_rn(num, d);
+        exact = true;
+    } else {
+        t = __dmul_rn(num, r);
+        t = __fma_rn(__fma_rn(-d, t, num), r, t);
+        t = __fma_rn(__fma_rn(-d, t, num), r, t);
+        const unsigned hi = (unsigned)__double2hiint(num) & 0x7fffffffu;
+        const unsigned lo = (unsigned)__double2loint(num);
+        exact = ((hi >> 20) - 123u) < 1800u || (hi | lo) == 0u || hi > 0x7ff00000u || (hi == 0x7ff00000u && lo != 0u) || n == 0;
     }
-    if (A <= G) return select_hot<G, G>(hs, sqrt_tab, A, root_visits, path, g, active, plen_out, parent_e_out, action_out);
-    return select_hot_loop<G>(hs, sqrt_tab, A, root_visits, path, g, active, plen_out, parent_e_out, action_out);
+    long long b = __double_as_longlong(__dadd_rn(q, t));
+    const long long mag = b & 0x7fffffffffffffffLL;
+    b = mag > PINF ? (first ? PINF : NINF) : (mag == 0 ? 0LL : b);
+    b = (n == 0) ? PINF : b;
+    return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
 }
 
-// Backup on the hot records (mcts.py:199-203): every parent on the path gets n += 1, W += v, the root
-// (path[0]) a second time; the value term q = W/n and RN(1/(1+n)) are refreshed here so that the next
-// walk does not have to.  U path entries per lane are processed together with no branch in between (entries
-// past the end of the path stand in as the root and their stores are predicated off), so their dependency
-// chains overlap.  q = W/n is the Markstein sequence of div_small; a value sum outside the range where
-// that is exact (never in practice) is redone with the IEEE division after the block.  A zero sum stays on
-// the sequence (it yields a zero; the sign of a zero value term never reaches a decision: scores are
-// compared with -0 folded into +0, and root values are divided separately).
-template <int G, int U>
-CM_DEVICE void backup_hot(uint32_t hs_addr, uint32_t hw_addr, uint32_t path_addr, int plen, float leaf_value, uint32_t recip_addr,
-                          int g) {
-    const double v = (double)leaf_value;
-#pragma unroll 1
-    for (int i0 = g; i0 < plen; i0 += U * G) {
-        int nd[U], n[U], ok[U];
-        double w[U];
-        int slow = 0;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * G;
-            ok[u] = i < plen ? 1 : 0;
-            nd[u] = lds32_s(path_addr + 4u * (uint32_t)(ok[u] ? i : 0));
+// Markstein sequence of div_small: a / d from r = RN(1/d); the correctly rounded quotient when markstein_ok(a)
+CM_DEVICE double markstein(double a, double d, double r) {
+    double q = __dmul_rn(a, r);
+    q = __fma_rn(__fma_rn(-d, q, a), r, q);
+    return __fma_rn(__fma_rn(-d, q, a), r, q);
+}
+// biased exponent in [123, 1923): the residuals of the sequence are exact
+CM_DEVICE bool markstein_ok(double a) { return ((((unsigned)__double2hiint(a) & 0x7fffffffu) >> 20) - 123u) < 1800u; }
+
+// Lane mapping of backup_rescore, fixed for the whole launch: the path entries of a tree are spread over
+// `lpt` lanes of ONE network warp.
+struct BackupLanes {
+    int ts;    // tree slot of this lane (-1: none)
+    int il;    // first path entry of this lane
+    int lpt;   // stride between the entries of a lane
+};
+CM_DEVICE BackupLanes backup_lanes(int TT, int nmw, int mw, int lane) {
+    const int tpw = (TT + nmw - 1) / nmw;  // trees per network warp
+    BackupLanes b;
+    b.lpt = 32 / tpw;
+    const int tl = lane / b.lpt;
+    b.il = lane - tl * b.lpt;
+    b.ts = tl < tpw ? mw * tpw + tl : -1;
+    return b;
+}
+
+// Backup (mcts.py:199-203) and the selection cache, on the network warps.  The lane of entry i owns parent
+// P = path[i]: it adds the leaf value to P (W += v, n += 1; the root, path[0], twice) and refreshes q = W/n and
+// RN(1/(1+n)).  To re-evaluate which child P will select next it needs the new statistics of the one child that
+// changed, C = path[i+1] (the leaf is not backed up): it recomputes them privately from C's old record, which is
+// why every lane reads before any lane writes (one warp: shared-memory accesses complete in program order).
+// The other children are not on the path and are read as they are.  Straight-line arithmetic; operands outside
+// the exact range of the Markstein sequence (never in practice) are redone with IEEE divisions at the end.
+CM_DEVICE void backup_rescore(uint32_t hs_t, uint32_t hw_t, uint32_t nxt_t, uint32_t path_t, const int* __restrict__ sel,
+                              const float* __restrict__ lg, uint32_t sq_addr, uint32_t rc_addr, int N, int A, int S_max, int TT,
+                              int HP, int A_net, int n_here, const BackupLanes bl) {
+    const bool valid = bl.ts >= 0 && bl.ts < n_here;
+    const int tsc = valid ? bl.ts : 0;
+    const int plen = valid ? sel[2 * TT + tsc] : 0;
+    const double v = (double)lg[tsc * HP + A_net];
+    const uint32_t path = path_t + 4u * (uint32_t)(tsc * (S_max + 2));
+    const uint32_t hs = hs_t + 32u * (uint32_t)(tsc * N);
+    const uint32_t hw = hw_t + 8u * (uint32_t)(tsc * N);
+    const uint32_t nxt = nxt_t + 4u * (uint32_t)(tsc * N);
+    const int maxlen = __reduce_max_sync(0xffffffffu, plen);
+    for (int i = bl.il; i - bl.il < maxlen; i += bl.lpt) {
+        const bool on = i < plen;
+        const bool has_c = i + 1 < plen;
+        const int P = lds32_s(path + 4u * (uint32_t)(on ? i : 0));
+        const int Cl = lds32_s(path + 4u * (uint32_t)(has_c ? i + 1 : 0));
+        // old statistics of P and of the child on the path
+        const uint32_t recP = hs + 32u * (uint32_t)P, recC = hs + 32u * (uint32_t)Cl;
+        const double wP = lds64_s(hw + 8u * (uint32_t)P);
+        const int nP = lds32_s(recP + 24u);
+        const int ceP = lds32_s(recP + 28u);
+        const double wC = lds64_s(hw + 8u * (uint32_t)Cl);
+        const int nC = lds32_s(recC + 24u);
+        const bool root = P == 0;
+        const int nPn = nP + (root ? 2 : 1);
+        const int nCn = nC + 1;
+        const double sq = lds64_s(sq_addr + 8u * (uint32_t)nPn);
+        const double rP = lds64_s(rc_addr + 8u * (uint32_t)nPn), rP1 = lds64_s(rc_addr + 8u * (uint32_t)nPn + 8u);
+        const double rC = lds64_s(rc_addr + 8u * (uint32_t)nCn), rC1 = lds64_s(rc_addr + 8u * (uint32_t)nCn + 8u);
+        // the other children's records (unchanged by this backup); C's own record is loaded too and ignored
+        const int base = 1 + ceP * A;
+        const int C = has_c ? Cl : -1;
+        const double wP1 = __dadd_rn(wP, v);
+        const double wPn = root ? __dadd_rn(wP1, v) : wP1;
+        const double wCn = __dadd_rn(wC, v);
+        double qPn = markstein(wPn, (double)nPn, rP);
+        double qCn = markstein(wCn, (double)nCn, rC);
+        if (!(markstein_ok(wPn) && markstein_ok(wCn))) {
+            if (!markstein_ok(wPn)) qPn = (wPn == 0.0) ? wPn : __ddiv_rn(wPn, (double)nPn);
+            if (!markstein_ok(wCn)) qCn = (wCn == 0.0) ? wCn : __ddiv_rn(wCn, (double)nCn);
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            w[u] = lds64_s(hw_addr + 8u * (uint32_t)nd[u]);
-            n[u] = lds32_s(hs_addr + 32u * (uint32_t)nd[u] + 24u);
-        }
-        // the shared-memory accesses are volatile asm and keep their program order: all loads of all entries
-        // first, then the arithmetic, then all stores, or one entry's stores would fence the next entry's loads
-        double ww[U], rn[U], r1[U], q[U], d[U], t[U], e[U];
-        int nn[U];
-        // one operation of every entry at a time: a warp issues in order, so the U dependency chains only
-        // overlap if the instruction stream itself interleaves them
-#pragma unroll
-        for (int u = 0; u < U; ++u) ww[u] = __dadd_rn(w[u], v);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const bool root = nd[u] == 0;
-            const double w2 = __dadd_rn(ww[u], v);
-            ww[u] = root ? w2 : ww[u];
-            nn[u] = n[u] + (root ? 2 : 1);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            rn[u] = lds64_s(recip_addr + 8u * (uint32_t)nn[u]);
-            r1[u] = lds64_s(recip_addr + 8u * (uint32_t)nn[u] + 8u);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) d[u] = (double)nn[u];
-#pragma unroll
-        for (int u = 0; u < U; ++u) t[u] = __dmul_rn(ww[u], rn[u]);
-#pragma unroll
-        for (int u = 0; u < U; ++u) e[u] = __fma_rn(-d[u], t[u], ww[u]);
-#pragma unroll
-        for (int u = 0; u < U; ++u) t[u] = __fma_rn(e[u], rn[u], t[u]);
-#pragma unroll
-        for (int u = 0; u < U; ++u) e[u] = __fma_rn(-d[u], t[u], ww[u]);
-#pragma unroll
-        for (int u = 0; u < U; ++u) q[u] = __fma_rn(e[u], rn[u], t[u]);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const unsigned hi = (unsigned)__double2hiint(ww[u]) & 0x7fffffffu;
-            const bool exact = ((hi >> 20) - 123u) < 1800u || (hi | (unsigned)__double2loint(ww[u])) == 0u;
-            slow |= (ok[u] && !exact) ? 1 : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t rec = hs_addr + 32u * (uint32_t)nd[u];
-            sts64_pred(hw_addr + 8u * (uint32_t)nd[u], ww[u], ok[u]);
-            sts64_pred(rec, q[u], ok[u]);
-            sts64_pred(rec + 16u, r1[u], ok[u]);
-            sts32_pred(rec + 24u, nn[u], ok[u]);
-        }
-        if (slow) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (ok[u]) sts64_pred(hs_addr + 32u * (uint32_t)nd[u], __ddiv_rn(ww[u], (double)nn[u]), 1);
+        __syncwarp();  // every lane has read the old records
+        if (on) {
+            sts64_s(hw + 8u * (uint32_t)P, wPn);
+            sts64_s(recP, qPn);
+            sts64_s(recP + 16u, rP1);
+            sts32_s(recP + 24u, nPn);
+            // which child does P select next time?
+            long long best = 0;
+            int best_c = base;
+            bool all_exact = true;
+#pragma unroll 2
+            for (int a = 0; a < A; ++a) {
+                const int c = base + a;
+                int4 ra, rb;
+                lds128_s(hs + 32u * (uint32_t)c, ra);
+                lds128_s(hs + 32u * (uint32_t)c + 16u, rb);
+                const bool is_c = c == C;
+                const double q = is_c ? qCn : __hiloint2double(ra.y, ra.x);
+                const double cp = __hiloint2double(ra.w, ra.z);
+                const double r = is_c ? rC1 : __hiloint2double(rb.y, rb.x);
+                const int n = is_c ? nCn : rb.z;
+                bool exact;
+                const long long key = score_key<false>(q, cp, r, n, sq, a == 0, exact);
+                all_exact = all_exact && exact;
+                if (a == 0 || key > best) { best = key; best_c = c; }
             }
+            if (!all_exact) {  // same scan with IEEE divisions
+                best_c = base;
+                for (int a = 0; a < A; ++a) {
+                    const int c = base + a;
+                    int4 ra, rb;
+                    lds128_s(hs + 32u * (uint32_t)c, ra);
+                    lds128_s(hs + 32u * (uint32_t)c + 16u, rb);
+                    const bool is_c = c == C;
+                    const double q = is_c ? qCn : __hiloint2double(ra.y, ra.x);
+                    const double cp = __hiloint2double(ra.w, ra.z);
+                    const int n = is_c ? nCn : rb.z;
+                    bool exact;
+                    const long long key = score_key<true>(q, cp, 0.0, n, sq, a == 0, exact);
+                    if (a == 0 || key > best) { best = key; best_c = c; }
+                }
+            }
+            sts32_s(nxt + 4u * (uint32_t)P, best_c);
         }
     }
 }
@@ -612,16 +486,16 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
     const float* wht_s = w_s + p.pk.heads_wt;
     const float* bh_s = w_s + p.pk.heads_b;
 
-    // team scratch: x0,x1 [H][XS] | xt [TT][H+4] | lg,eb [TT][HP] | sel [4][TT] | path [tpt][S_max+2] | hot W [tpt][N] | hot records [tpt][N]
+    // team scratch: x0,x1 [H][XS] | xt [TT][H+4] | lg[2],eb [TT][HP] | sel [4][TT] | path [tpt][S_max+2] | nxt [tpt][N] | hot W [tpt][N] | hot records [tpt][N]
     unsigned char* my = smem + p.off_teams + (size_t)team * p.team_bytes;
     float* x0 = reinterpret_cast<float*>(my);
     float* x1 = x0 + (size_t)H * XS;
     float* xt = x1 + (size_t)H * XS;
-    float* lg_t = xt + (size_t)TT * (H + 4);
-    float* eb_t = lg_t + TT * HP;
-    int* sel = reinterpret_cast<int*>(eb_t + TT * HP);   // [3][TT] parent_e, action, path length; then [TT] "checked walk" flags
-    int* unsafe_t = sel + 3 * TT;
+    float* lg_t = xt + (size_t)TT * (H + 4);              // logits + value of simulation s in buffer s & 1 (the root's in buffer 1)
+    float* eb_t = lg_t + 2 * TT * HP;
+    int* sel = reinterpret_cast<int*>(eb_t + TT * HP);   // [3][TT] parent_e, action, path length
     int* path_t = reinterpret_cast<int*>(my + p.off_path);
+    int* nxt_t = reinterpret_cast<int*>(my + p.off_nxt);
     double* hw_t = reinterpret_cast<double*>(my + p.off_hotw);
     HotSel* hs_t = reinterpret_cast<HotSel*>(my + p.off_hot);
     const int bar_team = 1 + team, bar_mlp = 1 + p.n_team + team;
@@ -649,6 +523,8 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
         const long long t_go = clock64() + (long long)team * p.stagger;
         while (clock64() < t_go) {}
     }
+    // (leaf - 1) / A by multiplication: exact for leaf - 1 < 2^32 / A
+    const unsigned magic_A = A > 1 ? (unsigned)((0x100000000ULL + (unsigned)A - 1u) / (unsigned)A) : 0u;
     const int team_global = blockIdx.x * p.n_team + team, team_stride = gridDim.x * p.n_team;
     for (int batch = team_global; batch < p.n_batches; batch += team_stride) {
         const int t_begin = batch * p.tpt;
@@ -666,23 +542,37 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
             int32_t* eidx = p.tv.child_eidx + tt * N;
             double* rprior = p.tv.root_prior + tt * A;
             int32_t* exp_node = p.tv.exp_node + tt * (S_max + 1);
-            float* lg = lg_t + tsc * HP;
             float* eb = eb_t + tsc * HP;
             int* path = path_t + tsc * (S_max + 2);
             HotSel* hs = hs_t + (size_t)tsc * N;
             double* hw = hw_t + (size_t)tsc * N;
-            const uint32_t hs_addr = smem_addr(hs), sq_addr = smem_addr(sq_s), path_addr = smem_addr(path);
-            const uint32_t hw_addr = smem_addr(hw), rc_addr = smem_addr(rc_s);
-            int* unsafe = unsafe_t + tsc;
+            int* nxt = nxt_t + (size_t)tsc * N;
+            const uint32_t hs_addr = smem_addr(hs), path_addr = smem_addr(path);
+            const uint32_t hw_addr = smem_addr(hw), nxt_addr = smem_addr(nxt);
+
+            // softmax of the logits of expansion k (buffer `buf`) -> priors of its children (mcts.py:189-196)
+            auto finish_expansion = [&](int k, int buf) {
+                const float* lg = lg_t + buf * TT * HP + tsc * HP;
+                const float ssum = softmax_team<G>(lg, eb, A_net, g, active);
+                if (active) {
+                    const int cbase = 1 + k * A;
+                    for (int a = g; a < A; a += G) {
+                        const float p32 = prior_div(eb[a], ssum);
+                        store_node(nodes + cbase + a, 0.0, 0, p32);
+                        sts64_s(hs_addr + 32u * (uint32_t)(cbase + a) + 8u, __dmul_rn(p.c_puct, (double)p32));
+                    }
+                }
+                __syncwarp();
+            };
 
             // ---- root: softmax of the root logits -> expand -> noise (mcts.py:126-136) -------------
             named_bar_sync(bar_team, cnt_team);  // the previous batch's logits have been consumed
             if (active && p.noise_mode == 2 && g == 0)
                 dirichlet_row_cold(rprior, A, p.alpha, p.seed, p.tree_base + (unsigned long long)t);
             named_bar_sync(bar_team, cnt_team);  // root logits published
-            if (active && g == 0) *unsafe = 0;
             __syncwarp();
             {
+                const float* lg = lg_t + TT * HP + tsc * HP;
                 const float ssum = softmax_team<G>(lg, eb, A_net, g, active);
                 if (active) {
                     for (int a = g; a < A; a += G) {
@@ -698,7 +588,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
                         h.q = 0.0; h.cp = __dmul_rn(p.c_puct, pd); h.r = 1.0; h.n = 0; h.ce = -1;
                         hs[1 + a] = h;
                         hw[1 + a] = 0.0;
-                        if (!cp_is_safe(h.cp)) *unsafe = 1;
+                        nxt[1 + a] = -1;
                     }
                     if (g == 0) {
                         store_node(nodes, 0.0, 0, 1.0f);
@@ -706,6 +596,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
                         h.q = 0.0; h.cp = 0.0; h.r = 1.0; h.n = 0; h.ce = 0;
                         hs[0] = h;
                         hw[0] = 0.0;
+                        nxt[0] = 1;  // every child unvisited: the first one
                         exp_node[0] = 0;
                     }
                 }
@@ -716,13 +607,11 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
             // ---- S simulations (mcts.py:139-140, 157-203) -------------------------------------------
             long long depth = 0;
             for (int s = 0; s < p.S; ++s) {
-                int plen, parent_e, action;
-                // bare-division walk unless one of the warp's trees holds a c_puct*prior outside its exact range
-                int leaf;
-                if (A <= G && !__any_sync(0xffffffffu, active && *unsafe != 0))
-                    leaf = select_hot_fast_any<G>(hs_addr, sq_addr, A, 2 * s, path_addr, g, active, plen, parent_e, action);
-                else
-                    leaf = select_hot_any<G>(hs, sq_s, A, 2 * s, path, g, active, plen, parent_e, action);
+                int plen;
+                const int leaf = select_chase(nxt_addr, path_addr, g, active, plen);
+                const unsigned lm1 = (unsigned)(leaf - 1);
+                const int parent_e = A > 1 ? (int)__umulhi(lm1, magic_A) : (int)lm1;
+                const int action = (int)lm1 - parent_e * A;
                 if (g == 0 && ts < TT) {
                     sel[ts] = active ? parent_e : 0;
                     sel[TT + ts] = active ? action : 0;
@@ -730,32 +619,36 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
                 }
                 CM_CLK(c0, plen + leaf)
                 named_bar_sync(bar_team, cnt_team);  // (A) selection published
-                named_bar_sync(bar_team, cnt_team);  // (B) logits + value published
-                CM_CLK(c1, __float_as_int(lg[A_net]))
+                CM_CLK(c6, sel[0])
+                // Node.expand of the leaf (mcts.py:78-89, 195-196) without the priors: the children exist and are
+                // unvisited, so the next walks score them +inf whatever the prior is.  The priors follow one
+                // simulation later (finish_expansion), before any of these children can have been visited.
                 const int k = s + 1;  // expansion index of the leaf
-                const float ssum = softmax_team<G>(lg, eb, A_net, g, active);
-                CM_CLK(c5, __float_as_int(ssum))   // softmax alone; c6: expansion; c2: the backup that follows
                 if (active) {
-                    const float value = lg[A_net];
                     const int cbase = 1 + k * A;
                     for (int a = g; a < A; a += G) {
-                        const float p32 = prior_div(eb[a], ssum);
-                        store_node(nodes + cbase + a, 0.0, 0, p32);
-                        const double cp = __dmul_rn(p.c_puct, (double)p32);
                         const uint32_t rec = hs_addr + 32u * (uint32_t)(cbase + a);
-                        sts128_s(rec, 0, 0, __double2loint(cp), __double2hiint(cp));       // q = 0, cp
-                        sts128_s(rec + 16u, 0, 0x3ff00000, 0, -1);                          // r = 1.0, n = 0, ce = -1
-                        sts64_pred(hw_addr + 8u * (uint32_t)(cbase + a), 0.0, 1);
-                        if (!cp_is_safe(cp)) *unsafe = 1;
+                        sts128_s(rec, 0, 0, 0, 0);                    // q = 0, cp = 0 (set by finish_expansion)
+                        sts128_s(rec + 16u, 0, 0x3ff00000, 0, -1);    // r = 1.0, n = 0, ce = -1
+                        sts64_s(hw_addr + 8u * (uint32_t)(cbase + a), 0.0);
+                        sts32_s(nxt_addr + 4u * (uint32_t)(cbase + a), -1);
                     }
-                    if (g == 0) { hs[leaf].ce = k; exp_node[k] = leaf; }
+                    if (g == 0) {
+                        sts32_s(hs_addr + 32u * (uint32_t)leaf + 28u, k);
+                        sts32_s(nxt_addr + 4u * (uint32_t)leaf, cbase);
+                        exp_node[k] = leaf;
+                    }
                     depth += plen;
                 }
-                CM_CLK(c6, hs[1].n)
+                __syncwarp();
+                CM_CLK(c1, hs[1].n)
+                if (s > 0) finish_expansion(s, (s - 1) & 1);  // the leaf of the previous simulation
+                CM_CLK(c5, hs[1].n)
                 named_bar_sync(bar_team, cnt_team);  // (C) the network warps have backed the value up
                 __syncwarp();
                 CM_CLK(c2, hs[0].n)
             }
+            if (p.S > 0) finish_expansion(p.S, (p.S - 1) & 1);
 
             // ---- statistics -> canonical records; visit counts -> probabilities (mcts.py:143-155) ---
             if (active) {
@@ -791,6 +684,9 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
             const int nblk = (H + NB - 1) / NB;
             const int H4 = H >> 2;
             float* hid0 = p.tv.hidden + (size_t)t_begin * hstride;
+            const uint32_t hs_a = smem_addr(hs_t), hw_a = smem_addr(hw_t), nxt_a = smem_addr(nxt_t), path_a = smem_addr(path_t);
+            const uint32_t sq_a = smem_addr(sq_s), rc_a = smem_addr(rc_s);
+            const BackupLanes bl = backup_lanes(TT, p.nmw, mw, lane);
 
             // ---- root: x0 = root hidden (also hidden row 0), heads -> logits --------------------------
             for (int i = mlane; i < TT * H4; i += nml) {
@@ -803,10 +699,11 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
                 *reinterpret_cast<float4*>(xt + (size_t)ts * (H + 4) + 4 * c) = v;
             }
             named_bar_sync(bar_team, cnt_team);  // xt filled; the tree warps are done with the previous batch's logits
-            team_heads<HS>(wht_s, bh_s, xt, H, HP, TT, A_net, lg_t, mlane, nml);
+            team_heads<HS>(wht_s, bh_s, xt, H, HP, TT, A_net, lg_t + TT * HP, mlane, nml);
             named_bar_sync(bar_team, cnt_team);  // root logits published
 
             for (int s = 0; s < p.S; ++s) {
+                float* lg_s = lg_t + (s & 1) * TT * HP;
                 named_bar_sync(bar_team, cnt_team);  // (A) selection published
                 CM_CLK(c3, sel[0])
                 // gather: x0[j][ts] = hidden[ts][parent_e][j] + Emb[action][j]   (network.py:229-230).
@@ -860,36 +757,12 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
                     float* tmp = cur; cur = nxt; nxt = tmp;
                 }
                 CM_CLK(c1, __float_as_int(xt[0]))
-                team_heads<HS>(wht_s, bh_s, xt, H, HP, TT, A_net + 1, lg_t, mlane, nml);
-                __syncwarp();
-                CM_CLK(c2, __float_as_int(lg_t[0]))
-                named_bar_sync(bar_team, cnt_team);  // (B) logits + value published
-                // Backup (mcts.py:199-203) on the network warps, one path entry per lane, while the tree warps
-                // turn the logits into the new node's children: W += v, n += 1 on every parent of the path, the
-                // root (path[0]) twice; q = W/n and RN(1/(1+n)) refreshed for the next walk.
-                {
-                    const int ts = mlane % TT;
-                    if (ts < n_here) {
-                        const int plen = sel[2 * TT + ts];
-                        const double v = (double)lg_t[ts * HP + A_net];
-                        const int* path = path_t + ts * (S_max + 2);
-                        HotSel* hs = hs_t + (size_t)ts * N;
-                        double* hw = hw_t + (size_t)ts * N;
-                        for (int i = mlane / TT; i < plen; i += nml / TT) {
-                            const int nd = path[i];
-                            const bool root = nd == 0;
-                            const double w1 = __dadd_rn(hw[nd], v);
-                            const double ww = root ? __dadd_rn(w1, v) : w1;
-                            const int nn = hs[nd].n + (root ? 2 : 1);
-                            hw[nd] = ww;
-                            hs[nd].q = div_small(ww, (double)nn, rc_s[nn]);
-                            hs[nd].r = rc_s[1 + nn];
-                            hs[nd].n = nn;
-                        }
-                    }
-                }
+                team_heads<HS>(wht_s, bh_s, xt, H, HP, TT, A_net + 1, lg_s, mlane, nml);
+                named_bar_sync(bar_mlp, cnt_mlp);  // logits + value visible to every network warp
+                CM_CLK(c2, __float_as_int(lg_s[0]))
+                backup_rescore(hs_a, hw_a, nxt_a, path_a, sel, lg_s, sq_a, rc_a, N, A, S_max, TT, HP, A_net, n_here, bl);
                 CM_CLK(c5, hs_t[0].n)
-                named_bar_sync(bar_team, cnt_team);  // (C) statistics updated
+                named_bar_sync(bar_team, cnt_team);  // (C) statistics and selection cache updated; logits of s published
             }
         }
     }
