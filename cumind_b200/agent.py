@@ -55,8 +55,8 @@ class Agent:
             self.optimizer_state = self.optimizer.init(self.network.blob)
         self.mcts = MCTS(self.network, config)
         self._rng = np.random.default_rng(key())
-        self._work: Optional[torch.Tensor] = None
-        self._pinned: Dict[str, torch.Tensor] = {}
+        self._host_plans: Dict[Any, Dict[str, Any]] = {}   # select_actions: buffers + C arguments per batch shape
+        self._device_index = int(self.device.index)
 
     # ---- action selection ------------------------------------------------------------------------
     def select_action(self, observation: np.ndarray, training: bool = False) -> Tuple[int, np.ndarray]:
@@ -92,33 +92,41 @@ class Agent:
             if philox_seed is None:
                 philox_seed = int(self._rng.integers(0, 2**63 - 1))
         cfg = self.mcts._cfg(mode, philox_seed or 0, tree_index_base)
-        need = int(lib.cumind_select_actions_work_bytes(C.byref(net._desc), B, A_cfg))
-        if self._work is None or self._work.numel() < need + 256:
-            self._work = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
-        wbase = self._work.data_ptr() + ((-self._work.data_ptr()) % 256)
-        pin = self._pinned
-        if "obs" not in pin or pin["obs"].shape != obs.shape:
-            pin["obs"] = torch.empty(obs.shape, dtype=torch.float32).pin_memory()
-            pin["actions"] = torch.empty((B,), dtype=torch.int32).pin_memory()
-            pin["probs"] = torch.empty((B, A_cfg), dtype=torch.float64).pin_memory()
-            pin["noise"] = torch.empty((B, A), dtype=torch.float64).pin_memory()
-        pin["obs"].numpy()[...] = obs
-        h_noise = None
+        # per batch shape: pinned host buffers (and NumPy views of them), the device work buffer, the C arguments
+        plan = self._host_plans.get((B, A_cfg, A))
+        if plan is None:
+            need = int(lib.cumind_select_actions_work_bytes(C.byref(net._desc), B, A_cfg))
+            work = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+            pin = {"obs": torch.empty(obs.shape, dtype=torch.float32).pin_memory(),
+                   "actions": torch.empty((B,), dtype=torch.int32).pin_memory(),
+                   "probs": torch.empty((B, A_cfg), dtype=torch.float64).pin_memory(),
+                   "noise": torch.empty((B, A), dtype=torch.float64).pin_memory()}
+            plan = {"need": need, "work": work, "wbase": C.c_void_p(work.data_ptr() + ((-work.data_ptr()) % 256)), "pin": pin,
+                    "np": {k: v.numpy() for k, v in pin.items()}, "ptr": {k: C.c_void_p(v.data_ptr()) for k, v in pin.items()},
+                    "null": C.c_void_p(0)}
+            self._host_plans.clear()  # one shape at a time: the buffers are sized for it
+            self._host_plans[(B, A_cfg, A)] = plan
+        views, ptr = plan["np"], plan["ptr"]
+        views["obs"][...] = obs
         if noise is not None:
-            pin["noise"].numpy()[...] = np.asarray(noise, dtype=np.float64)
-            h_noise = pin["noise"]
-        with torch.cuda.device(self.device):
+            views["noise"][...] = noise
+        def call():
             _native.check(lib.cumind_select_actions_host(
-                tree.handle, net._handle, C.c_void_p(pin["obs"].data_ptr()), C.byref(cfg),
-                C.c_void_p(h_noise.data_ptr() if h_noise is not None else 0), C.c_void_p(pin["actions"].data_ptr()),
-                C.c_void_p(pin["probs"].data_ptr()), C.c_void_p(wbase), need, _stream_ptr()))
-        probs = pin["probs"].numpy().copy()
+                tree.handle, net._handle, ptr["obs"], C.byref(cfg), ptr["noise"] if noise is not None else plan["null"],
+                ptr["actions"], ptr["probs"], plan["wbase"], plan["need"], _stream_ptr()))
+
+        if torch.cuda.current_device() == self._device_index:
+            call()
+        else:
+            with torch.cuda.device(self.device):
+                call()
+        probs = views["probs"].copy()
         if training:
             cdf = np.cumsum(probs, axis=1)
             u = self._rng.random(B)[:, None] * cdf[:, -1:]
             actions = np.minimum((u >= cdf).sum(axis=1), A_cfg - 1).astype(np.int32)
         else:
-            actions = pin["actions"].numpy().copy()
+            actions = views["actions"].copy()
         return actions, probs
 
     # ---- state -----------------------------------------------------------------------------------

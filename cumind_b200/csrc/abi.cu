@@ -979,6 +979,15 @@ extern "C" size_t cumind_select_actions_work_bytes(const cumind_net_desc* desc, 
     return work_offsets(desc, B, A_cfg).total;
 }
 
+// device-visible alias of a pinned (cudaHostAlloc / cudaHostRegister) host pointer, nullptr for pageable memory
+static void* mapped_ptr(const void* h) {
+    if (!h) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+    return a.devicePointer;
+}
+
 extern "C" int cumind_select_actions_host(cumind_tree* t, const cumind_net* n, const float* h_obs, const cumind_search_cfg* c,
                                           const double* h_noise, int32_t* h_actions, double* h_probs, void* d_work,
                                           size_t work_bytes, void* stream) {
@@ -997,17 +1006,34 @@ extern "C" int cumind_select_actions_host(cumind_tree* t, const cumind_net* n, c
     int32_t* d_actions = (int32_t*)(w + o.actions);
     const size_t osz = n->desc.obs_ndim == 1 ? (size_t)n->desc.obs_shape[0]
                                              : (size_t)n->desc.obs_shape[0] * n->desc.obs_shape[1] * n->desc.obs_shape[2];
-    CM_CUDA(cudaMemcpyAsync(d_obs, h_obs, (size_t)B * osz * sizeof(float), cudaMemcpyHostToDevice, st));
-    if (c->noise_mode == 1)
-        CM_CUDA(cudaMemcpyAsync(d_noise, h_noise, (size_t)B * t->tv.A * sizeof(double), cudaMemcpyHostToDevice, st));
+    // Pinned (mapped) host buffers up to a few MB: the GPU moves the data itself, one kernel each way.  Pageable
+    // or large buffers go through cudaMemcpyAsync (copy engines).  Either way the host<->device transfers are part of this call.
+    const size_t obs_bytes = (size_t)B * osz * sizeof(float), noise_bytes = (size_t)B * t->tv.A * sizeof(double);
+    const bool with_noise = c->noise_mode == 1;
+    void *m_obs = mapped_ptr(h_obs), *m_noise = with_noise ? mapped_ptr(h_noise) : nullptr;
+    void *m_actions = mapped_ptr(h_actions), *m_probs = mapped_ptr(h_probs);
+    const bool zero_copy = m_obs && m_actions && m_probs && (!with_noise || m_noise) && obs_bytes <= ((size_t)4 << 20) && obs_bytes % 16 == 0 &&
+                           noise_bytes % 16 == 0 && ((uintptr_t)m_obs | (uintptr_t)m_noise) % 16 == 0;
+    if (zero_copy) {
+        CM_CUDA(launch_stage_in(m_obs, d_obs, obs_bytes, m_noise, d_noise, with_noise ? noise_bytes : 0, st));
+        g_launches += 1;
+    } else {
+        CM_CUDA(cudaMemcpyAsync(d_obs, h_obs, obs_bytes, cudaMemcpyHostToDevice, st));
+        if (with_noise) CM_CUDA(cudaMemcpyAsync(d_noise, h_noise, noise_bytes, cudaMemcpyHostToDevice, st));
+    }
     int rc = cumind_initial_inference(n, d_obs, B, d_hidden, nullptr, nullptr, c->net_mode, stream);
     if (rc) return rc;
-    rc = cumind_search(t, n, d_hidden, c, c->noise_mode == 1 ? d_noise : nullptr, d_visits, d_probs, nullptr, stream);
+    rc = cumind_search(t, n, d_hidden, c, with_noise ? d_noise : nullptr, d_visits, d_probs, nullptr, stream);
     if (rc) return rc;
-    CM_CUDA(launch_argmax_first(d_probs, B, A_cfg, d_actions, st));
-    g_launches += 1;
-    CM_CUDA(cudaMemcpyAsync(h_actions, d_actions, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CM_CUDA(cudaMemcpyAsync(h_probs, d_probs, (size_t)B * A_cfg * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (zero_copy) {
+        CM_CUDA(launch_stage_out(d_probs, B, A_cfg, d_actions, (int32_t*)m_actions, (double*)m_probs, st));
+        g_launches += 1;
+    } else {
+        CM_CUDA(launch_argmax_first(d_probs, B, A_cfg, d_actions, st));
+        g_launches += 1;
+        CM_CUDA(cudaMemcpyAsync(h_actions, d_actions, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CM_CUDA(cudaMemcpyAsync(h_probs, d_probs, (size_t)B * A_cfg * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
     CM_CUDA(cudaStreamSynchronize(st));
     return 0;
 }

@@ -26,6 +26,10 @@
 #include "tc_common.cuh"
 #include "kernels.h"
 
+#ifndef CM_TEAM_KB
+#define CM_TEAM_KB 4  // k per half buffer of the layer loop's operand double buffering
+#endif
+
 namespace cm {
 
 // bar.sync id, count: all `count` threads (whole warps) of the named barrier; the warp reconverges first
@@ -299,69 +303,70 @@ CM_DEVICE void team_layer(const float* __restrict__ W, const float* __restrict__
             for (int t = 0; t < TQ; ++t) acc[v][t] = 0.0f;
         const float* x = xin + TQ * q;
         const float* w = W + j0;
-        float xb[2][4][TQ], wb[2][4][NV];
+        constexpr int KB = HC > 0 ? CM_TEAM_KB : 4;  // k per half buffer (runtime H: 4, any H % 4 == 0): the operands of the next KB k are in flight while KB k of FMAs issue
+        float xb[2][KB][TQ], wb[2][KB][NV];
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) { lds_vec<TQ>(x + kk * XS, xb[0][kk]); lds_vec<NV>(w + (size_t)kk * Hp, wb[0][kk]); }
+        for (int kk = 0; kk < KB; ++kk) { lds_vec<TQ>(x + kk * XS, xb[0][kk]); lds_vec<NV>(w + (size_t)kk * Hp, wb[0][kk]); }
         if constexpr (HC > 0) {
-            static_assert(HC % 8 == 0 && HC >= 16, "compile-time hidden size must be a multiple of 8");
+            static_assert(HC % (2 * KB) == 0 && HC >= 4 * KB, "compile-time hidden size must be a multiple of 8");
 #pragma unroll 1
-            for (int k0 = 0; k0 < HC - 8; k0 += 8) {
+            for (int k0 = 0; k0 < HC - 2 * KB; k0 += 2 * KB) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) { lds_vec<TQ>(x + (4 + kk) * XS, xb[1][kk]); lds_vec<NV>(w + (size_t)(4 + kk) * Hp, wb[1][kk]); }
+                for (int kk = 0; kk < KB; ++kk) { lds_vec<TQ>(x + (KB + kk) * XS, xb[1][kk]); lds_vec<NV>(w + (size_t)(KB + kk) * Hp, wb[1][kk]); }
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
+                for (int kk = 0; kk < KB; ++kk)
 #pragma unroll
                     for (int v = 0; v < NV; ++v)
 #pragma unroll
                         for (int t = 0; t < TQ; ++t) acc[v][t] = ffma(xb[0][kk][t], wb[0][kk][v], acc[v][t]);
-                x += 8 * XS;
-                w += (size_t)8 * Hp;
+                x += 2 * KB * XS;
+                w += (size_t)2 * KB * Hp;
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) { lds_vec<TQ>(x + kk * XS, xb[0][kk]); lds_vec<NV>(w + (size_t)kk * Hp, wb[0][kk]); }
+                for (int kk = 0; kk < KB; ++kk) { lds_vec<TQ>(x + kk * XS, xb[0][kk]); lds_vec<NV>(w + (size_t)kk * Hp, wb[0][kk]); }
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
+                for (int kk = 0; kk < KB; ++kk)
 #pragma unroll
                     for (int v = 0; v < NV; ++v)
 #pragma unroll
                         for (int t = 0; t < TQ; ++t) acc[v][t] = ffma(xb[1][kk][t], wb[1][kk][v], acc[v][t]);
             }
-            // last 8 k: nothing left to prefetch
+            // last 2*KB k: nothing left to prefetch
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) { lds_vec<TQ>(x + (4 + kk) * XS, xb[1][kk]); lds_vec<NV>(w + (size_t)(4 + kk) * Hp, wb[1][kk]); }
+            for (int kk = 0; kk < KB; ++kk) { lds_vec<TQ>(x + (KB + kk) * XS, xb[1][kk]); lds_vec<NV>(w + (size_t)(KB + kk) * Hp, wb[1][kk]); }
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
+            for (int kk = 0; kk < KB; ++kk)
 #pragma unroll
                 for (int v = 0; v < NV; ++v)
 #pragma unroll
                     for (int t = 0; t < TQ; ++t) acc[v][t] = ffma(xb[0][kk][t], wb[0][kk][v], acc[v][t]);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
+            for (int kk = 0; kk < KB; ++kk)
 #pragma unroll
                 for (int v = 0; v < NV; ++v)
 #pragma unroll
                     for (int t = 0; t < TQ; ++t) acc[v][t] = ffma(xb[1][kk][t], wb[1][kk][v], acc[v][t]);
         } else {
 #pragma unroll 1
-            for (int k0 = 0; k0 < H; k0 += 8) {
-                if (k0 + 4 < H) {
+            for (int k0 = 0; k0 < H; k0 += 2 * KB) {
+                if (k0 + KB < H) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) { lds_vec<TQ>(x + (4 + kk) * XS, xb[1][kk]); lds_vec<NV>(w + (size_t)(4 + kk) * Hp, wb[1][kk]); }
+                    for (int kk = 0; kk < KB; ++kk) { lds_vec<TQ>(x + (KB + kk) * XS, xb[1][kk]); lds_vec<NV>(w + (size_t)(KB + kk) * Hp, wb[1][kk]); }
                 }
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
+                for (int kk = 0; kk < KB; ++kk)
 #pragma unroll
                     for (int v = 0; v < NV; ++v)
 #pragma unroll
                         for (int t = 0; t < TQ; ++t) acc[v][t] = ffma(xb[0][kk][t], wb[0][kk][v], acc[v][t]);
-                x += 8 * XS;
-                w += (size_t)8 * Hp;
-                if (k0 + 8 < H) {
+                x += 2 * KB * XS;
+                w += (size_t)2 * KB * Hp;
+                if (k0 + 2 * KB < H) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) { lds_vec<TQ>(x + kk * XS, xb[0][kk]); lds_vec<NV>(w + (size_t)kk * Hp, wb[0][kk]); }
+                    for (int kk = 0; kk < KB; ++kk) { lds_vec<TQ>(x + kk * XS, xb[0][kk]); lds_vec<NV>(w + (size_t)kk * Hp, wb[0][kk]); }
                 }
-                if (k0 + 4 < H) {
+                if (k0 + KB < H) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
+                    for (int kk = 0; kk < KB; ++kk)
 #pragma unroll
                         for (int v = 0; v < NV; ++v)
 #pragma unroll
@@ -708,7 +713,9 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
                 CM_CLK(c3, sel[0])
                 // gather: x0[j][ts] = hidden[ts][parent_e][j] + Emb[action][j]   (network.py:229-230).
                 // Two items per lane and pass with both global loads in flight before either is used (the
-                // parent rows come from L2); with a compile-time H the item -> (tree, chunk) split is shifts.
+                // parent rows come from L2); consecutive lanes read consecutive 16-byte chunks of a row (the transposed stores
+                // below are 8-way bank conflicted; the conflict-free mapping, trees fastest, un-coalesces the L2 reads and
+                // measured slower: 1 320 vs 1 100 cycles).
                 {
                     const int H4c = HS > 0 ? HS / 4 : H4;
                     for (int i0 = mlane; i0 < TT * H4c; i0 += 2 * nml) {
@@ -789,8 +796,10 @@ static cudaError_t launch_one(const TeamParams& p, int grid, int block, size_t s
 template <int G, int TT, int TQ, int NV>
 static cudaError_t launch_t(const TeamParams& p, int grid, int block, size_t smem, cudaStream_t st) {
     const bool big = block > 512;
-    if (p.pk.H == 64)
+    if (p.pk.H == 64) {
+        if (block <= 384) return launch_one<G, TT, TQ, NV, 64, 384>(p, grid, block, smem, st);
         return big ? launch_one<G, TT, TQ, NV, 64, 1024>(p, grid, block, smem, st) : launch_one<G, TT, TQ, NV, 64, 512>(p, grid, block, smem, st);
+    }
     return big ? launch_one<G, TT, TQ, NV, 0, 1024>(p, grid, block, smem, st) : launch_one<G, TT, TQ, NV, 0, 512>(p, grid, block, smem, st);
 }
 
@@ -808,7 +817,7 @@ cudaError_t launch_search_team(int G, const TeamParams& p, int grid, int block, 
         if (p.TT == 16 && p.tile == 3 && G == 2 && p.pk.H == 64 && block <= 640) return launch_one<2, 16, 4, 1, 64, 640>(p, grid, block, smem, st);
         if (G != 2 || p.pk.H != 64 || block > 512) return cudaErrorInvalidValue;
         if (p.TT == 16 && p.tile == 1) return launch_one<2, 16, 4, 4, 64, 512>(p, grid, block, smem, st);
-        if (p.TT == 8 && p.tile == 1) return launch_one<2, 8, 4, 2, 64, 512>(p, grid, block, smem, st);
+        if (p.TT == 8 && p.tile == 1) return block <= 384 ? launch_one<2, 8, 4, 2, 64, 384>(p, grid, block, smem, st) : launch_one<2, 8, 4, 2, 64, 512>(p, grid, block, smem, st);
         if (p.TT == 8 && p.tile == 2) return launch_one<2, 8, 2, 4, 64, 512>(p, grid, block, smem, st);
         return cudaErrorInvalidValue;
     }

@@ -190,6 +190,32 @@ __global__ void argmax_first_kernel(const double* __restrict__ probs, int B, int
     actions[t] = best;
 }
 
+// Host-buffer path of cumind_select_actions_host when the caller's buffers are pinned (mapped) host memory:
+// the GPU reads the inputs and writes the results over PCIe itself, one kernel each way instead of two
+// cudaMemcpyAsync each way (a copy-engine transfer costs ~6 us of set-up for these 16-64 kB buffers).
+__global__ void stage_in_kernel(const float4* __restrict__ h_a, float4* __restrict__ d_a, size_t n_a, const float4* __restrict__ h_b,
+                                float4* __restrict__ d_b, size_t n_b) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_a) d_a[i] = h_a[i];
+    else if (i - n_a < n_b) d_b[i - n_a] = h_b[i - n_a];
+}
+// int(np.argmax(action_probs)) (agent.py:86) + the copy of actions and probabilities to the host buffers
+__global__ void stage_out_kernel(const double* __restrict__ probs, int B, int A, int32_t* __restrict__ d_actions,
+                                 int32_t* __restrict__ h_actions, double* __restrict__ h_probs) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B) return;
+    int best = 0;
+    double bv = probs[(size_t)t * A];
+    h_probs[(size_t)t * A] = bv;
+    for (int a = 1; a < A; ++a) {
+        const double v = probs[(size_t)t * A + a];
+        h_probs[(size_t)t * A + a] = v;
+        if (v > bv) { bv = v; best = a; }
+    }
+    d_actions[t] = best;
+    h_actions[t] = best;
+}
+
 // Self-test of div_small (the table-driven division of the fused select): random and structured
 // numerators against the IEEE division, bitwise.  counts[0] = mismatches, counts[1] = cases.
 __global__ void selftest_div_kernel(unsigned long long n_per_thread, unsigned long long seed, int max_d,
@@ -268,6 +294,17 @@ cudaError_t launch_finalize(const StepParams& p, int32_t* out_visits, double* ou
 cudaError_t launch_dirichlet(double* noise, int B, int A, double alpha, unsigned long long seed, unsigned long long tree_base,
                              cudaStream_t st) {
     dirichlet_kernel<<<(B + 127) / 128, 128, 0, st>>>(noise, B, A, alpha, seed, tree_base);
+    return cudaGetLastError();
+}
+// n_a / n_b in bytes (multiples of 16, 16-byte aligned pointers); either may be 0
+cudaError_t launch_stage_in(const void* h_a, void* d_a, size_t n_a, const void* h_b, void* d_b, size_t n_b, cudaStream_t st) {
+    const size_t va = n_a / 16, vb = n_b / 16, n = va + vb;
+    if (n == 0) return cudaSuccess;
+    stage_in_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float4*)h_a, (float4*)d_a, va, (const float4*)h_b, (float4*)d_b, vb);
+    return cudaGetLastError();
+}
+cudaError_t launch_stage_out(const double* probs, int B, int A, int32_t* d_actions, int32_t* h_actions, double* h_probs, cudaStream_t st) {
+    stage_out_kernel<<<(B + 127) / 128, 128, 0, st>>>(probs, B, A, d_actions, h_actions, h_probs);
     return cudaGetLastError();
 }
 cudaError_t launch_argmax_first(const double* probs, int B, int A, int32_t* actions, cudaStream_t st) {

@@ -252,6 +252,26 @@ def test_select_actions_host_path_matches_oracle():
         actions, probs = agent.select_actions(obs, training=False, noise=nz)
         assert np.array_equal(probs, o["out_probs"])
         assert np.array_equal(actions, np.argmax(o["out_probs"], axis=1))
+    # the same C-ABI call with PAGEABLE host buffers (cudaMemcpyAsync path instead of the mapped-memory kernels)
+    import ctypes as C
+
+    import torch
+
+    from cumind_b200 import _native
+    from cumind_b200.network import _stream_ptr
+
+    net, lib = agent.network, agent.mcts._lib
+    tree = agent.mcts._tree(B, 25, 2)
+    scfg = agent.mcts._cfg(1, 0, 0)
+    need = int(lib.cumind_select_actions_work_bytes(C.byref(net._desc), B, 2))
+    work = torch.empty(need + 256, dtype=torch.uint8, device=net.device)
+    wbase = work.data_ptr() + ((-work.data_ptr()) % 256)
+    h_obs, h_noise = np.ascontiguousarray(obs), np.ascontiguousarray(noise)
+    h_actions, h_probs = np.full((B,), -1, np.int32), np.zeros((B, 2), np.float64)
+    _native.check(lib.cumind_select_actions_host(tree.handle, net._handle, C.c_void_p(h_obs.ctypes.data), C.byref(scfg),
+                                                 C.c_void_p(h_noise.ctypes.data), C.c_void_p(h_actions.ctypes.data),
+                                                 C.c_void_p(h_probs.ctypes.data), C.c_void_p(wbase), need, _stream_ptr()))
+    assert np.array_equal(h_probs, probs) and np.array_equal(h_actions, actions)
     # single-observation reference entry agrees with the batch
     a0, p0 = agent.select_action(obs[3], training=False)
     o = lo.search(desc, blob, h, 25, 2, 1.25, 0.25, None)
