@@ -199,21 +199,24 @@ __global__ void stage_in_kernel(const float4* __restrict__ h_a, float4* __restri
     if (i < n_a) d_a[i] = h_a[i];
     else if (i - n_a < n_b) d_b[i - n_a] = h_b[i - n_a];
 }
-// int(np.argmax(action_probs)) (agent.py:86) + the copy of actions and probabilities to the host buffers
+// int(np.argmax(action_probs)) (agent.py:86) + the copy of actions and probabilities to the host buffers.
+// Threads [0, B): one tree each (first maximum, 4-byte coalesced writes); threads [B, B + n_vec): one 16-byte
+// vector of the probability matrix each, so the PCIe writes are full 128-byte lines per warp.
 __global__ void stage_out_kernel(const double* __restrict__ probs, int B, int A, int32_t* __restrict__ d_actions,
-                                 int32_t* __restrict__ h_actions, double* __restrict__ h_probs) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= B) return;
-    int best = 0;
-    double bv = probs[(size_t)t * A];
-    h_probs[(size_t)t * A] = bv;
-    for (int a = 1; a < A; ++a) {
-        const double v = probs[(size_t)t * A + a];
-        h_probs[(size_t)t * A + a] = v;
-        if (v > bv) { bv = v; best = a; }
+                                 int32_t* __restrict__ h_actions, double* __restrict__ h_probs, size_t n_vec, int vec) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (size_t)B) {
+        const int t = (int)i;
+        int best = 0;
+        double bv = probs[(size_t)t * A];
+        for (int a = 1; a < A; ++a) { const double v = probs[(size_t)t * A + a]; if (v > bv) { bv = v; best = a; } }
+        d_actions[t] = best;
+        h_actions[t] = best;
+    } else if (i - B < n_vec) {
+        const size_t j = i - B;
+        if (vec) reinterpret_cast<double2*>(h_probs)[j] = reinterpret_cast<const double2*>(probs)[j];
+        else h_probs[j] = probs[j];
     }
-    d_actions[t] = best;
-    h_actions[t] = best;
 }
 
 // Self-test of div_small (the table-driven division of the fused select): random and structured
@@ -304,7 +307,10 @@ cudaError_t launch_stage_in(const void* h_a, void* d_a, size_t n_a, const void* 
     return cudaGetLastError();
 }
 cudaError_t launch_stage_out(const double* probs, int B, int A, int32_t* d_actions, int32_t* h_actions, double* h_probs, cudaStream_t st) {
-    stage_out_kernel<<<(B + 127) / 128, 128, 0, st>>>(probs, B, A, d_actions, h_actions, h_probs);
+    const size_t n = (size_t)B * A;
+    const int vec = (n % 2 == 0) && ((uintptr_t)probs % 16 == 0) && ((uintptr_t)h_probs % 16 == 0);
+    const size_t n_vec = vec ? n / 2 : n, threads = (size_t)B + n_vec;
+    stage_out_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(probs, B, A, d_actions, h_actions, h_probs, n_vec, vec);
     return cudaGetLastError();
 }
 cudaError_t launch_argmax_first(const double* probs, int B, int A, int32_t* actions, cudaStream_t st) {

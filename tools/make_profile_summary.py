@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turn gpurun_out/<tag>_launches.csv + <tag>_fused.ncu-rep into tracked summaries under profiles/.
 
-    tools/make_profile_summary.py <tag> <kernel-substring>
+    tools/make_profile_summary.py <tag> <kernel-substring> [mangled-substring-for-the-line-tool]
 """
 import csv
 import os
@@ -11,6 +11,7 @@ from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, kernel = sys.argv[1], sys.argv[2]
+line_kernel = sys.argv[3] if len(sys.argv) > 3 else kernel  # mangled-name substring that selects ONE instantiation
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 
@@ -44,7 +45,9 @@ want = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__shared_mem_per_block_dynamic", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-        "smsp__cycles_active.avg", "sm__cycles_elapsed.max")
+        "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active")
 with open(os.path.join(out_dir, f"{tag}_fused_metrics.csv"), "w") as f:
     f.write("metric,unit,value\n")
     for n, u, v in zip(names, units, vals):
@@ -53,7 +56,7 @@ with open(os.path.join(out_dir, f"{tag}_fused_metrics.csv"), "w") as f:
 
 # ---- per-source-line attribution -------------------------------------------------------------------
 lib = os.path.join(ROOT, "cumind_b200", "_lib", "libcumind_b200.so")
-res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), rep, lib, kernel, "40"], capture_output=True, text=True)
+res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), rep, lib, line_kernel, "40"], capture_output=True, text=True)
 open(os.path.join(out_dir, f"{tag}_fused_by_line.txt"), "w").write(res.stdout)
 print(open(os.path.join(out_dir, f"{tag}_launches_summary.csv")).read())
 print(open(os.path.join(out_dir, f"{tag}_fused_metrics.csv")).read())
