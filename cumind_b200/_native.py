@@ -21,6 +21,8 @@ EXPORTS = [
     "cumind_search_plan", "cumind_search_phase_clocks", "cumind_search_stepwise", "cumind_select_actions_work_bytes", "cumind_select_actions_host",
     "cumind_tree_init_root", "cumind_select", "cumind_expand", "cumind_backup", "cumind_finalize", "cumind_dirichlet",
     "cumind_launch_count", "cumind_selftest_division", "cumind_adamw_step", "cumind_adamw_step_dev", "cumind_net_update_params_device",
+    "cumind_sumtree_create", "cumind_sumtree_destroy", "cumind_sumtree_tree_size", "cumind_sumtree_clear", "cumind_sumtree_update",
+    "cumind_sumtree_sample", "cumind_sumtree_read",
 ]
 
 NET_FP32_EXACT = 0
@@ -110,6 +112,16 @@ def load():
     lib.cumind_adamw_step.argtypes = [vp, vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, C.c_int64, f32, vp]
     lib.cumind_adamw_step_dev.argtypes = [vp, vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, vp, f32, vp]
     lib.cumind_net_update_params_device.argtypes = [vp, vp, sz, vp]
+    i64 = C.c_int64
+    lib.cumind_sumtree_create.argtypes = [i64, C.POINTER(vp)]
+    lib.cumind_sumtree_destroy.argtypes = [vp]
+    lib.cumind_sumtree_destroy.restype = None
+    lib.cumind_sumtree_tree_size.argtypes = [vp]
+    lib.cumind_sumtree_tree_size.restype = i64
+    lib.cumind_sumtree_clear.argtypes = [vp, vp]
+    lib.cumind_sumtree_update.argtypes = [vp, vp, vp, i64, vp]
+    lib.cumind_sumtree_sample.argtypes = [vp, vp, i64, vp, vp, vp]
+    lib.cumind_sumtree_read.argtypes = [vp, vp, vp]
     _lib = lib
     return lib
 

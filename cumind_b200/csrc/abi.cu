@@ -956,6 +956,61 @@ extern "C" int cumind_selftest_division(uint64_t n_per_thread, uint64_t seed, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// TreeBuffer's sum tree in device memory (memory.py:190-299)
+// ------------------------------------------------------------------------------------------------
+struct cumind_sumtree {
+    double* d_tree;
+    long long capacity, tree_size, n_nodes;
+    int depth;
+};
+
+extern "C" int cumind_sumtree_create(int64_t capacity, cumind_sumtree** out) {
+    if (!out || capacity < 1 || capacity > ((int64_t)1 << 40)) return fail("cumind_sumtree_create: bad argument");
+    cumind_sumtree* t = new cumind_sumtree();
+    t->capacity = capacity;
+    t->tree_size = 1;
+    t->depth = 0;
+    while (t->tree_size < capacity) { t->tree_size *= 2; ++t->depth; }   // memory.py:204-206
+    t->n_nodes = 2 * t->tree_size - 1;
+    cudaError_t e = cudaMalloc(&t->d_tree, sizeof(double) * (size_t)t->n_nodes);
+    if (e == cudaSuccess) e = cudaMemset(t->d_tree, 0, sizeof(double) * (size_t)t->n_nodes);
+    if (e != cudaSuccess) { cudaFree(t->d_tree); delete t; return fail_cuda("cumind_sumtree_create", e); }
+    *out = t;
+    return 0;
+}
+extern "C" void cumind_sumtree_destroy(cumind_sumtree* t) {
+    if (!t) return;
+    cudaFree(t->d_tree);
+    delete t;
+}
+extern "C" int64_t cumind_sumtree_tree_size(const cumind_sumtree* t) { return t ? t->tree_size : 0; }
+extern "C" int cumind_sumtree_clear(cumind_sumtree* t, void* stream) {
+    if (!t) return fail("cumind_sumtree_clear: NULL argument");
+    CM_CUDA(cudaMemsetAsync(t->d_tree, 0, sizeof(double) * (size_t)t->n_nodes, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int cumind_sumtree_update(cumind_sumtree* t, const int64_t* d_tree_idx, const double* d_priority, int64_t n, void* stream) {
+    if (!t || !d_tree_idx || !d_priority || n < 0) return fail("cumind_sumtree_update: bad argument");
+    if (n == 0) return 0;
+    CM_CUDA(launch_sumtree_update(t->d_tree, t->n_nodes, t->depth, (const long long*)d_tree_idx, d_priority, n, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+extern "C" int cumind_sumtree_sample(const cumind_sumtree* t, const double* d_uniform, int64_t batch, int64_t* d_tree_idx,
+                                     int64_t* d_data_idx, void* stream) {
+    if (!t || !d_uniform || !d_tree_idx || !d_data_idx || batch < 1) return fail("cumind_sumtree_sample: bad argument");
+    CM_CUDA(launch_sumtree_sample(t->d_tree, t->n_nodes, t->tree_size, d_uniform, batch, (long long*)d_tree_idx, (long long*)d_data_idx,
+                                  (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+extern "C" int cumind_sumtree_read(const cumind_sumtree* t, double* d_out, void* stream) {
+    if (!t || !d_out) return fail("cumind_sumtree_read: NULL argument");
+    CM_CUDA(cudaMemcpyAsync(d_out, t->d_tree, sizeof(double) * (size_t)t->n_nodes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Agent.select_action for a batch, host buffers in / out (agent.py:61-89)
 // ------------------------------------------------------------------------------------------------
 struct WorkOffsets { size_t obs, hidden, noise, visits, probs, actions, total; };

@@ -110,6 +110,12 @@ cudaError_t launch_adamw_dev_step(float* p, const float* g, float* m, float* v, 
 cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, const unsigned char* mask, size_t n, float lr, float b1,
                          float b2, float eps, float wd, long long step, float grad_scale, cudaStream_t st);
 
+// replay.cu — TreeBuffer's sum tree on the device (memory.py:190-299)
+cudaError_t launch_sumtree_update(double* tree, long long n_nodes, int depth, const long long* idx, const double* pri, long long n,
+                                  cudaStream_t st);
+cudaError_t launch_sumtree_sample(const double* tree, long long n_nodes, long long tree_size, const double* uniform, long long batch,
+                                  long long* tree_idx, long long* data_idx, cudaStream_t st);
+
 // conv_fp32.cu — image encoder, fp32-exact (ConvEncoder, network.py:111-147)
 size_t conv_encoder_work_bytes(const cumind_net_desc& d, int chunk);
 cudaError_t launch_conv_encoder(const NetView& nv, const float* obs, int B, float* hidden, float* work, int chunk,

@@ -1,0 +1,302 @@
+"""Replay buffers: the reference's three buffer classes, same names, constructor
+arguments, return values, error behaviour and quirks (src/cumind/data/memory.py), plus a device-resident
+sum tree for TreeBuffer.
+
+Host side (the reference's own data structures — a deque of trajectories, Python / NumPy global RNGs):
+    Memory                    memory.py:13-85    capacity, deque(maxlen), get_size / get_pct / is_ready / clear
+    MemoryBuffer              memory.py:88-113   uniform `random.sample`; a batch larger than the buffer returns everything
+    PrioritizedMemoryBuffer   memory.py:116-187  p_i**alpha / sum, `np.random.choice(..., replace=False)`
+    TreeBuffer                memory.py:190-299  sum tree in a flat array of 2*tree_size-1 float64
+
+Quirks that are reproduced on purpose (the parity tests run the reference file itself next to this one):
+  * `_propagate` (memory.py:212-217) recurses once more after reaching the root: `(0 - 1) // 2 == -1`, so every
+    update also adds `change` to `sum_tree[-1]`, the LAST leaf.  With a power-of-two capacity that is a real
+    slot whose priority drifts; otherwise it is a padding leaf that is never compared during retrieval;
+  * `TreeBuffer.sample` indexes the deque with the leaf's data index (memory.py:272-273): once the deque has
+    wrapped, slot i of the tree and element i of the deque are different trajectories; an index past the end of
+    the deque raises IndexError;
+  * `update_priorities` of TreeBuffer takes TREE indices and stores `(priority + epsilon) ** alpha`
+    (memory.py:285-288); PrioritizedMemoryBuffer stores the raw priority and ignores epsilon / beta.
+
+Device side: `TreeBuffer(..., device=torch.device)` keeps `sum_tree` on the GPU (cumind_sumtree_* in the C ABI,
+csrc/replay.cu): updates are applied in order with the same float64 additions, sampling retrieves the whole
+batch in one launch from injected or host-drawn uniforms.  The host mirror and the device tree hold the same
+bits (tests/test_memory.py).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import random
+from collections import deque
+from typing import Any, Deque, List, Optional, Sequence
+
+import numpy as np
+
+
+class Memory:
+    """memory.py:13-85."""
+
+    def __init__(self, capacity: int):
+        self.capacity = capacity
+        self.buffer: Deque[Any] = deque(maxlen=capacity)
+
+    def add(self, sample: Any) -> None:
+        raise NotImplementedError
+
+    def sample(self, batch_size: int) -> List[Any]:
+        raise NotImplementedError
+
+    def __len__(self) -> int:
+        return len(self.buffer)
+
+    def get_size(self) -> int:
+        return len(self)
+
+    def get_pct(self) -> float:
+        if self.capacity == 0:
+            raise ValueError("Buffer capacity is zero, cannot calculate percentage.")
+        return float((len(self) / self.capacity) * 100)
+
+    def is_ready(self, min_size: int = 0, min_fill_pct: float = 0) -> bool:
+        if min_size < 0 or min_fill_pct < 0 or min_fill_pct > 1:
+            raise ValueError("min_size must be non-negative and min_fill_pct must be between 0 and 1.")
+        if self.capacity == 0:
+            raise ValueError("Buffer capacity is zero, cannot check readiness.")
+        if min_size == 0 and min_fill_pct == 0:
+            raise ValueError("At least one of min_size or min_fill_pct must be greater than zero.")
+        return (len(self) >= min_size) and (len(self) >= min_fill_pct * self.capacity)
+
+    def clear(self) -> None:
+        self.buffer.clear()
+
+
+class MemoryBuffer(Memory):
+    """memory.py:88-113: uniform sampling without replacement (`random.sample`)."""
+
+    def add(self, sample: Any) -> None:
+        self.buffer.append(sample)
+
+    def sample(self, batch_size: int) -> List[Any]:
+        if len(self.buffer) < batch_size:
+            return list(self.buffer)
+        return random.sample(list(self.buffer), batch_size)
+
+
+class PrioritizedMemoryBuffer(Memory):
+    """memory.py:116-187."""
+
+    def __init__(self, capacity: int, alpha: float, epsilon: float, beta: float):
+        super().__init__(capacity)
+        self.alpha = alpha
+        self.beta = beta
+        self.epsilon = epsilon
+        self.priorities: Deque[float] = deque(maxlen=capacity)
+        self.max_priority = 1.0
+
+    def add(self, sample: Any) -> None:
+        self.buffer.append(sample)
+        self.priorities.append(self.max_priority)
+
+    def sample(self, batch_size: int) -> List[Any]:
+        if len(self.buffer) < batch_size:
+            return list(self.buffer)
+        priorities = np.array(self.priorities)
+        probabilities = (priorities**self.alpha) / np.sum(priorities**self.alpha)
+        indices = np.random.choice(len(self.buffer), size=batch_size, p=probabilities, replace=False)
+        return [self.buffer[i] for i in indices]
+
+    def update_priorities(self, indices: Sequence[int], priorities: Sequence[float]) -> None:
+        for idx, priority in zip(indices, priorities):
+            if idx < len(self.priorities):
+                self.priorities[idx] = priority
+                self.max_priority = max(self.max_priority, priority)
+
+    def clear(self) -> None:
+        super().clear()
+        self.priorities.clear()
+        self.max_priority = 1.0
+
+
+class DeviceSumTree:
+    """The flat sum tree of TreeBuffer (memory.py:204-231, 249-253) in device memory, behind the C ABI."""
+
+    def __init__(self, capacity: int, device=None):
+        import torch
+
+        from . import _native
+
+        if not torch.cuda.is_available():
+            raise _native.CuMindNativeError("DeviceSumTree needs a CUDA device (there is no CPU fallback)")
+        self._native = _native
+        self._lib = _native.load()
+        self._torch = torch
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.capacity = int(capacity)
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _native.check(self._lib.cumind_sumtree_create(C.c_int64(self.capacity), C.byref(handle)))
+        self._handle = handle
+        self.tree_size = int(self._lib.cumind_sumtree_tree_size(handle))
+        self.n_nodes = 2 * self.tree_size - 1
+
+    def _stream(self):
+        return C.c_void_p(self._torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self) -> None:
+        if getattr(self, "_handle", None):
+            self._lib.cumind_sumtree_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def clear(self) -> None:
+        with self._torch.cuda.device(self.device):
+            self._native.check(self._lib.cumind_sumtree_clear(self._handle, self._stream()))
+
+    def update(self, tree_idx, priority) -> None:
+        """`_update(tree_idx[k], priority[k])` for k = 0..n-1 IN ORDER (memory.py:249-253)."""
+        torch = self._torch
+        idx = torch.as_tensor(np.asarray(tree_idx, dtype=np.int64)).to(self.device) if not torch.is_tensor(tree_idx) else tree_idx.to(self.device, torch.int64)
+        pri = torch.as_tensor(np.asarray(priority, dtype=np.float64)).to(self.device) if not torch.is_tensor(priority) else priority.to(self.device, torch.float64)
+        if idx.numel() != pri.numel():
+            raise ValueError("tree_idx and priority must have the same length")
+        if idx.numel() == 0:
+            return
+        idx, pri = idx.contiguous(), pri.contiguous()
+        with torch.cuda.device(self.device):
+            self._native.check(self._lib.cumind_sumtree_update(self._handle, C.c_void_p(idx.data_ptr()), C.c_void_p(pri.data_ptr()),
+                                                               C.c_int64(idx.numel()), self._stream()))
+
+    def sample(self, uniforms):
+        """Retrieval of memory.py:265-273 for a whole batch: returns (tree_idx, data_idx) int64 device tensors.
+        uniforms[i] in [0, 1) stands for the `random.random()` inside `random.uniform(segment*i, segment*(i+1))`."""
+        torch = self._torch
+        u = torch.as_tensor(np.asarray(uniforms, dtype=np.float64)).to(self.device) if not torch.is_tensor(uniforms) else uniforms.to(self.device, torch.float64)
+        u = u.contiguous()
+        n = u.numel()
+        tree_idx = torch.empty(n, dtype=torch.int64, device=self.device)
+        data_idx = torch.empty(n, dtype=torch.int64, device=self.device)
+        if n:
+            with torch.cuda.device(self.device):
+                self._native.check(self._lib.cumind_sumtree_sample(self._handle, C.c_void_p(u.data_ptr()), C.c_int64(n),
+                                                                   C.c_void_p(tree_idx.data_ptr()), C.c_void_p(data_idx.data_ptr()), self._stream()))
+        return tree_idx, data_idx
+
+    def numpy(self) -> np.ndarray:
+        torch = self._torch
+        out = torch.empty(self.n_nodes, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._native.check(self._lib.cumind_sumtree_read(self._handle, C.c_void_p(out.data_ptr()), self._stream()))
+        return out.cpu().numpy()
+
+
+class TreeBuffer(Memory):
+    """memory.py:190-299.  `device=None`: the NumPy sum tree of the reference.  `device=<cuda device>`: the same
+    tree in device memory (DeviceSumTree); `sum_tree` then reads it back."""
+
+    def __init__(self, capacity: int, alpha: float, epsilon: float, device=None):
+        super().__init__(capacity)
+        self.alpha = alpha
+        self.epsilon = epsilon
+        self.max_priority = 1.0
+        self.tree_size = 1
+        while self.tree_size < capacity:
+            self.tree_size *= 2
+        self._dev: Optional[DeviceSumTree] = DeviceSumTree(capacity, device) if device is not None else None
+        self._host_tree = np.zeros(2 * self.tree_size - 1) if self._dev is None else None
+        self.data_pointer = 0
+        self.n_entries = 0
+
+    @property
+    def sum_tree(self) -> np.ndarray:
+        return self._host_tree if self._dev is None else self._dev.numpy()
+
+    # ---- host tree: the reference's recursion, iteratively (memory.py:212-231) ------------------
+    def _propagate(self, idx: int, change: float) -> None:
+        t = self._host_tree
+        while True:
+            parent = (idx - 1) // 2
+            t[parent] += change      # idx == 0: parent == -1, the last leaf (reference quirk)
+            if idx <= 0:
+                break
+            idx = parent
+
+    def _retrieve(self, idx: int, s: float) -> int:
+        t = self._host_tree
+        while True:
+            left = 2 * idx + 1
+            if left >= len(t):
+                return idx
+            if s <= t[left]:
+                idx = left
+            else:
+                s = s - t[left]
+                idx = left + 1
+
+    def _update(self, tree_idx: int, priority: float) -> None:
+        if self._dev is not None:
+            self._dev.update([tree_idx], [priority])
+            return
+        change = priority - self._host_tree[tree_idx]
+        self._host_tree[tree_idx] = priority
+        self._propagate(tree_idx, change)
+
+    def add(self, sample: Any) -> None:
+        self.buffer.append(sample)
+        tree_idx = self.data_pointer + self.tree_size - 1
+        self._update(tree_idx, self.max_priority)
+        self.data_pointer = (self.data_pointer + 1) % self.capacity
+        if self.n_entries < self.capacity:
+            self.n_entries += 1
+
+    def sample_indices(self, batch_size: int, uniforms: Optional[np.ndarray] = None) -> np.ndarray:
+        """The data indices `sample` would read (memory.py:265-273).  `uniforms` injects the draws of
+        `random.random()`; by default they come from the `random` module in the reference's order."""
+        if uniforms is None:
+            uniforms = np.array([random.random() for _ in range(batch_size)], dtype=np.float64)
+        uniforms = np.asarray(uniforms, dtype=np.float64)
+        if self._dev is not None:
+            _, data_idx = self._dev.sample(uniforms)
+            return data_idx.cpu().numpy()
+        segment = self._host_tree[0] / batch_size
+        out = np.empty(batch_size, dtype=np.int64)
+        for i in range(batch_size):
+            a, b = segment * i, segment * (i + 1)
+            s = a + (b - a) * uniforms[i]          # random.uniform(a, b)
+            out[i] = self._retrieve(0, s) - self.tree_size + 1
+        return out
+
+    def sample(self, batch_size: int) -> List[Any]:
+        if len(self.buffer) < batch_size:
+            return list(self.buffer)
+        return [self.buffer[int(i)] for i in self.sample_indices(batch_size)]
+
+    def update_priorities(self, indices: Sequence[int], priorities: Sequence[float]) -> None:
+        idx, pri = [], []
+        for tree_idx, priority in zip(indices, priorities):
+            p = (priority + self.epsilon) ** self.alpha
+            idx.append(int(tree_idx))
+            pri.append(float(p))
+            self.max_priority = max(self.max_priority, p)
+        if not idx:
+            return
+        if self._dev is not None:
+            self._dev.update(idx, pri)  # one launch, applied in order
+        else:
+            for t, p in zip(idx, pri):
+                self._update(t, p)
+
+    def clear(self) -> None:
+        super().clear()
+        if self._dev is not None:
+            self._dev.clear()
+        else:
+            self._host_tree.fill(0)
+        self.data_pointer = 0
+        self.n_entries = 0
+        self.max_priority = 1.0

@@ -16,10 +16,8 @@ the search kernels with `cumind_net_update_params_device`.
 
 from __future__ import annotations
 
-import collections
 import ctypes as C
 import os
-import random
 from datetime import datetime
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
@@ -29,32 +27,8 @@ import torch.nn.functional as F
 
 from . import _native, params as P
 from .checkpoint import load_checkpoint, save_checkpoint
+from .memory import MemoryBuffer  # noqa: F401  (re-exported: the buffer runner.train uses, memory.py:88-113)
 from .network import _stream_ptr
-
-
-class MemoryBuffer:
-    """Uniform replay of whole trajectories (src/cumind/data/memory.py:88-113, the buffer runner.train uses)."""
-
-    def __init__(self, capacity: int):
-        self.capacity = int(capacity)
-        self.buffer: collections.deque = collections.deque(maxlen=self.capacity)
-
-    def add(self, sample: Any) -> None:
-        self.buffer.append(sample)
-
-    def sample(self, batch_size: int) -> List[Any]:
-        if batch_size > len(self.buffer):
-            raise ValueError(f"Cannot sample {batch_size} items from buffer of size {len(self.buffer)}")
-        return random.sample(list(self.buffer), batch_size)
-
-    def __len__(self) -> int:
-        return len(self.buffer)
-
-    def get_pct(self) -> float:
-        return 100.0 * len(self.buffer) / self.capacity
-
-    def is_ready(self, min_size: int, min_pct: float = 0.0) -> bool:
-        return len(self.buffer) >= min_size and len(self.buffer) / self.capacity >= min_pct
 
 
 class _ParamViews:

@@ -258,6 +258,25 @@ int cumind_adamw_step_dev(float* d_params, const float* d_grads, float* d_m, flo
                           int64_t* d_step /* device counter, incremented first */, float grad_scale, void* stream);
 int cumind_net_update_params_device(cumind_net* net, const float* d_params, size_t n_params, void* stream);
 
+/* Replay: the sum tree of TreeBuffer (src/cumind/data/memory.py:190-299) in device memory.
+ * A flat float64 array of 2*tree_size-1 nodes, tree_size = the power of two >= capacity (memory.py:204-208).
+ * cumind_sumtree_update applies `_update(tree_idx[k], priority[k])` (memory.py:249-253, 212-217) for k = 0..n-1 IN
+ *   ORDER, with the reference's float64 additions — including its extra `sum_tree[-1] += change` step from the
+ *   root — so the array equals the reference's bit for bit.  Indices are TREE indices (leaf = data + tree_size-1).
+ * cumind_sumtree_sample is the retrieval of TreeBuffer.sample (memory.py:219-231, 265-273) for a whole batch:
+ *   s_i = random.uniform(segment*i, segment*(i+1)) with d_uniform[i] in [0,1) standing for random.random();
+ *   writes the tree index and the data index (tree index - tree_size + 1) of every sample.
+ * cumind_sumtree_read copies the array (device to device) for inspection. */
+typedef struct cumind_sumtree cumind_sumtree;
+int cumind_sumtree_create(int64_t capacity, cumind_sumtree** out);
+void cumind_sumtree_destroy(cumind_sumtree* tree);
+int64_t cumind_sumtree_tree_size(const cumind_sumtree* tree);
+int cumind_sumtree_clear(cumind_sumtree* tree, void* stream);
+int cumind_sumtree_update(cumind_sumtree* tree, const int64_t* d_tree_idx, const double* d_priority, int64_t n, void* stream);
+int cumind_sumtree_sample(const cumind_sumtree* tree, const double* d_uniform, int64_t batch, int64_t* d_tree_idx,
+                          int64_t* d_data_idx, void* stream);
+int cumind_sumtree_read(const cumind_sumtree* tree, double* d_out, void* stream);
+
 /* Diagnostic: checks the table-driven small-divisor division used by the fused select kernel
  * (a/d from RN(1/d) with two FMA residual corrections) against the IEEE division on the device,
  * bitwise, over 148*4*256*n_per_thread random and structured numerators and divisors 1..max_divisor.
