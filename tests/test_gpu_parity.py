@@ -187,6 +187,48 @@ def test_team_search_leaves_the_bare_division_when_it_is_not_exact(c_puct):
         assert np.array_equal(visits, o["out_visits"]) and np.array_equal(probs, o["out_probs"])
 
 
+@pytest.mark.parametrize("kind", ["inf_values", "nan_values", "nan_priors"])
+def test_search_with_non_finite_values_follows_python_max(kind):
+    """Value sums that overflow to +-inf / NaN and NaN priors: Python's max() (mcts.py:76) never replaces its first
+    candidate by a NaN and never replaces a NaN first candidate; unvisited children still score +inf.  Both
+    schedules must take exactly the oracle's decisions (statistics compared NaN-aware: NaN payloads differ
+    between x86 and the GPU)."""
+    from cumind_b200 import _native
+    from cumind_b200.mcts import MCTS
+    from oracle import network_np as nn
+
+    A, H, S, B = 3, 32, 30, 257
+    params = nn.random_params((4,), A, H, 2, 32, 33, bias_scale=0.05)
+    pred = params["prediction_network"]
+    if kind == "inf_values":
+        pred["value_head"]["kernel"] = (pred["value_head"]["kernel"] * np.float32(3e38)).astype(np.float32)
+    elif kind == "nan_values":
+        pred["value_head"]["kernel"] = (pred["value_head"]["kernel"] * np.float32(3e38)).astype(np.float32)
+        pred["value_head"]["bias"] = np.array([np.nan], np.float32) * np.ones_like(pred["value_head"]["bias"])
+    else:
+        pred["policy_head"]["kernel"] = (pred["policy_head"]["kernel"] * np.float32(3e38)).astype(np.float32)
+    blob = nn.flatten_params(params, (4,))
+    net = _network((4,), A, H, 2, 32, blob)
+    rng = np.random.default_rng(3)
+    h = rng.standard_normal((B, H)).astype(np.float32)
+    noise = rng.dirichlet([0.3] * A, size=B)
+    with np.errstate(all="ignore"):
+        o = lo.search(lo.make_desc((4,), A, H, 2), blob, h, S, A, 1.25, 0.25, noise)
+    assert not np.isfinite(o["value_sum"]).all() or kind == "nan_priors"
+    used = 1 + A * (S + 1)
+    for schedule in (_native.SCHED_TEAM, _native.SCHED_WARP):
+        mcts = MCTS(net, _Cfg(S, A))
+        mcts.schedule = schedule
+        probs, visits = mcts.search_batch(h, noise=noise)
+        d = mcts.dump_trees()
+        assert np.array_equal(d["visit"][:, :used], o["visit"][:, :used]), (kind, schedule)
+        assert np.array_equal(d["exp_node"][:, : S + 1], o["exp_node"][:, : S + 1])
+        assert np.array_equal(d["child_eidx"][:, :used], o["child_eidx"][:, :used])
+        assert np.array_equal(d["value_sum"][:, :used], o["value_sum"][:, :used], equal_nan=True)
+        assert np.array_equal(d["prior"][:, :used], o["prior"][:, :used], equal_nan=True)
+        assert np.array_equal(visits, o["out_visits"]) and np.array_equal(probs, o["out_probs"], equal_nan=True)
+
+
 def _assert_trees_equal(mcts, o, S, A):
     d = mcts.dump_trees()
     used = 1 + A * (S + 1)
