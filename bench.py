@@ -53,6 +53,8 @@ def set_workload(name: str):
         OBS_SHAPE, A, H, L, CC, MODEL_DTYPE = (84, 84, 3), 4, 64, 2, 32, "bfloat16"
     elif name == "atari-literal":
         OBS_SHAPE, A, H, L, CC, MODEL_DTYPE = (3, 84, 84), 4, 64, 2, 32, "bfloat16"
+    elif name == "cartpole-h128":   # the shipped checkpoint's width (configuration.json: hidden_dim 128), SURVEY §8(d) config #2
+        H = 128
     elif name != "cartpole":
         raise ValueError(name)
 
@@ -236,7 +238,8 @@ def run_reference(args, rank: int, world: int):
 
 
 def workload_config(args, per_gpu: int):
-    title = "BASELINE configs[1]: CartPole-shaped synthetic self-play" if WORKLOAD == "cartpole" else f"BASELINE configs[2] ({WORKLOAD}): image observations"
+    title = ("BASELINE configs[1]: CartPole-shaped synthetic self-play" if WORKLOAD == "cartpole" else
+             "CartPole-shaped, shipped-checkpoint width" if WORKLOAD == "cartpole-h128" else f"BASELINE configs[2] ({WORKLOAD}): image observations")
     mode = "fp32-exact network" if MODEL_DTYPE == "float32" else "bf16 tensor-core (tcgen05) network"
     return {"workload": f"{title}, B={per_gpu} trees per GPU, S={args.sims} simulations, "
                         f"obs {OBS_SHAPE}, A={A}, hidden_dim={H}, num_blocks={L}, {mode}, injected Dirichlet({ALPHA}) noise, c_puct={C_PUCT}",
@@ -374,7 +377,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "search_team_kernel" if mcts.plan(B)["schedule"] == "team" else "search_fused_kernel", "kernel_ms": kern_ms_mean, "algorithmic_bytes_per_sim": algorithmic_bytes_per_sim(dbar),
                 "mean_path_length": dbar, "peak_source": peak_src, "encoder_ms": enc_ms_mean}
-    if WORKLOAD != "cartpole":
+    if WORKLOAD.startswith("atari"):
         # image workload: the conv trunk dominates and is tensor-pipe bound
         tf_peak = float(json.load(open(peaks_path)).get("bf16_tflops", 1590.0)) if os.path.exists(peaks_path) else 1590.0
         tf = encoder_flops_per_obs() * B / (enc_ms_mean * 1e-3) / 1e12
@@ -475,13 +478,13 @@ def main():
     ap.add_argument("--phase-clocks", action="store_true", help="print the team kernel's per-phase SM cycles and exit")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--workload", default="cartpole", choices=["cartpole", "atari", "atari-literal"],
+    ap.add_argument("--workload", default="cartpole", choices=["cartpole", "cartpole-h128", "atari", "atari-literal"],
                     help="cartpole = BASELINE configs[1] (the bench line); atari = configs[2], measured for profiles/ only")
     args = ap.parse_args()
     set_workload(args.workload)
     if args.workload != "cartpole":
         args.no_cpu = True
-        if args.trees == 4096:
+        if args.trees == 4096 and args.workload.startswith("atari"):
             args.trees = 1024
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
