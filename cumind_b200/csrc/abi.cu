@@ -403,6 +403,8 @@ extern "C" int cumind_initial_inference(const cumind_net* cn, const float* d_obs
         if ((n->desc.conv_channels & 3) != 0) return fail("image encoder needs conv_channels % 4 == 0");
         const bool tc = net_mode == CUMIND_NET_BF16_TC;
         if (tc && !n->conv_tc_ok) return fail("CUMIND_NET_BF16_TC image encoder needs conv_channels % 16 == 0 and <= 256");
+        // 1024 images per pass: smaller passes that would keep the three activation buffers inside L2 measured slower
+        // (0.91 ms at 512, 0.98 at 256 vs 0.85 at 1024: the layers are bound by per-tile latency, not by DRAM)
         const int chunk = tc ? (B < 1024 ? B : 1024) : (B < 128 ? B : 128);
         const size_t need = tc ? conv_tc_work_bytes(n->desc, chunk) : conv_encoder_work_bytes(n->desc, chunk);
         if (need > n->work_bytes) {

@@ -274,6 +274,22 @@ __global__ void __launch_bounds__(128) conv_tc_halo_kernel(const ConvTcArgs a) {
     const long long n_tiles = (long long)a.n_img * tiles_per_img;
     const int n_chunks = 18 * 10 * NJ;
     const int y = tid >> 3, x = tid & 7;
+    // this thread's halo chunks are tile-invariant: (yy, xx), destination, source offset relative to the tile origin
+    // (Cin <= 32: at most six chunks per thread, kept in registers; the index divisions leave the tile loop)
+    const bool small = n_chunks <= 6 * 128;
+    int c_dst[6], c_rel[6], c_yx[6];
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+        const int idx = u * 128 + tid;
+        c_dst[u] = -1; c_rel[u] = 0; c_yx[u] = 0;
+        if (idx < n_chunks) {
+            const int pixi = idx / NJ, j = idx - pixi * NJ;
+            const int yy = pixi / 10, xx = pixi - yy * 10;
+            c_dst[u] = ((yy * NJ + j) * 10 + xx) * 16;
+            c_rel[u] = ((yy - 1) * a.Wi + (xx - 1)) * a.Cin + j * 8;
+            c_yx[u] = (yy << 8) | xx;
+        }
+    }
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int img = (int)(tile / tiles_per_img);
         const int trem = (int)(tile - (long long)img * tiles_per_img);
@@ -281,26 +297,30 @@ __global__ void __launch_bounds__(128) conv_tc_halo_kernel(const ConvTcArgs a) {
         const int oy0 = ty * 16, ox0 = tx * 8;
         const __nv_bfloat16* in = a.in_bf16 + (size_t)img * a.Hi * a.Wi * a.Cin;
         // ---- stage the halo: chunk idx = (yy*10 + xx)*NJ + j (a pixel's channels are contiguous in global) ----
-        for (int base = 0; base < n_chunks; base += 128 * 6) {
+        if (small) {
+            const __nv_bfloat16* org = in + ((size_t)oy0 * a.Wi + ox0) * a.Cin;
             uint4 v[6];
-            int dst[6];
 #pragma unroll
             for (int u = 0; u < 6; ++u) {
-                const int idx = base + u * 128 + tid;
                 v[u] = make_uint4(0, 0, 0, 0);
-                dst[u] = -1;
-                if (idx < n_chunks) {
-                    const int pixi = idx / NJ, j = idx - pixi * NJ;
-                    const int yy = pixi / 10, xx = pixi - yy * 10;
-                    const int iy = oy0 + yy - 1, ix = ox0 + xx - 1;
-                    dst[u] = ((yy * NJ + j) * 10 + xx) * 16;
-                    if (iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi)
-                        v[u] = *reinterpret_cast<const uint4*>(in + ((size_t)iy * a.Wi + ix) * a.Cin + j * 8);
+                if (c_dst[u] >= 0) {
+                    const int iy = oy0 + (c_yx[u] >> 8) - 1, ix = ox0 + (c_yx[u] & 255) - 1;
+                    if (iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi) v[u] = *reinterpret_cast<const uint4*>(org + c_rel[u]);
                 }
             }
 #pragma unroll
             for (int u = 0; u < 6; ++u)
-                if (dst[u] >= 0) *reinterpret_cast<uint4*>(h_s + dst[u]) = v[u];
+                if (c_dst[u] >= 0) *reinterpret_cast<uint4*>(h_s + c_dst[u]) = v[u];
+        } else {
+            for (int idx = tid; idx < n_chunks; idx += 128) {
+                const int pixi = idx / NJ, j = idx - pixi * NJ;
+                const int yy = pixi / 10, xx = pixi - yy * 10;
+                const int iy = oy0 + yy - 1, ix = ox0 + xx - 1;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi)
+                    v = *reinterpret_cast<const uint4*>(in + ((size_t)iy * a.Wi + ix) * a.Cin + j * 8);
+                *reinterpret_cast<uint4*>(h_s + ((yy * NJ + j) * 10 + xx) * 16) = v;
+            }
         }
         // prefetch the residual while the MMAs run
         const int oy = oy0 + y, ox = ox0 + x;
