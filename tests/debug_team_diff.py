@@ -1,4 +1,5 @@
-"""Debug helper: run one team-schedule search against the C oracle and report where the trees differ."""
+"""TEST INFRASTRUCTURE (not collected by pytest): run one team-schedule search against the C oracle and report where the
+trees differ.  Lives under tests/ because it imports oracle/.  python tests/debug_team_diff.py"""
 import sys
 import numpy as np
 sys.path.insert(0, ".")
