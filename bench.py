@@ -69,11 +69,45 @@ PARAM_SEED, OBS_SEED, NOISE_SEED = 42, 0, 1
 FALLBACK_HBM_GBS = 6650.0
 
 
-def make_inputs(B: int, rank: int):
-    from oracle import network_np as nn  # parameter generator only (shared with the parity tests)
+def synthetic_params(seed: int):
+    """Random-init weights of the named architecture (lecun-normal-scale kernels, zero biases, identity BatchNorm), the
+    nested layout of cumind_b200/params.py.  Same draw order as the parity tests' generator, so both arms and the
+    tests search the same networks; the native arm does not import oracle/."""
+    rng = np.random.default_rng(seed)
+    f32 = np.float32
 
-    params = nn.random_params(OBS_SHAPE, A, H, L, CC, PARAM_SEED)
-    blob = nn.flatten_params(params, OBS_SHAPE)
+    def dense(i, o):
+        k = (rng.standard_normal((i, o)) / np.sqrt(i)).astype(f32)
+        return {"kernel": k, "bias": (rng.standard_normal(o) * 0.0).astype(f32)}   # signed zeros, as the tests' generator draws them
+
+    def conv(i, o):
+        k = (rng.standard_normal((3, 3, i, o)) / np.sqrt(9 * i)).astype(f32)
+        return {"kernel": k, "bias": (rng.standard_normal(o) * 0.0).astype(f32)}
+
+    def bn(c):
+        return {"scale": np.ones(c, f32), "bias": np.zeros(c, f32), "mean": np.zeros(c, f32), "var": np.ones(c, f32)}
+
+    if len(OBS_SHAPE) == 1:
+        layers, cur = {}, OBS_SHAPE[0]
+        for i in range(L):
+            layers[i] = dense(cur, H)
+            cur = H
+        enc = {"layers": layers}
+    else:
+        enc = {"initial_conv": conv(OBS_SHAPE[2], CC),
+               "residual_blocks": {i: {"conv1": conv(CC, CC), "bn1": bn(CC), "conv2": conv(CC, CC), "bn2": bn(CC)} for i in range(L)},
+               "final_dense": dense(CC, H)}
+    dyn = {"action_embedding": {"embedding": (rng.standard_normal((A, H)) / np.sqrt(H)).astype(f32)},
+           "layers": {i: dense(H, H) for i in range(L)}, "reward_head": dense(H, 1)}
+    pred = {"policy_head": dense(H, A), "value_head": dense(H, 1)}
+    return {"representation_network": {"encoder": enc}, "dynamics_network": dyn, "prediction_network": pred}
+
+
+def make_inputs(B: int, rank: int):
+    from cumind_b200 import params as P
+
+    params = synthetic_params(PARAM_SEED)
+    blob = P.flatten(params, OBS_SHAPE, A, H, L, CC)
     rng_obs = np.random.default_rng(OBS_SEED + 1000 * rank)
     obs = (rng_obs.standard_normal((B,) + OBS_SHAPE) if len(OBS_SHAPE) == 1 else rng_obs.random((B,) + OBS_SHAPE)).astype(np.float32)
     noise = np.random.default_rng(NOISE_SEED + 1000 * rank).dirichlet([ALPHA] * A, size=B)
@@ -94,7 +128,7 @@ def _cpu_init(S: int, max_trees: int):
     from oracle import mcts_port as port
     from oracle import network_np as nn
 
-    params = nn.random_params(OBS_SHAPE, A, H, L, CC, PARAM_SEED)
+    params = synthetic_params(PARAM_SEED)
     net = nn.NumpyCuMindNetwork(params, OBS_SHAPE, blas=True)
     rng = np.random.default_rng(os.getpid())
     obs = rng.standard_normal((max_trees,) + OBS_SHAPE).astype(np.float32)
