@@ -371,6 +371,12 @@ def run_native(args, rank: int, world: int, local_rank: int):
     visits_ok = bool(np.all(dump["visit"][:, 0] == 2 * S))
 
     # ---- end to end through the public API: host buffers in, host results out -------------------
+    # the caller (an environment loop) writes its observations and noise into the agent's pinned host buffers; every
+    # step the GPU reads them from there (H2D inside the timed region) and writes actions + probabilities back (D2H)
+    hb = agent.host_buffers(B)
+    hb["obs"][...] = obs
+    hb["noise"][...] = noise
+    obs, noise = hb["obs"], hb["noise"]
     for _ in range(3):
         agent.select_actions(obs, training=False, noise=noise)
     torch.cuda.synchronize()

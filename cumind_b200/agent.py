@@ -70,6 +70,31 @@ class Agent:
             action_idx = int(np.argmax(action_probs))
         return action_idx, action_probs
 
+    def _host_plan(self, B: int, A_cfg: int, A: int) -> Dict[str, Any]:
+        """Per batch shape: pinned host buffers (and NumPy views of them), the device work buffer, the C arguments."""
+        net, lib = self.network, self.mcts._lib
+        plan = self._host_plans.get((B, A_cfg, A))
+        if plan is None:
+            need = int(lib.cumind_select_actions_work_bytes(C.byref(net._desc), B, A_cfg))
+            work = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+            pin = {"obs": torch.empty((B,) + tuple(net.observation_shape), dtype=torch.float32).pin_memory(),
+                   "actions": torch.empty((B,), dtype=torch.int32).pin_memory(),
+                   "probs": torch.empty((B, A_cfg), dtype=torch.float64).pin_memory(),
+                   "noise": torch.empty((B, A), dtype=torch.float64).pin_memory()}
+            plan = {"need": need, "work": work, "wbase": C.c_void_p(work.data_ptr() + ((-work.data_ptr()) % 256)), "pin": pin,
+                    "np": {k: v.numpy() for k, v in pin.items()}, "ptr": {k: C.c_void_p(v.data_ptr()) for k, v in pin.items()},
+                    "null": C.c_void_p(0)}
+            self._host_plans.clear()  # one shape at a time: the buffers are sized for it
+            self._host_plans[(B, A_cfg, A)] = plan
+        return plan
+
+    def host_buffers(self, B: int) -> Dict[str, np.ndarray]:
+        """Pinned host arrays `{"obs": [B,*obs] float32, "noise": [B,A] float64}` that select_actions reads without a
+        staging copy when they are passed back to it: environments write their observations straight into them."""
+        A_cfg = int(self.config.action_space_size)
+        views = self._host_plan(int(B), A_cfg, min(A_cfg, self.network.action_space_size))["np"]
+        return {"obs": views["obs"], "noise": views["noise"]}
+
     def select_actions(self, observations: np.ndarray, training: bool = False, noise: Optional[np.ndarray] = None,
                        philox_seed: Optional[int] = None, tree_index_base: int = 0) -> Tuple[np.ndarray, np.ndarray]:
         """Batched select_action through ONE C-ABI call with host buffers (cumind_select_actions_host):
@@ -92,23 +117,12 @@ class Agent:
             if philox_seed is None:
                 philox_seed = int(self._rng.integers(0, 2**63 - 1))
         cfg = self.mcts._cfg(mode, philox_seed or 0, tree_index_base)
-        # per batch shape: pinned host buffers (and NumPy views of them), the device work buffer, the C arguments
-        plan = self._host_plans.get((B, A_cfg, A))
-        if plan is None:
-            need = int(lib.cumind_select_actions_work_bytes(C.byref(net._desc), B, A_cfg))
-            work = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
-            pin = {"obs": torch.empty(obs.shape, dtype=torch.float32).pin_memory(),
-                   "actions": torch.empty((B,), dtype=torch.int32).pin_memory(),
-                   "probs": torch.empty((B, A_cfg), dtype=torch.float64).pin_memory(),
-                   "noise": torch.empty((B, A), dtype=torch.float64).pin_memory()}
-            plan = {"need": need, "work": work, "wbase": C.c_void_p(work.data_ptr() + ((-work.data_ptr()) % 256)), "pin": pin,
-                    "np": {k: v.numpy() for k, v in pin.items()}, "ptr": {k: C.c_void_p(v.data_ptr()) for k, v in pin.items()},
-                    "null": C.c_void_p(0)}
-            self._host_plans.clear()  # one shape at a time: the buffers are sized for it
-            self._host_plans[(B, A_cfg, A)] = plan
+        plan = self._host_plan(B, A_cfg, A)
         views, ptr = plan["np"], plan["ptr"]
-        views["obs"][...] = obs
-        if noise is not None:
+        # inputs written in place into host_buffers() are already in the pinned memory the GPU reads
+        if obs.ctypes.data != views["obs"].ctypes.data:
+            views["obs"][...] = obs
+        if noise is not None and not (isinstance(noise, np.ndarray) and noise.ctypes.data == views["noise"].ctypes.data):
             views["noise"][...] = noise
         def call():
             _native.check(lib.cumind_select_actions_host(

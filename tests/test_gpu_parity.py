@@ -294,6 +294,12 @@ def test_select_actions_host_path_matches_oracle():
         actions, probs = agent.select_actions(obs, training=False, noise=nz)
         assert np.array_equal(probs, o["out_probs"])
         assert np.array_equal(actions, np.argmax(o["out_probs"], axis=1))
+    # inputs written in place into the agent's pinned buffers (no staging copy) give the same answer
+    hb = agent.host_buffers(B)
+    hb["obs"][...] = obs
+    hb["noise"][...] = noise
+    a2, p2 = agent.select_actions(hb["obs"], training=False, noise=hb["noise"])
+    assert np.array_equal(a2, actions) and np.array_equal(p2, probs)
     # the same C-ABI call with PAGEABLE host buffers (cudaMemcpyAsync path instead of the mapped-memory kernels)
     import ctypes as C
 
