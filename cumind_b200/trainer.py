@@ -139,6 +139,7 @@ class Trainer:
         self._step_dev = torch.tensor([self._count], dtype=torch.int64, device=dev)
         self._mask = torch.as_tensor(trainable_mask(self._dims)).to(dev)
         self.use_cuda_graph = True
+        self.graph_distributed = True   # torch.distributed: two graphs around an eager all-reduce
         self._graph, self._graph_key, self._graph_out, self._static = None, None, None, None
         self._state_stale = False
 
@@ -181,20 +182,18 @@ class Trainer:
             return forward_losses(self._flat, self._dims, torch.as_tensor(np.asarray(observations, np.float32)).to(dev),
                                   torch.as_tensor(np.asarray(actions)).to(dev), t, self.config.num_unroll_steps)
 
-    def _eager_step(self, observations, actions, targets) -> Dict[str, torch.Tensor]:
-        """loss -> grad -> (all-reduce) -> AdamW -> push parameters; every launch on the current stream."""
+    def _fwd_bwd(self, observations, actions, targets):
+        """loss -> grad of the flat parameter blob (torch autograd over views of it)."""
         leaf = self._flat.detach().requires_grad_(True)   # fresh autograd leaf over the same storage
         losses = forward_losses(leaf, self._dims, observations, actions, targets, self.config.num_unroll_steps)
         total = losses["value_loss"] + losses["policy_loss"] + losses["reward_loss"]
         total.backward()
         grad = leaf.grad
         self.last_grad = grad
-        losses = {k: v.detach() for k, v in losses.items()}
-        total = total.detach()
-        world = 1
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            world = torch.distributed.get_world_size()
-            torch.distributed.all_reduce(grad)            # one flat bucket over NCCL / NVLink
+        return {**{k: v.detach() for k, v in losses.items()}, "total_loss": total.detach()}, grad
+
+    def _apply(self, grad, world: int) -> None:
+        """AdamW on the (all-reduced) flat gradient, then push the parameters to the search kernels' layouts."""
         opt = self.agent.optimizer
         with torch.no_grad():
             _native.check(self._lib.cumind_adamw_step_dev(
@@ -202,7 +201,16 @@ class Trainer:
                 C.c_void_p(self._v.data_ptr()), C.c_void_p(self._mask.data_ptr()), self._flat.numel(), opt.learning_rate, opt.b1,
                 opt.b2, opt.eps, opt.weight_decay, C.c_void_p(self._step_dev.data_ptr()), 1.0 / world, _stream_ptr()))
             self.agent.network.update_from_device(self._flat)
-        return {**losses, "total_loss": total}
+
+    def _eager_step(self, observations, actions, targets) -> Dict[str, torch.Tensor]:
+        """loss -> grad -> (all-reduce) -> AdamW -> push parameters; every launch on the current stream."""
+        out, grad = self._fwd_bwd(observations, actions, targets)
+        world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size()
+            torch.distributed.all_reduce(grad)            # one flat bucket over NCCL / NVLink
+        self._apply(grad, world)
+        return out
 
     def _graph_step(self, observations, actions, targets) -> Dict[str, torch.Tensor]:
         """Replay the whole step from one CUDA graph (static shapes; single process)."""
@@ -233,6 +241,43 @@ class Trainer:
         self._graph.replay()
         return self._graph_out
 
+    def _graph_step_distributed(self, observations, actions, targets) -> Dict[str, torch.Tensor]:
+        """torch.distributed: the step as two CUDA graphs (loss + gradient | AdamW + parameter push) around ONE eager
+        NCCL all-reduce of the flat gradient — the collective itself is not captured."""
+        world = torch.distributed.get_world_size()
+        key = (tuple(observations.shape), tuple(actions.shape))
+        if self._graph is None or self._graph_key != key:
+            self._static = (observations.clone(), actions.clone(), {k: v.clone() for k, v in targets.items()})
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            state = (self._flat.detach().clone(), self._m.clone(), self._v.clone(), self._step_dev.clone())
+            with torch.cuda.stream(side):
+                for _ in range(3):                       # warm-up outside the capture (every rank: same three all-reduces)
+                    self._eager_step(*self._static)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            with torch.no_grad():
+                self._flat.copy_(state[0]); self._m.copy_(state[1]); self._v.copy_(state[2]); self._step_dev.copy_(state[3])
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self._graph_out, self._graph_grad = self._fwd_bwd(*self._static)
+            with torch.cuda.graph(g2, pool=g1.pool()):
+                self._apply(self._graph_grad, world)
+            with torch.no_grad():
+                self._flat.copy_(state[0]); self._m.copy_(state[1]); self._v.copy_(state[2]); self._step_dev.copy_(state[3])
+            self.agent.network.update_from_device(self._flat)
+            self._graph, self._graph_key = (g1, g2), key
+        so, sa, st = self._static
+        so.copy_(observations); sa.copy_(actions)
+        for k in st:
+            st[k].copy_(targets[k])
+        g1, g2 = self._graph
+        g1.replay()
+        torch.distributed.all_reduce(self._graph_grad)
+        g2.replay()
+        self.last_grad = self._graph_grad
+        return self._graph_out
+
     def train_step(self, batch: Optional[Tuple[Any, Any, Dict[str, Any]]] = None) -> Dict[str, float]:
         """One optimiser step.  `batch` = (observations, actions [B,K], targets) skips the replay sampling."""
         if batch is None:
@@ -246,6 +291,8 @@ class Trainer:
         distributed = torch.distributed.is_available() and torch.distributed.is_initialized()
         if self.use_cuda_graph and not distributed:
             out = self._graph_step(observations, actions, targets)
+        elif self.use_cuda_graph and self.graph_distributed:
+            out = self._graph_step_distributed(observations, actions, targets)
         else:
             out = self._eager_step(observations, actions, targets)
         self._count += 1
