@@ -2,20 +2,23 @@
 // warp-specialised: the tree walk and the network run on different warps of the same CTA, and the
 // tree statistics live in shared memory while a tree is being searched.
 //
-// The per-tree work of one simulation is a serial chain (walk d levels of float64 PUCT -> dynamics
-// MLP -> heads -> softmax -> backup).  search_fused.cu gives every warp the whole chain of its own
+// The per-tree work of one simulation is a serial chain (walk d levels -> dynamics MLP -> heads ->
+// backup with float64 PUCT re-scoring; softmax -> priors trails one simulation behind).  search_fused.cu gives every warp the whole chain of its own
 // few trees, so each phase runs at a fraction of a warp's lanes and an SM holds only a handful of
 // warps.  Here a CTA is split into TEAMS; a team owns up to TT trees (a batch) and has two kinds of warps:
 //
-//   tree warps     G = pow2 >= A lanes per tree (32/G trees per warp): select_child / ucb_score
-//                  (mcts.py:51-76, 165-171), softmax -> Node.expand (78-89, 189-196), backup (199-203).
-//                  Latency-bound.  They work on "hot" records in shared memory that hold what one level
-//                  of the walk needs in a form that keeps its dependency chain short (see HotSel): the
-//                  value term W/n is refreshed by the backup (off the walk's critical path), c_puct*prior
-//                  is fixed at expansion, and RN(1/(1+n)) for the exact table-driven division rides along.
+//   tree warps     G = pow2 >= A lanes per tree (32/G trees per warp): the walk of mcts.py:165-171 as a pointer chase
+//                  through the selection cache (select_chase), Node.expand (78-89, 195-196) in two parts — the
+//                  children are created right after the walk, their priors (softmax, 189-196) one simulation
+//                  later, off the critical path — and the visit-count normalisation at the end (143-155).
 //   network warps  dynamics + prediction (network.py:217-236, 254-266) for all trees of the team as one
 //                  register-tiled product: lane = (group of TQ trees, NV neurons), operands double
-//                  buffered from shared memory, TQ*NV sequential-k FMA chains per lane.
+//                  buffered from shared memory, TQ*NV sequential-k FMA chains per lane; then the backup
+//                  (mcts.py:199-203) merged with the re-evaluation of select_child / ucb_score (51-76) for
+//                  every parent on the path (backup_rescore), which is what fills the selection cache.
+//                  The "hot" records in shared memory (HotSel) hold what that needs in a form that keeps its
+//                  dependency chain short: W/n already divided, c_puct*prior fixed at expansion, RN(1/(1+n))
+//                  for the exact table-driven division.
 //
 // The two roles hand over through shared memory and two named barriers per simulation (bar.sync id,
 // count: no CTA-wide barrier, teams never wait for each other).  The canonical tree arrays in HBM
