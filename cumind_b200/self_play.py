@@ -9,9 +9,39 @@ over B trees) per step, so the host loop no longer starves the GPU.
 
 from __future__ import annotations
 
+from collections.abc import Sequence
 from typing import Any, Dict, List, Optional
 
 import numpy as np
+
+
+class Trajectory(Sequence):
+    """One episode as array views (observation [T,*obs], action [T], reward [T], policy [T,A], done [T]) that reads like
+    the reference's list of step dicts (src/cumind/data/self_play.py:50-57): `len(t)`, `t[i]` -> dict, `t[:k]` -> list of
+    dicts, iteration.  run_batch stores the steps of all environments step-major and hands out episodes as strided
+    views, so the per-step host work does not grow with the number of environments."""
+
+    __slots__ = ("observation", "action", "reward", "policy", "done")
+
+    def __init__(self, observation, action, reward, policy, done):
+        self.observation, self.action, self.reward, self.policy, self.done = observation, action, reward, policy, done
+
+    def __len__(self) -> int:
+        return len(self.action)
+
+    def _step(self, i: int) -> Dict[str, Any]:
+        return {"observation": self.observation[i], "action": int(self.action[i]), "reward": float(self.reward[i]),
+                "policy": self.policy[i], "done": bool(self.done[i])}
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._step(j) for j in range(*i.indices(len(self)))]
+        n = len(self)
+        if i < 0:
+            i += n
+        if not 0 <= i < n:
+            raise IndexError(i)
+        return self._step(i)
 
 
 class SelfPlay:
@@ -34,25 +64,37 @@ class SelfPlay:
             self.memory.add(episode)
         return episode
 
-    def run_batch(self, vec_env, num_steps: int, training: bool = True, philox_seed: Optional[int] = None) -> List[List[List[Dict[str, Any]]]]:
+    def run_batch(self, vec_env, num_steps: int, training: bool = True, philox_seed: Optional[int] = None) -> List[List[Trajectory]]:
         """Step `vec_env.num_envs` environments `num_steps` times.  Returns, per environment, the list of
-        its finished episodes followed by the (possibly unfinished) current one, each a list of step dicts."""
+        its finished episodes followed by the (possibly unfinished) current one, each a Trajectory (reads like the
+        reference's list of step dicts).  Finished episodes go to `memory.add` as they end."""
         B = vec_env.num_envs
-        finished: List[List[List[Dict[str, Any]]]] = [[] for _ in range(B)]
-        current: List[List[Dict[str, Any]]] = [[] for _ in range(B)]
         observation, _ = vec_env.reset()
+        observation = np.asarray(observation)
+        A = int(self.agent.config.action_space_size)
+        # step-major storage of everything the step record holds; episodes are slices [first step : last step + 1, env]
+        obs_buf = np.empty((num_steps,) + observation.shape, dtype=observation.dtype)
+        act_buf = np.empty((num_steps, B), dtype=np.int32)
+        rew_buf = np.empty((num_steps, B), dtype=np.float32)
+        pol_buf = np.empty((num_steps, B, A), dtype=np.float64)
+        done_buf = np.zeros((num_steps, B), dtype=bool)
+        start = np.zeros(B, dtype=np.int64)
+        finished: List[List[Trajectory]] = [[] for _ in range(B)]
+
+        def episode(i: int, s0: int, s1: int) -> Trajectory:
+            return Trajectory(obs_buf[s0:s1, i], act_buf[s0:s1, i], rew_buf[s0:s1, i], pol_buf[s0:s1, i], done_buf[s0:s1, i])
+
         for step in range(num_steps):
             seed = None if philox_seed is None else philox_seed + step
             actions, policies = self.agent.select_actions(observation, training=training, philox_seed=seed)
             next_observation, reward, terminated, truncated, _ = vec_env.step(actions)
             done = np.logical_or(terminated, truncated)
-            for i in range(B):
-                current[i].append({"observation": observation[i], "action": int(actions[i]), "reward": float(reward[i]),
-                                   "policy": policies[i], "done": bool(done[i])})
-                if done[i]:
-                    if self.memory is not None:
-                        self.memory.add(current[i])
-                    finished[i].append(current[i])
-                    current[i] = []
-            observation = next_observation
-        return [finished[i] + ([current[i]] if current[i] else []) for i in range(B)]
+            obs_buf[step], act_buf[step], rew_buf[step], pol_buf[step], done_buf[step] = observation, actions, reward, policies, done
+            for i in np.nonzero(done)[0]:                      # only the environments whose episode just ended
+                ep = episode(int(i), int(start[i]), step + 1)
+                if self.memory is not None:
+                    self.memory.add(ep)
+                finished[i].append(ep)
+                start[i] = step + 1
+            observation = np.asarray(next_observation)
+        return [finished[i] + ([episode(i, int(start[i]), num_steps)] if start[i] < num_steps else []) for i in range(B)]

@@ -28,6 +28,66 @@ def test_cartpole_vec_physics_and_auto_reset():
     assert ended.all()
 
 
+class _FakeAgent:
+    """select_actions stand-in (no GPU): random policies, actions sampled from them."""
+
+    class config:
+        action_space_size = 2
+
+    def __init__(self, seed=0):
+        self.rng = np.random.default_rng(seed)
+
+    def select_actions(self, obs, training=True, philox_seed=None):
+        p = self.rng.dirichlet([1.0, 1.0], size=obs.shape[0])
+        return (self.rng.random(obs.shape[0]) < p[:, 1]).astype(np.int32), p
+
+
+def test_run_batch_bookkeeping_equals_the_per_environment_loop():
+    """run_batch stores the steps step-major and hands out episodes as array views (Trajectory); the records, the
+    episode boundaries and what reaches memory.add equal the reference-style loop that appends one dict per
+    environment and step (src/cumind/data/self_play.py:44-61)."""
+    from cumind_b200.self_play import SelfPlay, Trajectory
+
+    class Mem:
+        def __init__(self):
+            self.items = []
+
+        def add(self, x):
+            self.items.append(x)
+
+    B, T = 37, 120
+    mem = Mem()
+    got = SelfPlay(_FakeAgent(), mem).run_batch(CartPoleVec(B, seed=2), T)
+    agent, env = _FakeAgent(), CartPoleVec(B, seed=2)
+    obs, _ = env.reset()
+    cur, fin = [[] for _ in range(B)], [[] for _ in range(B)]
+    for _ in range(T):
+        a, p = agent.select_actions(obs)
+        nobs, r, te, tr, _ = env.step(a)
+        d = te | tr
+        for i in range(B):
+            cur[i].append({"observation": obs[i], "action": int(a[i]), "reward": float(r[i]), "policy": p[i], "done": bool(d[i])})
+            if d[i]:
+                fin[i].append(cur[i])
+                cur[i] = []
+        obs = nobs
+    want = [fin[i] + ([cur[i]] if cur[i] else []) for i in range(B)]
+    n = 0
+    for i in range(B):
+        assert len(got[i]) == len(want[i])
+        for e, w in zip(got[i], want[i]):
+            assert isinstance(e, Trajectory) and len(e) == len(w)
+            for s, t in zip(e, w):
+                n += 1
+                assert set(s) == {"observation", "action", "reward", "policy", "done"}
+                assert (s["action"], s["reward"], s["done"]) == (t["action"], t["reward"], t["done"])
+                assert np.array_equal(s["observation"], t["observation"]) and np.array_equal(s["policy"], t["policy"])
+            assert [x["action"] for x in e[:5]] == [x["action"] for x in w[:5]] and e[-1]["done"] == w[-1]["done"]
+            with pytest.raises(IndexError):
+                e[len(e)]
+    assert n == B * T and len(mem.items) == sum(len(f) for f in fin)
+
+
 @pytest.mark.gpu
 def test_batched_self_play_runs_the_fused_search_per_step():
     from cumind_b200 import Agent, Config
