@@ -167,6 +167,9 @@ class DeviceSumTree:
             raise ValueError("tree_idx and priority must have the same length")
         if idx.numel() == 0:
             return
+        lo, hi = int(idx.min()), int(idx.max())
+        if lo < 0 or hi >= self.n_nodes:   # the NumPy tree of the reference raises here (negative indices are not supported)
+            raise IndexError(f"tree index out of range [0, {self.n_nodes}): {lo if lo < 0 else hi}")
         idx, pri = idx.contiguous(), pri.contiguous()
         with torch.cuda.device(self.device):
             self._native.check(self._lib.cumind_sumtree_update(self._handle, C.c_void_p(idx.data_ptr()), C.c_void_p(pri.data_ptr()),

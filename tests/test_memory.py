@@ -200,5 +200,7 @@ def test_device_sum_tree_matches_host_tree_on_random_batches(cap):
         assert host.max_priority == dev.max_priority
         u = rng.random(257)
         assert np.array_equal(host.sample_indices(257, uniforms=u), dev.sample_indices(257, uniforms=u))
+    with pytest.raises(IndexError):
+        dev._dev.update([dev._dev.n_nodes], [1.0])
     host.clear(), dev.clear()
     assert not dev.sum_tree.any() and len(dev) == 0
