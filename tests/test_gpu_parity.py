@@ -163,6 +163,22 @@ def test_team_search_vs_oracle_all_geometries(shape, geom):
     assert hp.bits_equal(mcts.last_root_value.cpu().numpy(), o["out_root_value"])
 
 
+def test_more_actions_than_lanes_in_both_schedules():
+    """A = 40 > 32 lanes per tree: the tree warps stride over the children, the rescoring loops over all of them."""
+    from cumind_b200 import _native
+    from cumind_b200.mcts import MCTS
+
+    A, H, S, B = 40, 32, 12, 150
+    o, h, noise, blob = _team_case(A, H, S, B)
+    net = _network((4,), A, H, 2, 32, blob)
+    for schedule in (_native.SCHED_TEAM, _native.SCHED_WARP):
+        mcts = MCTS(net, _Cfg(S, A))
+        mcts.schedule = schedule
+        probs, visits = mcts.search_batch(h, noise=noise)
+        _assert_trees_equal(mcts, o, S, A)
+        assert np.array_equal(visits, o["out_visits"]) and np.array_equal(probs, o["out_probs"])
+
+
 @pytest.mark.parametrize("c_puct", [1e290, 3e-300, 0.0, float("inf")], ids=["huge", "tiny", "zero", "inf"])
 def test_team_search_leaves_the_bare_division_when_it_is_not_exact(c_puct):
     """The team kernel's walk divides with the bare Markstein sequence only while c_puct*prior stays in the
