@@ -291,6 +291,46 @@ def test_baseline_config2_full_size_bit_exact():
     assert hp.bits_equal(rv, o["out_root_value"])
 
 
+def test_baseline_config4_full_size_schedules_agree_and_invariants_hold():
+    """BASELINE configs[3]: 65 536 CartPole-shaped trees x 50 simulations.  Too many for the CPU oracle in a test, so
+    the two independent CUDA schedules check each other (team: 16 rounds of shared-memory trees; warp: trees in
+    HBM/L2) — every output of every tree identical — next to the size-independent invariants of the reference
+    semantics (root.n == 2S, sum of root-child visits == S - A, probabilities sum to 1) and a 2 048-tree slice
+    checked against the oracle bit for bit (sharding by environment: a slice searched alone gives the same trees)."""
+    import torch
+
+    from cumind_b200 import _native
+    from cumind_b200.mcts import MCTS
+    from oracle import network_np as nn
+
+    B, A, H, S = 65536, 2, 64, 50
+    blob = nn.flatten_params(nn.random_params((4,), A, H, 2, 32, 42), (4,))
+    net = _network((4,), A, H, 2, 32, blob)
+    obs = np.random.default_rng(0).standard_normal((B, 4)).astype(np.float32)
+    noise = np.random.default_rng(1).dirichlet([0.3] * A, size=B)
+    h_gpu = net.representation_network(obs)
+    out = {}
+    for name, schedule in (("warp", _native.SCHED_WARP), ("team", _native.SCHED_TEAM)):
+        mcts = MCTS(net, _Cfg(S, A))
+        mcts.schedule = schedule
+        assert mcts.plan(B)["schedule"] == name
+        probs, visits = mcts.search_batch(h_gpu, noise=noise, return_device=True)
+        out[name] = (probs.clone(), visits.clone(), mcts.last_root_value.clone())
+        del mcts
+        torch.cuda.empty_cache()
+    for a, b in zip(out["warp"], out["team"]):
+        assert torch.equal(a.view(torch.int64) if a.dtype == torch.float64 else a, b.view(torch.int64) if b.dtype == torch.float64 else b)
+    probs, visits, _ = out["team"]
+    assert bool((visits.sum(dim=1) == S - A).all()) and bool((visits >= 0).all())
+    assert bool(((probs.sum(dim=1) - 1.0).abs() < 1e-12).all())
+    # a slice against the oracle
+    lo_, hi_ = 30000, 32048
+    desc = lo.make_desc((4,), A, H, 2)
+    h, _, _ = lo.initial_inference(desc, blob, obs[lo_:hi_])
+    o = lo.search(desc, blob, h, S, A, 1.25, 0.25, noise[lo_:hi_])
+    assert np.array_equal(visits[lo_:hi_].cpu().numpy(), o["out_visits"]) and np.array_equal(probs[lo_:hi_].cpu().numpy(), o["out_probs"])
+
+
 def test_select_actions_host_path_matches_oracle():
     """Agent.select_actions -> cumind_select_actions_host (host buffers in/out) == oracle actions."""
     from cumind_b200 import Config
