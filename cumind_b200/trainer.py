@@ -16,7 +16,9 @@ the search kernels with `cumind_net_update_params_device`.
 
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import gc
 import os
 from datetime import datetime
 from typing import Any, Dict, List, Optional, Sequence, Tuple
@@ -29,6 +31,20 @@ from . import _native, params as P
 from .checkpoint import load_checkpoint, save_checkpoint
 from .memory import MemoryBuffer  # noqa: F401  (re-exported: the buffer runner.train uses, memory.py:88-113)
 from .network import _stream_ptr
+
+
+@contextlib.contextmanager
+def _no_gc():
+    """No cyclic garbage collection while a CUDA graph is being captured: a collected Agent / MCTS / DeviceSumTree frees
+    device memory in its finaliser (cudaFree), and any such call during a capture invalidates it."""
+    gc.collect()
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was:
+            gc.enable()
 
 
 class _ParamViews:
@@ -228,7 +244,7 @@ class Trainer:
             with torch.no_grad():                        # undo the warm-up updates
                 self._flat.copy_(state[0]); self._m.copy_(state[1]); self._v.copy_(state[2]); self._step_dev.copy_(state[3])
             self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
+            with _no_gc(), torch.cuda.graph(self._graph):
                 self._graph_out = self._eager_step(*self._static)
             with torch.no_grad():                        # capture does not execute: state is unchanged, but be explicit
                 self._flat.copy_(state[0]); self._m.copy_(state[1]); self._v.copy_(state[2]); self._step_dev.copy_(state[3])
@@ -259,9 +275,9 @@ class Trainer:
             with torch.no_grad():
                 self._flat.copy_(state[0]); self._m.copy_(state[1]); self._v.copy_(state[2]); self._step_dev.copy_(state[3])
             g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g1):
+            with _no_gc(), torch.cuda.graph(g1):
                 self._graph_out, self._graph_grad = self._fwd_bwd(*self._static)
-            with torch.cuda.graph(g2, pool=g1.pool()):
+            with _no_gc(), torch.cuda.graph(g2, pool=g1.pool()):
                 self._apply(self._graph_grad, world)
             with torch.no_grad():
                 self._flat.copy_(state[0]); self._m.copy_(state[1]); self._v.copy_(state[2]); self._step_dev.copy_(state[3])
