@@ -126,6 +126,29 @@ def load():
     return lib
 
 
+_pending_destroy = []
+
+
+def destroy_handle(fn, handle) -> None:
+    """Call a `*_destroy` entry point (they cudaFree) — but never while the current stream is capturing a CUDA graph: a
+    finaliser that runs during a capture (garbage collection) would invalidate it.  Deferred handles are destroyed by
+    the next call made outside a capture."""
+    import torch
+
+    capturing = False
+    try:
+        capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+    except Exception:
+        capturing = False
+    if capturing:
+        _pending_destroy.append((fn, handle))
+        return
+    while _pending_destroy:
+        f, h = _pending_destroy.pop()
+        f(h)
+    fn(handle)
+
+
 def check(rc: int) -> None:
     if rc != 0:
         msg = load().cumind_last_error().decode("utf-8", "replace")

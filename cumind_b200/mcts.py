@@ -101,7 +101,7 @@ class _TreeSlab:
     def __del__(self):
         try:
             if self.handle.value:
-                self.lib.cumind_tree_destroy(self.handle)
+                _native.destroy_handle(self.lib.cumind_tree_destroy, self.handle)
                 self.handle = C.c_void_p()
         except Exception:
             pass

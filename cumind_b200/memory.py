@@ -145,7 +145,7 @@ class DeviceSumTree:
 
     def close(self) -> None:
         if getattr(self, "_handle", None):
-            self._lib.cumind_sumtree_destroy(self._handle)
+            self._native.destroy_handle(self._lib.cumind_sumtree_destroy, self._handle)
             self._handle = None
 
     def __del__(self):

@@ -152,7 +152,7 @@ class CuMindNetwork:
     def __del__(self):
         try:
             if getattr(self, "_handle", None) is not None and self._handle.value:
-                self._lib.cumind_net_destroy(self._handle)
+                _native.destroy_handle(self._lib.cumind_net_destroy, self._handle)
                 self._handle = C.c_void_p()
         except Exception:
             pass
