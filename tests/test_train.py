@@ -2,6 +2,8 @@
 and the GPU step (torch autograd over the flat blob + cumind_adamw_step) against the oracle.
 Tolerances: gradients rtol 1e-4 (fp32 GEMM reductions vs float64), AdamW update rtol 1e-5."""
 
+import os
+
 import numpy as np
 import pytest
 
@@ -148,3 +150,36 @@ def test_trainer_runs_from_replay_with_bootstrapped_targets_and_image_observatio
     mask = trainable_mask(iagent.network._dims).astype(bool)
     after = iagent.network.blob
     assert np.array_equal(after[~mask], before[~mask]) and not np.array_equal(after[mask], before[mask])
+
+
+@pytest.mark.gpu
+def test_distributed_two_graph_step_equals_the_eager_step():
+    """torch.distributed initialised (world_size 1 over gloo, so it runs on one GPU): the step replayed as two CUDA graphs
+    around an eager all-reduce follows exactly the same training trajectory as the eager step."""
+    import torch
+    import torch.distributed as dist
+
+    from cumind_b200 import Agent, Config
+    from cumind_b200.trainer import MemoryBuffer, Trainer
+
+    params, obs, actions, targets, (D, A, H, L, K) = _problem(B=32, A=3, H=16, L=2, K=3, D=5, seed=9)
+    cfg = Config(hidden_dim=H, num_blocks=L, action_space_size=A, observation_shape=(D,), num_unroll_steps=K, learning_rate=1e-2,
+                 weight_decay=1e-4, num_simulations=4)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29731")
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        runs = []
+        for graphs in (True, False):
+            agent = Agent(cfg)
+            agent.load_state({"network_state": params, "optimizer_state": {"count": 0}})
+            tr = Trainer(agent, MemoryBuffer(4), cfg)
+            tr.use_cuda_graph = graphs
+            losses = [tr.train_step((obs, actions, targets))["total_loss"] for _ in range(6)]
+            runs.append((losses, agent.network.blob.copy()))
+            if graphs:
+                assert isinstance(tr._graph, tuple) and len(tr._graph) == 2   # the two-graph path was taken
+        assert runs[0][0] == runs[1][0]
+        assert np.array_equal(runs[0][1], runs[1][1])
+    finally:
+        dist.destroy_process_group()
