@@ -41,7 +41,6 @@ struct TeamParams {
     double c_puct, frac, one_minus_frac, alpha;
     int noise_mode;
     unsigned long long seed, tree_base;
-    int path_in_smem;
     // team geometry: n_team teams per CTA, each ntw tree warps + nmw network warps; TT tree slots per
     // team (compile-time in the kernel: 8 or 16), of which tpt are used per batch
     int n_team, ntw, nmw, TT, tpt, n_batches;

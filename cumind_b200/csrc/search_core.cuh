@@ -236,35 +236,6 @@ CM_DEVICE void backup_path(Node* __restrict__ nodes, const int* __restrict__ pat
     }
 }
 
-// Same backup with the record loads of up to four path entries per lane in flight at once (the team
-// kernel runs it with G as small as 2, where the serial version pays one L1 round trip per entry).
-template <int G>
-CM_DEVICE void backup_path_ilp(Node* __restrict__ nodes, const int* __restrict__ path, int plen, float leaf_value, int g) {
-    const double v = (double)leaf_value;
-#pragma unroll 1
-    for (int i0 = g; i0 < plen; i0 += 4 * G) {
-        int nd[4];
-        Node r[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * G;
-            nd[u] = i < plen ? path[i] : -1;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (nd[u] >= 0) r[u] = load_node(nodes + nd[u]);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (nd[u] >= 0) {
-                double w = __dadd_rn(r[u].value_sum, v);
-                int n = r[u].visit + 1;
-                if (nd[u] == 0) { w = __dadd_rn(w, v); n += 1; }
-                store_node(nodes + nd[u], w, n, r[u].prior);
-            }
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // Network, fp32-exact mode: every dot product is a sequential-k chain of IEEE fused multiply-adds,
 // exactly as oracle/cumind_oracle.c::cmo_linear.  Per-tree helpers (stepwise kernels) first, then the
