@@ -22,7 +22,7 @@ EXPORTS = [
     "cumind_tree_init_root", "cumind_select", "cumind_expand", "cumind_backup", "cumind_finalize", "cumind_dirichlet",
     "cumind_launch_count", "cumind_selftest_division", "cumind_adamw_step", "cumind_adamw_step_dev", "cumind_net_update_params_device",
     "cumind_sumtree_create", "cumind_sumtree_destroy", "cumind_sumtree_tree_size", "cumind_sumtree_clear", "cumind_sumtree_update",
-    "cumind_sumtree_sample", "cumind_sumtree_read",
+    "cumind_sumtree_sample", "cumind_sumtree_read", "cumind_search_from_obs", "cumind_net_reserve",
 ]
 
 NET_FP32_EXACT = 0
@@ -98,6 +98,8 @@ def load():
     search_args = [vp, vp, vp, C.POINTER(SearchCfg), vp, vp, vp, vp, vp]
     lib.cumind_search.argtypes = search_args
     lib.cumind_search_stepwise.argtypes = search_args
+    lib.cumind_search_from_obs.argtypes = [vp, vp, vp, C.POINTER(SearchCfg), vp, vp, vp, vp, vp, vp]
+    lib.cumind_net_reserve.argtypes = [vp, i32]
     lib.cumind_search_phase_clocks.argtypes = search_args[:-1] + [vp, vp]
     lib.cumind_search_plan.argtypes = [vp, vp, C.POINTER(SearchCfg), C.POINTER(i32 * 8)]
     lib.cumind_select_actions_host.argtypes = [vp, vp, vp, C.POINTER(SearchCfg), vp, vp, vp, vp, sz, vp]

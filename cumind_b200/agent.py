@@ -75,6 +75,7 @@ class Agent:
         net, lib = self.network, self.mcts._lib
         plan = self._host_plans.get((B, A_cfg, A))
         if plan is None:
+            net.reserve(B)
             need = int(lib.cumind_select_actions_work_bytes(C.byref(net._desc), B, A_cfg))
             work = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
             pin = {"obs": torch.empty((B,) + tuple(net.observation_shape), dtype=torch.float32).pin_memory(),

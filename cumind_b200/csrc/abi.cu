@@ -345,6 +345,26 @@ extern "C" int cumind_net_update_params(cumind_net* n, const float* h_params, si
     return 0;
 }
 
+static int encoder_chunk(bool tc, int B) { return tc ? (B < 1024 ? B : 1024) : (B < 128 ? B : 128); }
+
+extern "C" int cumind_net_reserve(cumind_net* n, int32_t max_batch) {
+    if (!n || max_batch <= 0) return fail("cumind_net_reserve: bad argument");
+    if (n->desc.obs_ndim != 3) return 0;
+    size_t need = conv_encoder_work_bytes(n->desc, encoder_chunk(false, max_batch));
+    if (n->conv_tc_ok) {
+        const size_t t = conv_tc_work_bytes(n->desc, encoder_chunk(true, max_batch));
+        if (t > need) need = t;
+    }
+    if (need <= n->work_bytes) return 0;
+    CM_CUDA(cudaDeviceSynchronize());
+    cudaFree(n->d_work);
+    n->d_work = nullptr;
+    n->work_bytes = 0;
+    CM_CUDA(cudaMalloc(&n->d_work, need));
+    n->work_bytes = need;
+    return 0;
+}
+
 extern "C" int cumind_net_destroy(cumind_net* n) {
     if (!n) return 0;
     cudaFree(n->d_blob);
@@ -405,16 +425,10 @@ extern "C" int cumind_initial_inference(const cumind_net* cn, const float* d_obs
         if (tc && !n->conv_tc_ok) return fail("CUMIND_NET_BF16_TC image encoder needs conv_channels % 16 == 0 and <= 256");
         // 1024 images per pass: smaller passes that would keep the three activation buffers inside L2 measured slower
         // (0.91 ms at 512, 0.98 at 256 vs 0.85 at 1024: the layers are bound by per-tile latency, not by DRAM)
-        const int chunk = tc ? (B < 1024 ? B : 1024) : (B < 128 ? B : 128);
+        const int chunk = encoder_chunk(tc, B);
         const size_t need = tc ? conv_tc_work_bytes(n->desc, chunk) : conv_encoder_work_bytes(n->desc, chunk);
-        if (need > n->work_bytes) {
-            CM_CUDA(cudaStreamSynchronize(st));
-            cudaFree(n->d_work);
-            n->d_work = nullptr;
-            n->work_bytes = 0;
-            CM_CUDA(cudaMalloc(&n->d_work, need));
-            n->work_bytes = need;
-        }
+        if (need > n->work_bytes)
+            return fail("cumind_initial_inference: image-encoder workspace too small for this batch; call cumind_net_reserve(net, max_batch) first");
         if (tc)
             CM_CUDA(launch_conv_encoder_tc(nv, n->d_cpack, n->cpk, n->sm_count, d_obs, B, d_hidden, (unsigned char*)n->d_work, chunk, st));
         else
@@ -643,6 +657,7 @@ static int plan_fused(const cumind_tree* t, const cumind_net* n, const cumind_se
     p.slot_bytes = (unsigned)slot;
     p.off_bar = (unsigned)((off_slots + (size_t)nw * slot + 7) & ~(size_t)7);
     p.n_sqrt = n_sqrt;
+    p.pdl = 0;
     return 0;
 }
 
@@ -745,6 +760,7 @@ static int plan_team(const cumind_tree* t, const cumind_net* n, const cumind_sea
     p.off_bar = (unsigned)((off_teams + (size_t)n_team * team_bytes + 7) & ~(size_t)7);
     p.n_sqrt = n_sqrt;
     p.clk = nullptr;
+    p.pdl = 0;
     p.tile = 0;
     p.stagger = 0;
     if (const char* e = getenv("CUMIND_TEAM_TILE")) p.tile = atoi(e);        // tuning only
@@ -781,9 +797,11 @@ extern "C" int cumind_search_stepwise(cumind_tree* t, const cumind_net* n, const
     return 0;
 }
 
-extern "C" int cumind_search(cumind_tree* t, const cumind_net* n, const float* d_root_hidden, const cumind_search_cfg* c,
-                             const double* d_noise, int32_t* d_out_visits, double* d_out_probs, double* d_out_root_value,
-                             void* stream) {
+// pdl: d_root_hidden is written by the kernel launched just before on `stream`, which calls pdl_launch_dependents():
+// the search kernel is launched with programmatic stream serialization so that its prologue overlaps that kernel.
+static int search_impl(cumind_tree* t, const cumind_net* n, const float* d_root_hidden, const cumind_search_cfg* c,
+                       const double* d_noise, int32_t* d_out_visits, double* d_out_probs, double* d_out_root_value,
+                       void* stream, bool pdl) {
     if (check_search("cumind_search", t, n, c, d_noise)) return 1;
     if (!d_root_hidden || !d_out_visits || !d_out_probs) return fail("cumind_search: NULL device pointer");
     FusedPlan pl;
@@ -802,6 +820,7 @@ extern "C" int cumind_search(cumind_tree* t, const cumind_net* n, const float* d
             tp.p.out_visits = d_out_visits;
             tp.p.out_probs = d_out_probs;
             tp.p.out_root_value = d_out_root_value;
+            tp.p.pdl = pdl ? 1 : 0;
             CM_CUDA(launch_search_team(tp.G, tp.p, tp.grid, tp.block, tp.smem, (cudaStream_t)stream));
             g_launches += 1;
             return 0;
@@ -814,9 +833,29 @@ extern "C" int cumind_search(cumind_tree* t, const cumind_net* n, const float* d
     pl.p.out_visits = d_out_visits;
     pl.p.out_probs = d_out_probs;
     pl.p.out_root_value = d_out_root_value;
+    pl.p.pdl = pdl ? 1 : 0;
     CM_CUDA(launch_search_fused(pl.G, pl.R, pl.p, pl.grid, pl.block, pl.smem, (cudaStream_t)stream));
     g_launches += 1;
     return 0;
+}
+
+extern "C" int cumind_search(cumind_tree* t, const cumind_net* n, const float* d_root_hidden, const cumind_search_cfg* c,
+                             const double* d_noise, int32_t* d_out_visits, double* d_out_probs, double* d_out_root_value,
+                             void* stream) {
+    return search_impl(t, n, d_root_hidden, c, d_noise, d_out_visits, d_out_probs, d_out_root_value, stream, false);
+}
+
+// Agent.select_action for a batch with every buffer on the device (agent.py:73-79: encode -> search is one call in
+// the reference too): initial_inference (representation network only) and the search are issued back to back from
+// here, so no host work sits between the two launches, and for vector observations the search kernel is a
+// programmatic dependent launch whose parameter staging overlaps the encoder.
+extern "C" int cumind_search_from_obs(cumind_tree* t, const cumind_net* n, const float* d_obs, const cumind_search_cfg* c,
+                                      const double* d_noise, float* d_hidden_work, int32_t* d_out_visits, double* d_out_probs,
+                                      double* d_out_root_value, void* stream) {
+    if (!t || !n || !c || !d_obs || !d_hidden_work) return fail("cumind_search_from_obs: NULL argument");
+    int rc = cumind_initial_inference(n, d_obs, t->tv.B, d_hidden_work, nullptr, nullptr, c->net_mode, stream);
+    if (rc) return rc;
+    return search_impl(t, n, d_hidden_work, c, d_noise, d_out_visits, d_out_probs, d_out_root_value, stream, n->desc.obs_ndim == 1);
 }
 
 // introspection for tests / bench: the launch configuration cumind_search would use
@@ -1080,7 +1119,7 @@ extern "C" int cumind_select_actions_host(cumind_tree* t, const cumind_net* n, c
     }
     int rc = cumind_initial_inference(n, d_obs, B, d_hidden, nullptr, nullptr, c->net_mode, stream);
     if (rc) return rc;
-    rc = cumind_search(t, n, d_hidden, c, with_noise ? d_noise : nullptr, d_visits, d_probs, nullptr, stream);
+    rc = search_impl(t, n, d_hidden, c, with_noise ? d_noise : nullptr, d_visits, d_probs, nullptr, stream, n->desc.obs_ndim == 1);
     if (rc) return rc;
     if (zero_copy) {
         CM_CUDA(launch_stage_out(d_probs, B, A_cfg, d_actions, (int32_t*)m_actions, (double*)m_probs, st));

@@ -269,6 +269,13 @@ CM_DEVICE float2 ffma2v(float2 a, float2 b, float2 c) {
 }
 CM_DEVICE float frelu(float v) { return v > 0.0f ? v : 0.0f; }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// may start while the previous kernel of the stream is still running; pdl_wait() blocks until that kernel has
+// completed and its writes are visible (a no-op for a normal launch), pdl_launch_dependents() lets the next
+// kernel of the stream start its prologue early.
+CM_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+CM_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // exp(d), d <= 0, float64, mul/add only — the same operation sequence as cmo_pexp (oracle) so the
 // fp32-rounded result is bit-identical on CPU and GPU.
 CM_DEVICE double pexp(double d) {

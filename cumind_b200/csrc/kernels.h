@@ -22,7 +22,27 @@ struct FusedParams {
     // shared-memory carve-up (bytes)
     unsigned off_sqrt, off_recip, off_slots, slot_bytes, off_bar;
     int n_sqrt;
+    int pdl;                   // host only: launch with programmatic stream serialization (root_hidden comes from the previous kernel)
 };
+
+#ifdef __CUDACC__
+// <<<grid, block, smem, st>>> with an optional programmatic-dependent-launch attribute: the kernel may start while
+// the previous kernel of the stream drains and must call pdl_wait() before it reads that kernel's output.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
 
 // search_fused.cu
 cudaError_t launch_search_fused(int G, int R, const FusedParams& p, int grid, int block, size_t smem, cudaStream_t st);
@@ -50,6 +70,7 @@ struct TeamParams {
     unsigned off_sqrt, off_recip, off_teams, team_bytes, off_bar, off_path, off_nxt, off_hotw, off_hot;
     int n_sqrt;
     long long* clk;            // [grid][16] phase clocks (diagnostic) or nullptr
+    int pdl;                   // host only: launch with programmatic stream serialization
 };
 bool team_variant_ok(int G, int TT);
 cudaError_t launch_search_team(int G, const TeamParams& p, int grid, int block, size_t smem, cudaStream_t st);

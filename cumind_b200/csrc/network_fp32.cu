@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(256) vector_encoder_tile_kernel(const float* _
     float* w_s = sm;                                           // encoder parameters
     const int M = D > H ? D : H;
     float* xbuf = sm + ((n_enc + 3) & ~3) + (size_t)(threadIdx.x >> 5) * 2 * M * TW;
+    pdl_launch_dependents();  // the search kernel behind this one may stage its parameters meanwhile
     for (int i = threadIdx.x; i < n_enc; i += blockDim.x) w_s[i] = enc[i];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(kWarps * 32) vector_encoder_kernel(const float
     const int M = D > H ? D : H;
     float* a = sm + (size_t)w * 2 * M;
     float* c = a + M;
+    pdl_launch_dependents();
     const int r = blockIdx.x * kWarps + w;
     const bool active = r < B;
     if (active)

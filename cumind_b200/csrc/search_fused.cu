@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(512, 1) search_fused_kernel(const FusedParams 
     }
     mbar_wait(bar, 0);
     __syncthreads();
+    pdl_wait();  // root_hidden (and the noise) may come from the previous kernel of the stream
 
     const float* emb_s = w_s + p.pk.emb;
     const float* wh_s = w_s + p.pk.heads_w;
@@ -249,8 +250,7 @@ template <int GS, int R>
 static cudaError_t launch_one(const FusedParams& p, int grid, int block, size_t smem, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(search_fused_kernel<GS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    search_fused_kernel<GS, R><<<grid, block, smem, st>>>(p);
-    return cudaGetLastError();
+    return launch_kernel_pdl(search_fused_kernel<GS, R>, grid, block, smem, st, p.pdl != 0, p);
 }
 
 template <int GS>

@@ -207,6 +207,35 @@ class MCTS:
             return probs, visits
         return probs.cpu().numpy(), visits.cpu().numpy()
 
+    def search_from_obs(self, observations: torch.Tensor, noise: Optional[torch.Tensor] = None, philox_seed: Optional[int] = None,
+                        tree_index_base: int = 0):
+        """encode -> search (agent.py:73-79) for B device-resident observations through ONE C call
+        (cumind_search_from_obs): both kernels are issued back to back from C, the search as a programmatic
+        dependent launch behind the encoder.  `observations` [B,*obs] float32 and `noise` [B,A] float64 are CUDA
+        tensors; returns device tensors (probs [B,A_cfg] float64, visits [B,A_cfg] int32).  Output and work
+        buffers are kept per batch size, so repeated calls allocate nothing."""
+        net = self.network
+        B = int(observations.shape[0])
+        A_cfg = int(self.config.action_space_size)
+        A = min(A_cfg, net.action_space_size)
+        tree = self._tree(B, int(self.config.num_simulations), A)
+        buf = getattr(self, "_obs_buffers", None)
+        if buf is None or buf[0].shape[0] != B or buf[1].shape[1] != A_cfg:
+            net.reserve(B)
+            buf = (torch.empty((B, net.hidden_dim), dtype=torch.float32, device=net.device),
+                   torch.empty((B, A_cfg), dtype=torch.int32, device=net.device),
+                   torch.empty((B, A_cfg), dtype=torch.float64, device=net.device),
+                   torch.empty((B,), dtype=torch.float64, device=net.device))
+            self._obs_buffers = buf
+        hidden, visits, probs, root_value = buf
+        mode = 1 if noise is not None else (2 if philox_seed is not None else 0)
+        cfg = self._cfg(mode, philox_seed or 0, tree_index_base)
+        self.last_cfg = cfg
+        _native.check(self._lib.cumind_search_from_obs(tree.handle, net._handle, _ptr(observations), C.byref(cfg), _ptr(noise),
+                                                       _ptr(hidden), _ptr(visits), _ptr(probs), _ptr(root_value), _stream_ptr()))
+        self.last_root_value = root_value
+        return probs, visits
+
     def plan(self, B: int) -> Dict[str, int]:
         """Launch configuration cumind_search would use for B trees with the current config."""
         A = min(int(self.config.action_space_size), self.network.action_space_size)

@@ -113,6 +113,16 @@ class CuMindNetwork:
                                                       C.byref(self._handle)))
         self.params = P.unflatten(blob, *self._dims)
         self._blob = blob
+        self._reserved = 0
+
+    def reserve(self, max_batch: int) -> None:
+        """Size the image encoder's activation workspace for batches of up to `max_batch` observations
+        (cumind_net_reserve: allocates and synchronises — the inference entry points never do).  Called on demand
+        by the wrappers below when a larger batch shows up; call it up front before capturing a CUDA graph."""
+        if len(self.observation_shape) == 3 and int(max_batch) > self._reserved:
+            with torch.cuda.device(self.device):
+                _native.check(self._lib.cumind_net_reserve(self._handle, int(max_batch)))
+            self._reserved = int(max_batch)
 
     def _refresh_host(self) -> None:
         """After a device-side optimiser step the host copy is stale: pull it back on demand."""
@@ -168,6 +178,7 @@ class CuMindNetwork:
     def _initial(self, observation, want_heads: bool):
         obs = self._as_device(observation, self.observation_shape)
         B = obs.shape[0]
+        self.reserve(B)
         hidden = torch.empty((B, self.hidden_dim), dtype=torch.float32, device=self.device)
         logits = torch.empty((B, self.action_space_size), dtype=torch.float32, device=self.device) if want_heads else None
         value = torch.empty((B,), dtype=torch.float32, device=self.device) if want_heads else None

@@ -117,6 +117,11 @@ int cumind_net_create(const cumind_net_desc* desc, const float* h_params, size_t
                       cumind_net** out);
 int cumind_net_update_params(cumind_net* net, const float* h_params, size_t n_params, void* stream);
 int cumind_net_destroy(cumind_net* net);
+/* Image encoders keep their layer activations in a device workspace owned by `net`.  cumind_net_reserve sizes it
+ * for batches of up to max_batch observations (both arithmetic modes); call it once after cumind_net_create —
+ * it allocates and synchronises the device.  cumind_initial_inference never allocates: it fails with an error
+ * that names this function when the reserved workspace is too small.  Vector-observation networks need none. */
+int cumind_net_reserve(cumind_net* net, int32_t max_batch);
 
 /* CuMindNetwork.initial_inference (network.py:288-300).
  * d_obs [B, *obs_shape] fp32 -> d_hidden [B,H], d_logits [B,A] (may be NULL), d_value [B] (may be NULL). */
@@ -189,6 +194,16 @@ int cumind_search(cumind_tree* tree, const cumind_net* net, const float* d_root_
                   const cumind_search_cfg* cfg, const double* d_noise,
                   int32_t* d_out_visits, double* d_out_probs, double* d_out_root_value,
                   void* stream);
+
+/* Agent.select_action for a batch with every buffer already on the device (agent.py:73-79: the reference encodes
+ * and searches in one call too): initial_inference (representation network, network.py:288-300) into the caller's
+ * d_hidden_work [B,H], then cumind_search on it, both issued from this one call so no host work separates the
+ * launches; for vector observations the search is a programmatic dependent launch whose parameter staging
+ * overlaps the encoder.  Other arguments as cumind_search. */
+int cumind_search_from_obs(cumind_tree* tree, const cumind_net* net, const float* d_obs,
+                           const cumind_search_cfg* cfg, const double* d_noise, float* d_hidden_work,
+                           int32_t* d_out_visits, double* d_out_probs, double* d_out_root_value,
+                           void* stream);
 
 /* The launch configuration cumind_search would use: out = {schedule (0 = stepwise fallback,
  * CUMIND_SCHED_WARP, CUMIND_SCHED_TEAM), lanes per tree G, WARP: outputs per lane R / TEAM: trees

@@ -1,0 +1,226 @@
+// layer_bench.cu — cycles per 64x64 dynamics layer for 16 trees on one SM, by layer design (sm_100a).
+//   V0  lane tile 4 trees x 2 neurons, W and x from shared memory, scalar FFMA      (round-1 team_layer)
+//   V1  the same with FFMA2 (x scalar operand, weight pair)
+//   V2  weights in registers: lane = one neuron (64 registers per layer), x k-major, broadcast LDS.128 of 4 trees,
+//       FFMA2 = w (scalar) x {x_t, x_t+1}; 4 warps = 2 neuron halves x 2 tree halves
+//   V3  weights in registers: lane = neuron pair (64 register pairs per layer), x row-major [t][k], broadcast
+//       LDS.128 of 4 k of one tree, FFMA2 = x (scalar) x {w_j, w_j+1}; 2 warps x 8 trees
+// `groups` = how many independent 4-warp groups run the loop at the same time on the SM (teams).
+#include <cstdio>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ float2 ffma2(float x, float2 w, float2 acc) {
+    unsigned long long xx, ww, aa, dd;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ww) : "f"(w.x), "f"(w.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "f"(acc.x), "f"(acc.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(dd) : "l"(xx), "l"(ww), "l"(aa));
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(dd));
+    return r;
+}
+__device__ __forceinline__ void bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+constexpr int H = 64, TT = 16, XS = TT + 4, RS = H + 4;
+
+// V0 / V1: smem W [k][64], x [k][XS]
+template <bool F2>
+__device__ void layer_smem(const float* W, const float* b, const float* xin, float* xout, int lane, int warp) {
+    const int q = lane / 8, np = lane & 7;
+    const int j0 = warp * 16 + 2 * np;
+    float acc[2][4] = {};
+    const float* x = xin + 4 * q;
+    const float* w = W + j0;
+#pragma unroll 8
+    for (int k = 0; k < H; ++k) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + k * XS);
+        const float2 wv = *reinterpret_cast<const float2*>(w + k * H);
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+        if constexpr (F2) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float2 r = ffma2(xs[t], wv, make_float2(acc[0][t], acc[1][t]));
+                acc[0][t] = r.x; acc[1][t] = r.y;
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                acc[0][t] = __fmaf_rn(xs[t], wv.x, acc[0][t]);
+                acc[1][t] = __fmaf_rn(xs[t], wv.y, acc[1][t]);
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+        const float4 r = *reinterpret_cast<const float4*>(xin + (j0 + v) * XS + 4 * q);
+        const float bb = b[j0 + v];
+        float4 y;
+        y.x = fmaxf(acc[v][0] + bb, 0.f) + r.x; y.y = fmaxf(acc[v][1] + bb, 0.f) + r.y;
+        y.z = fmaxf(acc[v][2] + bb, 0.f) + r.z; y.w = fmaxf(acc[v][3] + bb, 0.f) + r.w;
+        *reinterpret_cast<float4*>(xout + (j0 + v) * XS + 4 * q) = y;
+    }
+}
+
+// V2: w[64] registers (lane = neuron j), x k-major broadcast, trees 8*th .. 8*th+7
+__device__ __forceinline__ void layer_wreg1(const float (&w)[H], float bb, const float* xin, float* xout, int j, int th) {
+    float2 acc[4] = {};
+    const float* x = xin + 8 * th;
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(x + k * XS);
+        const float4 c = *reinterpret_cast<const float4*>(x + k * XS + 4);
+        acc[0] = ffma2(w[k], make_float2(a.x, a.y), acc[0]);
+        acc[1] = ffma2(w[k], make_float2(a.z, a.w), acc[1]);
+        acc[2] = ffma2(w[k], make_float2(c.x, c.y), acc[2]);
+        acc[3] = ffma2(w[k], make_float2(c.z, c.w), acc[3]);
+    }
+    const float4 r0 = *reinterpret_cast<const float4*>(xin + j * XS + 8 * th);
+    const float4 r1 = *reinterpret_cast<const float4*>(xin + j * XS + 8 * th + 4);
+    float4 y0, y1;
+    y0.x = fmaxf(acc[0].x + bb, 0.f) + r0.x; y0.y = fmaxf(acc[0].y + bb, 0.f) + r0.y;
+    y0.z = fmaxf(acc[1].x + bb, 0.f) + r0.z; y0.w = fmaxf(acc[1].y + bb, 0.f) + r0.w;
+    y1.x = fmaxf(acc[2].x + bb, 0.f) + r1.x; y1.y = fmaxf(acc[2].y + bb, 0.f) + r1.y;
+    y1.z = fmaxf(acc[3].x + bb, 0.f) + r1.z; y1.w = fmaxf(acc[3].y + bb, 0.f) + r1.w;
+    *reinterpret_cast<float4*>(xout + j * XS + 8 * th) = y0;
+    *reinterpret_cast<float4*>(xout + j * XS + 8 * th + 4) = y1;
+}
+
+// V3: w2[64] register pairs (lane = neurons 2*lane, 2*lane+1), x row-major [t][RS] broadcast, NT trees from t0
+template <int NT>
+__device__ __forceinline__ void layer_wreg2(const float2 (&w)[H], float2 bb, const float* xin, float* xout, int lane, int t0) {
+    float2 acc[NT] = {};
+#pragma unroll
+    for (int k = 0; k < H; k += 4) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const float4 a = *reinterpret_cast<const float4*>(xin + (t0 + t) * RS + k);
+            acc[t] = ffma2(a.x, w[k], acc[t]);
+            acc[t] = ffma2(a.y, w[k + 1], acc[t]);
+            acc[t] = ffma2(a.z, w[k + 2], acc[t]);
+            acc[t] = ffma2(a.w, w[k + 3], acc[t]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        const float2 r = *reinterpret_cast<const float2*>(xin + (t0 + t) * RS + 2 * lane);
+        float2 y;
+        y.x = fmaxf(acc[t].x + bb.x, 0.f) + r.x;
+        y.y = fmaxf(acc[t].y + bb.y, 0.f) + r.y;
+        *reinterpret_cast<float2*>(xout + (t0 + t) * RS + 2 * lane) = y;
+    }
+}
+
+template <int V>
+__global__ void __launch_bounds__(384, 1) k_layer(const float* Wg, long long* out, float* sink, int iters) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = warp / 4, wg = warp & 3;
+    float* W = sm;                        // [2][64][64] + bias [2][64]
+    float* xb = sm + 2 * H * H + 2 * H + grp * 3 * H * RS;  // three activation buffers per group
+    for (int i = tid; i < 2 * H * H + 2 * H; i += blockDim.x) W[i] = Wg[i];
+    for (int i = tid; i < (int)(blockDim.x / 128) * 3 * H * RS; i += blockDim.x) sm[2 * H * H + 2 * H + i] = 0.001f * (i % 97);
+    __syncthreads();
+    float* x0 = xb; float* x1 = xb + H * RS; float* x2 = xb + 2 * H * RS;
+    const float* b0 = W + 2 * H * H; const float* b1 = b0 + H;
+    long long t0c = 0, t1c = 0;
+    if constexpr (V == 0 || V == 1) {
+        t0c = clock64();
+        for (int it = 0; it < iters; ++it) {
+            layer_smem<V == 1>(W, b0, x0, x1, lane, wg);
+            bar(1 + grp, 128);
+            layer_smem<V == 1>(W + H * H, b1, x1, x2, lane, wg);
+            bar(1 + grp, 128);
+            float* t = x0; x0 = x2; x2 = t;
+        }
+        t1c = clock64();
+    } else if constexpr (V == 2) {
+        const int j = (wg & 1) * 32 + lane, th = wg >> 1;
+        float w0[H], w1[H];
+#pragma unroll
+        for (int k = 0; k < H; ++k) { w0[k] = W[k * H + j]; w1[k] = W[H * H + k * H + j]; }
+        const float bb0 = b0[j], bb1 = b1[j];
+        t0c = clock64();
+        for (int it = 0; it < iters; ++it) {
+            layer_wreg1(w0, bb0, x0, x1, j, th);
+            bar(1 + grp, 128);
+            layer_wreg1(w1, bb1, x1, x2, j, th);
+            bar(1 + grp, 128);
+            float* t = x0; x0 = x2; x2 = t;
+        }
+        t1c = clock64();
+    } else if constexpr (V == 3) {
+        // warps 0,1 of the group: layer 0 of trees 0-7 / 8-15; warps 2,3: layer 1 (pipelined over iterations)
+        const int layer = wg >> 1, t0 = (wg & 1) * 8;
+        float2 w2[H];
+#pragma unroll
+        for (int k = 0; k < H; ++k) w2[k] = *reinterpret_cast<const float2*>(W + layer * H * H + k * H + 2 * lane);
+        const float2 bb = *reinterpret_cast<const float2*>((layer ? b1 : b0) + 2 * lane);
+        t0c = clock64();
+        for (int it = 0; it < iters; ++it) {
+            if (layer == 0) {
+                layer_wreg2<8>(w2, bb, x0, x1, lane, t0);
+                bar(1 + grp, 128);   // x1 ready
+                bar(5 + grp, 128);   // x1 consumed
+            } else {
+                bar(1 + grp, 128);
+                layer_wreg2<8>(w2, bb, x1, x2, lane, t0);
+                bar(5 + grp, 128);
+            }
+        }
+        t1c = clock64();
+    } else if constexpr (V == 4) {
+        // V3 arithmetic, all 4 warps on the same layer (4 trees each), both layers' weights resident: 256 registers
+        // of weights do not fit, so the second layer's pairs are reloaded from shared memory once per layer call
+        const int t0 = wg * 4;
+        float2 w2[H];
+        t0c = clock64();
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < H; ++k) w2[k] = *reinterpret_cast<const float2*>(W + k * H + 2 * lane);
+            layer_wreg2<4>(w2, *reinterpret_cast<const float2*>(b0 + 2 * lane), x0, x1, lane, t0);
+            bar(1 + grp, 128);
+#pragma unroll
+            for (int k = 0; k < H; ++k) w2[k] = *reinterpret_cast<const float2*>(W + H * H + k * H + 2 * lane);
+            layer_wreg2<4>(w2, *reinterpret_cast<const float2*>(b1 + 2 * lane), x1, x2, lane, t0);
+            bar(1 + grp, 128);
+            float* t = x0; x0 = x2; x2 = t;
+        }
+        t1c = clock64();
+    }
+    if (lane == 0 && wg == 0) out[blockIdx.x * 8 + grp] = t1c - t0c;
+    if (tid < 64) sink[blockIdx.x * 64 + tid] = x0[tid * 4] + x1[tid * 4] + x2[tid * 4];
+}
+
+template <int V>
+void run(const char* name, const float* Wg, long long* out, float* sink) {
+    const int iters = 200;
+    for (int groups : {1, 2, 3}) {
+        const size_t smem = (size_t)(2 * H * H + 2 * H + groups * 3 * H * RS) * 4;
+        cudaFuncSetAttribute(k_layer<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaMemset(out, 0, 148 * 8 * 8);
+        k_layer<V><<<148, 128 * groups, smem>>>(Wg, out, sink, iters);
+        cudaError_t e = cudaDeviceSynchronize();
+        long long h[148 * 8];
+        cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+        double s = 0;
+        for (int b = 0; b < 148; ++b) for (int g = 0; g < groups; ++g) s += (double)h[b * 8 + g];
+        printf("%-64s groups=%d: %8.1f cycles per (2 layers x 16 trees) per group  [%s]\n", name, groups, s / (148.0 * groups * iters),
+               cudaGetErrorString(e));
+    }
+}
+
+int main() {
+    float* Wg; long long* out; float* sink;
+    cudaMalloc(&Wg, (2 * H * H + 2 * H) * 4);
+    cudaMalloc(&out, 148 * 8 * 8);
+    cudaMalloc(&sink, 148 * 64 * 4);
+    float hw[2 * H * H + 2 * H];
+    for (int i = 0; i < 2 * H * H + 2 * H; ++i) hw[i] = 0.01f * ((i * 37) % 19 - 9);
+    cudaMemcpy(Wg, hw, sizeof(hw), cudaMemcpyHostToDevice);
+    run<0>("V0 smem W, 4x2 tile, scalar FFMA (round 1)", Wg, out, sink);
+    run<1>("V1 smem W, 4x2 tile, FFMA2", Wg, out, sink);
+    run<2>("V2 reg W (lane = neuron), x k-major broadcast, FFMA2 over tree pairs", Wg, out, sink);
+    run<3>("V3 reg W pairs, x row-major broadcast, 2 warps per layer, pipelined", Wg, out, sink);
+    run<4>("V4 reg W pairs reloaded per layer, 4 warps per layer", Wg, out, sink);
+    return 0;
+}
