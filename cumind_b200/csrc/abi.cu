@@ -687,24 +687,32 @@ static int plan_team(const cumind_tree* t, const cumind_net* n, const cumind_sea
     if (nmw > 8) nmw = 8;
     const int team_warps = ntw + nmw;
     const int XS = TT + 4;
+    // layer-warpgroup mode (search_team.cu, KR > 0): hidden_dim 64; warps 0-3 of the CTA run the dynamics layers of all teams
+    bool lw = team_lw_variant_ok(G, TT, H) && c->schedule != CUMIND_SCHED_TEAM_CLASSIC;
+    if (const char* e = getenv("CUMIND_TEAM_LW")) lw = lw && atoi(e) != 0;   // tuning only
+    const int lw_warps = lw ? 4 : 0;
+    const int RS = 68;
     const TeamPackLayout& pk = n->team_pk;
     const size_t pack_bytes = pk.total * sizeof(float);
     const int n_sqrt = 2 * S_max + 4;
     auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     const size_t off_sqrt = al16(pack_bytes);
     const size_t off_recip = al16(off_sqrt + (size_t)n_sqrt * sizeof(double));
-    const size_t off_teams = (off_recip + (size_t)n_sqrt * sizeof(double) + 127) & ~(size_t)127;
-    const size_t team_base = al16((size_t)(2 * H * XS + TT * (H + 4) + 3 * TT * pk.HP + 4 * TT) * 4);
+    const size_t off_wg = al16(off_recip + (size_t)n_sqrt * sizeof(double));
+    const size_t wg_bytes = lw ? (size_t)4 * 2 * (TT / 4) * RS * sizeof(float) : 0;
+    const size_t off_teams = (off_wg + wg_bytes + 127) & ~(size_t)127;
+    const size_t team_base = lw ? al16((size_t)(2 * TT * RS + 3 * TT * pk.HP + 4 * TT) * 4)
+                                : al16((size_t)(2 * H * XS + TT * (H + 4) + 3 * TT * pk.HP + 4 * TT) * 4);
     const size_t per_tree = (size_t)(S_max + 2) * sizeof(int) + (size_t)N * 44;  // path + selection cache + hot W + hot records
     const size_t kMax = 227 * 1024;
     if (off_teams + team_base + per_tree + 256 > kMax) { why = "one tree does not fit the team kernel's shared memory"; return 1; }
     int n_team = c->teams_per_cta > 0 ? c->teams_per_cta : (tps + TT - 1) / TT;
     if (n_team < 1) n_team = 1;
-    if (n_team > 7) n_team = 7;
-    // the automatic choice keeps the CTA at <= 512 threads (128 registers per thread)
-    const int max_threads = c->teams_per_cta > 0 ? 1024 : 512;
-    while (n_team > 1 && n_team * team_warps * 32 > max_threads) --n_team;
-    if (n_team * team_warps * 32 > 1024) { why = "team does not fit a CTA"; return 1; }
+    if (n_team > (lw ? 3 : 7)) n_team = lw ? 3 : 7;
+    // the automatic choice keeps the CTA at <= 512 threads (128 registers per thread); with the layer warpgroup at <= 448
+    const int max_threads = lw ? (c->teams_per_cta > 0 ? 640 : 512) : (c->teams_per_cta > 0 ? 1024 : 512);
+    while (n_team > 1 && (lw_warps + n_team * team_warps) * 32 > max_threads) --n_team;
+    if ((lw_warps + n_team * team_warps) * 32 > (lw ? 640 : 1024)) { why = "team does not fit a CTA"; return 1; }
     // trees per batch: spread the SM's trees evenly over its teams, within TT and within shared memory
     int tpt = 0;
     for (;; --n_team) {
@@ -732,7 +740,7 @@ static int plan_team(const cumind_tree* t, const cumind_net* n, const cumind_sea
     if (grid > sm) grid = sm;
     pl.G = G;
     pl.grid = grid;
-    pl.block = n_team * team_warps * 32;
+    pl.block = (lw_warps + n_team * team_warps) * 32;
     pl.smem = total;
     TeamParams& p = pl.p;
     p.tv = t->tv;
@@ -761,6 +769,9 @@ static int plan_team(const cumind_tree* t, const cumind_net* n, const cumind_sea
     p.n_sqrt = n_sqrt;
     p.clk = nullptr;
     p.pdl = 0;
+    p.lw = 0;
+    if (lw) { const int th = pl.block; p.lw = th <= 256 ? 40 : (th <= 384 ? 28 : (th <= 512 ? 16 : 8)); }   // = the instantiation launch_lw picks
+    p.off_wg = (unsigned)off_wg;
     p.tile = 0;
     p.stagger = 0;
     if (const char* e = getenv("CUMIND_TEAM_TILE")) p.tile = atoi(e);        // tuning only
@@ -811,10 +822,10 @@ static int search_impl(cumind_tree* t, const cumind_net* n, const float* d_root_
     // one fused launch beats 3 launches per simulation through the tensor-core expansion kernel
     // (measured in profiles/README.md), and it is more accurate.  cumind_search_stepwise always
     // honours net_mode (tcgen05 expansion kernel in bf16 mode).
-    if (c->schedule < 0 || c->schedule > CUMIND_SCHED_TEAM) return fail("unknown schedule");
+    if (c->schedule < 0 || c->schedule > CUMIND_SCHED_TEAM_CLASSIC) return fail("unknown schedule");
     if (c->schedule != CUMIND_SCHED_WARP) {
         TeamPlan tp;
-        if (plan_team(t, n, c, tp, why) == 0 && (c->schedule == CUMIND_SCHED_TEAM || team_is_preferred(tp, n->sm_count))) {
+        if (plan_team(t, n, c, tp, why) == 0 && (c->schedule >= CUMIND_SCHED_TEAM || team_is_preferred(tp, n->sm_count))) {
             tp.p.root_hidden = d_root_hidden;
             tp.p.noise = d_noise;
             tp.p.out_visits = d_out_visits;
@@ -865,9 +876,9 @@ extern "C" int cumind_search_plan(const cumind_tree* t, const cumind_net* n, con
     for (int i = 0; i < 8; ++i) out[i] = 0;
     if (c->schedule != CUMIND_SCHED_WARP) {
         TeamPlan tp;
-        if (plan_team(t, n, c, tp, why) == 0 && (c->schedule == CUMIND_SCHED_TEAM || team_is_preferred(tp, n->sm_count))) {
+        if (plan_team(t, n, c, tp, why) == 0 && (c->schedule >= CUMIND_SCHED_TEAM || team_is_preferred(tp, n->sm_count))) {
             out[0] = CUMIND_SCHED_TEAM; out[1] = tp.G; out[2] = tp.p.tpt; out[3] = tp.grid; out[4] = tp.block;
-            out[5] = (int32_t)tp.smem; out[6] = tp.p.n_team; out[7] = tp.p.nmw;
+            out[5] = (int32_t)tp.smem; out[6] = tp.p.n_team; out[7] = tp.p.nmw + 256 * tp.p.lw;
             return 0;
         }
     }

@@ -168,10 +168,59 @@ CM_DEVICE void team_layer(const float* __restrict__ W, const float* __restrict__
     }
 }
 
+// ---- layer warpgroup (KR > 0, hidden_dim 64) ------------------------------------------------------
+// One dynamics layer for NT trees of ONE warp: lane = the neuron pair (2*lane, 2*lane+1), so a warp covers all 64
+// neurons of its trees and the layers of a tree never leave the warp.  The activations are row-major per tree
+// (row stride RS floats): x[t][k..k+3] is one broadcast LDS.128 for the whole warp and feeds four FFMA2
+// (x_k as the scalar operand, the weight pair {W[k][2l], W[k][2l+1]}, the accumulator pair).  The weight pairs of
+// k < KR stay in registers for the whole launch (wr), the others come from the k-major copy in shared memory
+// (one conflict-free LDS.64 per k).  Same sequential-k FMA chain per (tree, neuron) as team_layer.
+// hid != nullptr (last layer): also store the new hidden rows of the first n_valid trees (global, 256 B per row).
+template <int NT, int KR, int RS>
+CM_DEVICE void wg_layer(const float2 (&wr)[KR > 0 ? KR : 1], const float* __restrict__ Wl, float2 bias, const float* __restrict__ xin,
+                        float* __restrict__ xout, float* __restrict__ hid, size_t hstride, int n_valid, int lane) {
+    float2 acc[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc[t] = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int k4 = 0; k4 < 64; k4 += 4) {
+        float4 a[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) a[t] = *reinterpret_cast<const float4*>(xin + t * RS + k4);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const int k = k4 + kk;
+            float2 w;
+            if (k < KR) w = wr[k < KR ? k : 0];
+            else w = *reinterpret_cast<const float2*>(Wl + k * 64);
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const float xv = kk == 0 ? a[t].x : (kk == 1 ? a[t].y : (kk == 2 ? a[t].z : a[t].w));
+                acc[t] = ffma2(xv, w, acc[t]);
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        const float2 r = *reinterpret_cast<const float2*>(xin + t * RS + 2 * lane);
+        float2 y;
+        y.x = fadd(frelu(fadd(acc[t].x, bias.x)), r.x);
+        y.y = fadd(frelu(fadd(acc[t].y, bias.y)), r.y);
+        *reinterpret_cast<float2*>(xout + t * RS + 2 * lane) = y;
+        if (hid != nullptr && t < n_valid) *reinterpret_cast<float2*>(hid + (size_t)t * hstride) = y;
+    }
+}
+
 // G lanes per tree; TT tree slots per team; lane tile of the network warps = TQ trees x NV neurons;
 // HS = compile-time hidden size (64: H == Hp == 64, loops without branches) or 0 (any H % 4 == 0).
-template <int G, int TT, int TQ, int NV, int HS, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p) {
+// KR > 0: LAYER WARPGROUP mode (hidden_dim 64 only).  Warps 0-3 of the CTA do nothing but the dynamics layers, for
+// every team in turn, with the weight pairs of k < KR resident in their registers (wg_layer); the network warps of
+// a team gather the parent rows row-major, hand them over (named barriers X0R / X2R), and compute heads + backup as
+// before.  The layers then cost the shared-memory pipe half of what the register-tiled product of team_layer does
+// (no operand transposes, one broadcast LDS.128 per 4 k and tree), and one team's layers never run against the
+// other's.  KR = 0: the network warps compute the layers themselves (team_layer).
+template <int G, int TT, int TQ, int NV, int HS, int KR>
+CM_DEVICE void search_team_body(const TeamParams& p) {
     constexpr int TPW = 32 / G;       // trees per tree warp
     constexpr int XS = TT + 4;        // row stride of the activation tiles (floats)
     constexpr int Q = TT / TQ;        // tree groups across a network warp
@@ -188,9 +237,12 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
     const int lane = tid & 31, warp = tid >> 5;
     const int H = p.pk.H, L = p.pk.L, HP = p.pk.HP, A = p.tv.A, A_net = p.A_net;
     const int S_max = p.tv.S_max, N = p.tv.N;
+    constexpr int LWW = KR > 0 ? 4 : 0;   // warps of the layer warpgroup
+    constexpr int RS = 68;                // row stride of the row-major activation rows (KR > 0)
     const int team_warps = p.ntw + p.nmw;
-    const int team = warp / team_warps, wt = warp - team * team_warps;
-    const bool is_tree = wt < p.ntw;
+    const bool is_layerwg = KR > 0 && warp < LWW;
+    const int team = is_layerwg ? 0 : (warp - LWW) / team_warps, wt = is_layerwg ? 0 : (warp - LWW) - team * team_warps;
+    const bool is_tree = !is_layerwg && wt < p.ntw;
 
     // ---- stage parameters (TMA bulk) + sqrt / reciprocal tables ------------------------------------
     if (tid == 0) {
@@ -221,9 +273,10 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
 
     // team scratch: x0,x1 [H][XS] | xt [TT][H+4] | lg[2],eb [TT][HP] | sel [4][TT] | path [tpt][S_max+2] | nxt [tpt][N] | hot W [tpt][N] | hot records [tpt][N]
     unsigned char* my = smem + p.off_teams + (size_t)team * p.team_bytes;
+    // KR > 0: x0 [TT][RS] (gathered rows, row-major) | xt [TT][RS] (rows after the last layer) | lg ...
     float* x0 = reinterpret_cast<float*>(my);
-    float* x1 = x0 + (size_t)H * XS;
-    float* xt = x1 + (size_t)H * XS;
+    float* x1 = KR > 0 ? x0 : x0 + (size_t)H * XS;
+    float* xt = KR > 0 ? x0 + (size_t)TT * RS : x1 + (size_t)H * XS;
     float* lg_t = xt + (size_t)TT * (H + 4);              // logits + value of simulation s in buffer s & 1 (the root's in buffer 1)
     float* eb_t = lg_t + 2 * TT * HP;
     int* sel = reinterpret_cast<int*>(eb_t + TT * HP);   // [3][TT] parent_e, action, path length
@@ -233,6 +286,9 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
     HotSel* hs_t = reinterpret_cast<HotSel*>(my + p.off_hot);
     const int bar_team = 1 + team, bar_mlp = 1 + p.n_team + team;
     const int cnt_team = team_warps * 32, cnt_mlp = p.nmw * 32;
+    // layer warpgroup hand-over: X0R = "the gathered rows of team i are in x0" (network warps arrive, layer warps wait),
+    // X2R = "the new hidden rows of team i are in xt" (layer warps arrive, network warps wait)
+    const int cnt_x = p.nmw * 32 + LWW * 32;
     const size_t hstride = (size_t)(S_max + 1) * H;
     const bool clk_on = p.clk != nullptr && team == 0 && lane == 0 && (wt == 0 || wt == p.ntw);
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, tmark = 0;
@@ -255,6 +311,63 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
     if (p.stagger > 0 && team > 0) {
         const long long t_go = clock64() + (long long)team * p.stagger;
         while (clock64() < t_go) {}
+    }
+    if constexpr (KR > 0) {
+        if (is_layerwg) {
+            constexpr int NT = TT / 4;            // tree slots per layer warp
+            const int ts0 = warp * NT;
+            float2 wr0[KR], wr1[KR];
+            const float* W0 = w_s + p.pk.layer_w(0) + 2 * lane;
+            const float* W1 = w_s + p.pk.layer_w(L > 1 ? 1 : 0) + 2 * lane;
+#pragma unroll
+            for (int k = 0; k < KR; ++k) {
+                wr0[k] = *reinterpret_cast<const float2*>(W0 + k * 64);
+                wr1[k] = *reinterpret_cast<const float2*>(W1 + k * 64);
+            }
+            float* xa = reinterpret_cast<float*>(smem + p.off_wg) + (size_t)warp * 2 * NT * RS;   // per-warp ping-pong rows (L > 2)
+            float* xb = xa + NT * RS;
+            const int team_stride = gridDim.x * p.n_team;
+            const bool wclk = p.clk != nullptr && warp == 0 && lane == 0;
+            long long lc0 = 0, lc1 = 0;
+            for (int first = blockIdx.x * p.n_team; first < p.n_batches; first += team_stride) {
+                for (int s = 0; s < p.S; ++s) {
+                    for (int tm = 0; tm < p.n_team; ++tm) {
+                        const int batch = first + tm;
+                        if (batch >= p.n_batches) break;
+                        const int t_begin = batch * p.tpt;
+                        const int n_here = (p.tv.B - t_begin) < p.tpt ? (p.tv.B - t_begin) : p.tpt;
+                        unsigned char* tsc = smem + p.off_teams + (size_t)tm * p.team_bytes;
+                        const float* x0t = reinterpret_cast<const float*>(tsc) + ts0 * RS;
+                        float* x2t = reinterpret_cast<float*>(tsc) + (size_t)TT * RS + ts0 * RS;
+                        float* hid = p.tv.hidden + ((size_t)(t_begin + ts0) * (S_max + 1) + (size_t)(s + 1)) * H + 2 * lane;
+                        const long long tw0 = wclk ? clock64() : 0;
+                        named_bar_sync(1 + 2 * p.n_team + tm, cnt_x);   // X0R
+                        const long long tw1 = wclk ? clock64() : 0;
+                        const float* in = x0t;
+                        for (int l = 0; l < L; ++l) {
+                            const bool last = l == L - 1;
+                            float* out = last ? x2t : ((l & 1) ? xb : xa);
+                            const float2 bias = *reinterpret_cast<const float2*>(w_s + p.pk.layer_b(l) + 2 * lane);
+                            float* h = last ? hid : nullptr;
+                            const int nv = n_here - ts0;
+                            if (l == 0) wg_layer<NT, KR, RS>(wr0, W0, bias, in, out, h, (size_t)(S_max + 1) * H, nv, lane);
+                            else if (l == 1) wg_layer<NT, KR, RS>(wr1, W1, bias, in, out, h, (size_t)(S_max + 1) * H, nv, lane);
+                            else {
+                                const float2 none[1] = {make_float2(0.f, 0.f)};
+                                wg_layer<NT, 0, RS>(none, w_s + p.pk.layer_w(l) + 2 * lane, bias, in, out, h, (size_t)(S_max + 1) * H, nv, lane);
+                            }
+                            __syncwarp();
+                            in = out;
+                        }
+                        __syncwarp();
+                        asm volatile("bar.arrive %0, %1;" ::"r"(1 + 3 * p.n_team + tm), "r"(cnt_x) : "memory");   // X2R
+                        if (wclk) { const long long tw2 = clock64(); lc0 += tw1 - tw0; lc1 += tw2 - tw1; }
+                    }
+                }
+            }
+            if (wclk) { p.clk[(size_t)blockIdx.x * 16 + 7] = lc0; p.clk[(size_t)blockIdx.x * 16 + 15] = lc1; }
+            return;
+        }
     }
     // (leaf - 1) / A by multiplication: exact for leaf - 1 < 2^32 / A
     const unsigned magic_A = A > 1 ? (unsigned)((0x100000000ULL + (unsigned)A - 1u) / (unsigned)A) : 0u;
@@ -439,6 +552,45 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
                 float* lg_s = lg_t + (s & 1) * TT * HP;
                 named_bar_sync(bar_team, cnt_team);  // (A) selection published
                 CM_CLK(c3, sel[0])
+                if constexpr (KR > 0) {
+                    // gather, row-major: x0[ts][j] = hidden[ts][parent_e][j] + Emb[action][j]   (network.py:229-230); 16 lanes
+                    // per row, every load and store 16 bytes and conflict-free; all loads of a lane in flight together
+                    constexpr int PER = (TT * 16 + 127) / 128;   // items per lane with four network warps
+                    float4 hv[PER], ev[PER];
+#pragma unroll
+                    for (int u = 0; u < PER; ++u) {
+                        const int i = mlane + u * nml;
+                        const int ts = i >> 4, c = i & 15;
+                        hv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        ev[u] = hv[u];
+                        if (i < TT * 16 && ts < n_here) {
+                            const int pe = sel[ts], ac = sel[TT + ts];
+                            hv[u] = *reinterpret_cast<const float4*>(hid0 + (size_t)ts * hstride + (size_t)pe * H + 4 * c);
+                            ev[u] = *reinterpret_cast<const float4*>(emb_s + (size_t)ac * H + 4 * c);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < PER; ++u) {
+                        const int i = mlane + u * nml;
+                        if (i < TT * 16)
+                            *reinterpret_cast<float4*>(x0 + (size_t)(i >> 4) * RS + 4 * (i & 15)) =
+                                make_float4(fadd(hv[u].x, ev[u].x), fadd(hv[u].y, ev[u].y), fadd(hv[u].z, ev[u].z), fadd(hv[u].w, ev[u].w));
+                    }
+                    for (int i = mlane + PER * nml; i < TT * 16; i += nml) {   // fewer than four network warps
+                        const int ts = i >> 4, c = i & 15;
+                        float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f), e4 = h4;
+                        if (ts < n_here) {
+                            h4 = *reinterpret_cast<const float4*>(hid0 + (size_t)ts * hstride + (size_t)sel[ts] * H + 4 * c);
+                            e4 = *reinterpret_cast<const float4*>(emb_s + (size_t)sel[TT + ts] * H + 4 * c);
+                        }
+                        *reinterpret_cast<float4*>(x0 + (size_t)ts * RS + 4 * c) = make_float4(fadd(h4.x, e4.x), fadd(h4.y, e4.y), fadd(h4.z, e4.z), fadd(h4.w, e4.w));
+                    }
+                    __syncwarp();
+                    asm volatile("bar.arrive %0, %1;" ::"r"(1 + 2 * p.n_team + team), "r"(cnt_x) : "memory");   // X0R: rows handed to the layer warpgroup
+                    CM_CLK(c0, __float_as_int(x0[0]))
+                    named_bar_sync(1 + 3 * p.n_team + team, cnt_x);                                            // X2R: new hidden rows in xt
+                    CM_CLK(c4, __float_as_int(xt[0]))
+                } else {
                 // gather: x0[j][ts] = hidden[ts][parent_e][j] + Emb[action][j]   (network.py:229-230).
                 // Two items per lane and pass with both global loads in flight before either is used (the
                 // parent rows come from L2); consecutive lanes read consecutive 16-byte chunks of a row (the transposed stores
@@ -491,6 +643,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
                     named_bar_sync(bar_mlp, cnt_mlp);
                     float* tmp = cur; cur = nxt; nxt = tmp;
                 }
+                }
                 CM_CLK(c1, __float_as_int(xt[0]))
                 team_heads<HS>(wht_s, bh_s, xt, H, HP, TT, A_net + 1, lg_s, mlane, nml);
                 named_bar_sync(bar_mlp, cnt_mlp);  // logits + value visible to every network warp
@@ -508,9 +661,28 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
     }
 }
 
+template <int G, int TT, int TQ, int NV, int HS, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p) {
+    search_team_body<G, TT, TQ, NV, HS, 0>(p);
+}
+// Layer-warpgroup variants: the register budget is stated directly (ptxas derives it from __launch_bounds__ with the
+// thread count rounded up to whole warpgroups, which would give a 14-warp CTA 128 registers instead of 144).
+template <int G, int TT, int TQ, int NV, int HS, int NREG, int KR>
+__global__ void __maxnreg__(NREG) search_team_lw_kernel(const TeamParams p) {
+    search_team_body<G, TT, TQ, NV, HS, KR>(p);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host-side launch: the instantiations that exist (team_variant_ok) and the dispatch over them
 // ------------------------------------------------------------------------------------------------
+template <int G, int TT, int TQ, int NV, int HS, int NREG, int KR>
+static cudaError_t launch_one_lw(const TeamParams& p, int grid, int block, size_t smem, cudaStream_t st) {
+    auto k = search_team_lw_kernel<G, TT, TQ, NV, HS, NREG, KR>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return launch_kernel_pdl(k, grid, block, smem, st, p.pdl != 0, p);
+}
+
 template <int G, int TT, int TQ, int NV, int HS, int MAXT>
 static cudaError_t launch_one(const TeamParams& p, int grid, int block, size_t smem, cudaStream_t st) {
     auto k = search_team_kernel<G, TT, TQ, NV, HS, MAXT>;
@@ -530,6 +702,22 @@ static cudaError_t launch_t(const TeamParams& p, int grid, int block, size_t sme
     return big ? launch_one<G, TT, TQ, NV, 0, 1024>(p, grid, block, smem, st) : launch_one<G, TT, TQ, NV, 0, 512>(p, grid, block, smem, st);
 }
 
+// layer-warpgroup instantiations: hidden_dim 64, G in {2,4,8}; register-resident k per block size (KR)
+bool team_lw_variant_ok(int G, int TT, int H) { return H == 64 && (TT == 8 || TT == 16) && (G == 2 || G == 4 || G == 8); }
+
+template <int G, int TT>
+static cudaError_t launch_lw(const TeamParams& p, int grid, int block, size_t smem, cudaStream_t st) {
+    constexpr int TQ = TT == 16 ? 4 : 2;
+    // The register file is 16 384 registers per SM sub-partition and warps are dealt round-robin to the four of them:
+    // registers per thread = 16384 / (32 * ceil(warps / 4)), rounded down to a multiple of 8.  The resident k (KR) is
+    // what that budget leaves after the accumulators, the x rows in flight and the backup arithmetic.
+    if (block <= 256) return launch_one_lw<G, TT, TQ, 2, 64, 224, 40>(p, grid, block, smem, st);   // e.g. one team, 3 network warps
+    if (block <= 384) return launch_one_lw<G, TT, TQ, 2, 64, 168, 28>(p, grid, block, smem, st);   // one team, or two teams with 3 network warps
+    if (block <= 512) return launch_one_lw<G, TT, TQ, 2, 64, 128, 16>(p, grid, block, smem, st);   // two teams
+    if (block <= 640) return launch_one_lw<G, TT, TQ, 2, 64, 96, 8>(p, grid, block, smem, st);     // three teams
+    return cudaErrorInvalidValue;
+}
+
 bool team_variant_ok(int G, int TT) {
     if (TT == 16) return G == 2 || G == 4 || G == 8;
     if (TT == 8) return G == 2 || G == 4 || G == 8 || G == 16 || G == 32;
@@ -539,6 +727,23 @@ bool team_variant_ok(int G, int TT) {
 // p.tile: 0 = default (16: 4x2, 8: 2x2); tuning alternatives exist for G = 2, Hp = 64, <= 512 threads only
 cudaError_t launch_search_team(int G, const TeamParams& p, int grid, int block, size_t smem, cudaStream_t st) {
     if (!team_variant_ok(G, p.TT)) return cudaErrorInvalidValue;
+    if (p.lw > 0) {
+        if (!team_lw_variant_ok(G, p.TT, p.pk.H)) return cudaErrorInvalidValue;
+        if (p.TT == 16) {
+            switch (G) {
+                case 2: return launch_lw<2, 16>(p, grid, block, smem, st);
+                case 4: return launch_lw<4, 16>(p, grid, block, smem, st);
+                case 8: return launch_lw<8, 16>(p, grid, block, smem, st);
+            }
+        } else {
+            switch (G) {
+                case 2: return launch_lw<2, 8>(p, grid, block, smem, st);
+                case 4: return launch_lw<4, 8>(p, grid, block, smem, st);
+                case 8: return launch_lw<8, 8>(p, grid, block, smem, st);
+            }
+        }
+        return cudaErrorInvalidValue;
+    }
     if (p.tile != 0) {
         if (p.TT == 16 && p.tile == 2 && G == 2 && p.pk.H == 64 && block <= 640) return launch_one<2, 16, 2, 2, 64, 640>(p, grid, block, smem, st);
         if (p.TT == 16 && p.tile == 3 && G == 2 && p.pk.H == 64 && block <= 640) return launch_one<2, 16, 4, 1, 64, 640>(p, grid, block, smem, st);

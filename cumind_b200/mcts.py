@@ -247,7 +247,7 @@ class MCTS:
         plan = {"fused": 1 if v[0] else 0, "schedule": {0: "stepwise", 1: "warp", 2: "team"}[v[0]], "lanes_per_tree": v[1],
                 "grid": v[3], "block": v[4], "smem_bytes": v[5]}
         if v[0] == _native.SCHED_TEAM:
-            plan.update(trees_per_team=v[2], teams_per_cta=v[6], net_warps_per_team=v[7])
+            plan.update(trees_per_team=v[2], teams_per_cta=v[6], net_warps_per_team=v[7] % 256, layer_warpgroup_resident_k=v[7] // 256)
         else:
             plan.update(outputs_per_lane=v[2])
         return plan

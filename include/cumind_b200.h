@@ -96,10 +96,13 @@ typedef struct cumind_search_cfg {
 
 /* How cumind_search maps the work onto the GPU (all produce identical results):
  *   WARP  search_fused.cu: every group of `lanes_per_tree` lanes runs the whole search of one tree
- *   TEAM  search_team.cu : warp-specialised teams (tree-walk warps + network warps), see DESIGN.md */
+ *   TEAM  search_team.cu : warp-specialised teams (tree-walk warps + network warps); with
+ *         hidden_dim 64 the dynamics layers of all teams run on a dedicated layer warpgroup whose weights are
+ *         partly register-resident */
 #define CUMIND_SCHED_AUTO 0
 #define CUMIND_SCHED_WARP 1
 #define CUMIND_SCHED_TEAM 2
+#define CUMIND_SCHED_TEAM_CLASSIC 3 /* TEAM without the layer warpgroup (the network warps compute the layers) */
 
 typedef struct cumind_net  cumind_net;   /* opaque: packed parameters on one device  */
 typedef struct cumind_tree cumind_tree;  /* opaque: view over a caller-owned SoA slab */
@@ -208,7 +211,7 @@ int cumind_search_from_obs(cumind_tree* tree, const cumind_net* net, const float
 /* The launch configuration cumind_search would use: out = {schedule (0 = stepwise fallback,
  * CUMIND_SCHED_WARP, CUMIND_SCHED_TEAM), lanes per tree G, WARP: outputs per lane R / TEAM: trees
  * per team batch, grid, block, dynamic shared memory bytes, TEAM: teams per CTA, TEAM: network
- * warps per team}. */
+ * warps per team + 256 * (register-resident k of the layer warpgroup, 0 = none)}. */
 int cumind_search_plan(const cumind_tree* tree, const cumind_net* net, const cumind_search_cfg* cfg,
                        int32_t* out8);
 

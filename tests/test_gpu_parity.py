@@ -67,7 +67,7 @@ def test_network_bit_exact_vs_golden(case):
     assert hp.bits_equal(net.representation_network(d["obs"]).cpu().numpy(), d["h"])
 
 
-@pytest.mark.parametrize("path", ["team", "warp", "stepwise"])
+@pytest.mark.parametrize("path", ["team", "team_classic", "warp", "stepwise"])
 @pytest.mark.parametrize("case", SEARCH, ids=[c["id"] for c in SEARCH])
 def test_search_matches_reference_trees(case, path):
     from cumind_b200 import _native
@@ -77,7 +77,10 @@ def test_search_matches_reference_trees(case, path):
     net = _network(case["obs_shape"], case["A_net"], case["H"], case["L"], 32, d["params"])
     mcts = MCTS(net, _Cfg(case["S"], case["A_cfg"], case["c_puct"], case["alpha"], case["frac"]))
     mcts.stepwise = path == "stepwise"
-    mcts.schedule = {"team": _native.SCHED_TEAM, "warp": _native.SCHED_WARP, "stepwise": _native.SCHED_AUTO}[path]
+    if path == "team_classic" and case["H"] != 64:
+        pytest.skip("the layer warpgroup only exists for hidden_dim 64: 'team' already ran the classic kernel")
+    mcts.schedule = {"team": _native.SCHED_TEAM, "team_classic": _native.SCHED_TEAM_CLASSIC, "warp": _native.SCHED_WARP,
+                     "stepwise": _native.SCHED_AUTO}[path]
     noise = None if d["noise"] is None else d["noise"][None]
     probs, visits = mcts.search_batch(d["root_h"][None], noise=noise)
     A = min(case["A_net"], case["A_cfg"])
@@ -139,24 +142,30 @@ def _team_case(A, H, S, B):
 TEAM_GEOMETRIES = [(0, 0, 0, 0), (1, 4, 0, 0), (3, 2, 8, 0), (2, 1, 4, 0), (4, 3, 16, 0), (2, 8, 11, 0), (6, 4, 0, 0), (1, 2, 5, 32), (2, 4, 16, 4)]
 
 
+@pytest.mark.parametrize("classic", [False, True], ids=["layerwg", "classic"])
 @pytest.mark.parametrize("geom", TEAM_GEOMETRIES, ids=lambda g: "T%dM%dS%dG%d" % g)
-@pytest.mark.parametrize("shape", [(2, 64, 50), (4, 64, 50), (18, 32, 25), (3, 16, 30), (2, 128, 25), (5, 24, 20), (1, 32, 7)],
+@pytest.mark.parametrize("shape", [(2, 64, 50), (4, 64, 50), (18, 32, 25), (3, 16, 30), (2, 128, 25), (5, 24, 20), (1, 32, 7), (8, 64, 20)],
                          ids=lambda s: f"A{s[0]}H{s[1]}S{s[2]}")
-def test_team_search_vs_oracle_all_geometries(shape, geom):
-    """search_team.cu (tree warps + network warps) against the C oracle: every array of every tree, for
-    every team geometry the launch knobs can produce (ragged last batch: B is not a multiple of anything)."""
+def test_team_search_vs_oracle_all_geometries(shape, geom, classic):
+    """search_team.cu (tree warps + network warps; with hidden_dim 64 also the layer-warpgroup variant, which is what
+    SCHED_TEAM then selects) against the C oracle: every array of every tree, for every team geometry the launch
+    knobs can produce (ragged last batch: B is not a multiple of anything)."""
     from cumind_b200 import _native
     from cumind_b200.mcts import MCTS
 
     A, H, S = shape
+    if classic and H != 64:
+        pytest.skip("no layer warpgroup for this hidden_dim: SCHED_TEAM already is the classic kernel")
     B = 1237
     o, h, noise, blob = _team_case(A, H, S, B)
     net = _network((4,), A, H, 2, 32, blob)
     mcts = MCTS(net, _Cfg(S, A))
-    mcts.schedule = _native.SCHED_TEAM
+    mcts.schedule = _native.SCHED_TEAM_CLASSIC if classic else _native.SCHED_TEAM
     mcts.teams_per_cta, mcts.net_warps_per_team, mcts.trees_per_team, mcts.lanes_per_tree = geom
     plan = mcts.plan(B)
     assert plan["schedule"] == "team", plan
+    if H == 64 and geom[3] in (0, 4):
+        assert (plan["layer_warpgroup_resident_k"] > 0) == (not classic), plan
     probs, visits = mcts.search_batch(h, noise=noise)
     _assert_trees_equal(mcts, o, S, A)
     assert np.array_equal(visits, o["out_visits"]) and np.array_equal(probs, o["out_probs"])
