@@ -502,7 +502,7 @@ def phase_clocks(mcts, hidden, d_noise, tree_index_base, S):
     c = clk.cpu().numpy().astype(np.float64)
     names = ["tree.select", "tree.expand_children", "tree.wait_network_backup", "tree.root_and_final", "tree.softmax_priors", "tree.barrier_A",
              "net.gather", "net.layer_barriers", "net.heads", "net.wait_trees", "net.layer_compute", "net.backup_rescore",
-             "layerwg.wait_rows_both_teams", "layerwg.layers_both_teams"]
+             "layerwg.wait_rows_all_teams", "layerwg.layer0_all_teams"]
     cols = [0, 1, 2, 3, 5, 6, 8, 9, 10, 11, 12, 13, 7, 15]
     out = {"plan": plan, "cycles_per_simulation_mean": {n: float(c[:, k].mean()) / S for n, k in zip(names, cols)},
            "cycles_per_simulation_max": {n: float(c[:, k].max()) / S for n, k in zip(names, cols)}}

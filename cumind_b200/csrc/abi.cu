@@ -681,14 +681,19 @@ static int plan_team(const cumind_tree* t, const cumind_net* n, const cumind_sea
     const int tps = (B + sm - 1) / sm;  // trees per SM
     int TT = (G <= 8 && tps > 8) ? 16 : 8;
     if (c->trees_per_team > 0) TT = (c->trees_per_team > 8 && G <= 8) ? 16 : 8;
+    // layer-warpgroup mode prefers up to four small teams (8 tree slots each) over two large ones: the chain of one
+    // simulation is mostly latency, so more teams in flight overlap more of it and a team's layers are two short jobs
+    const bool lw_wanted = H == 64 && n->desc.num_blocks == 2 && c->schedule != CUMIND_SCHED_TEAM_CLASSIC && G <= 8;
+    if (lw_wanted && c->trees_per_team <= 0 && c->teams_per_cta <= 0 && tps <= 32 && G <= 4) TT = 8;
     if (!team_variant_ok(G, TT)) { why = "no team kernel for this lane mapping"; return 1; }
     const int ntw = (TT + TPW - 1) / TPW;
     int nmw = c->net_warps_per_team > 0 ? c->net_warps_per_team : 4;
     if (nmw > 8) nmw = 8;
-    const int team_warps = ntw + nmw;
+    int team_warps = ntw + nmw;
     const int XS = TT + 4;
-    // layer-warpgroup mode (search_team.cu, KR > 0): hidden_dim 64; warps 0-3 of the CTA run the dynamics layers of all teams
-    bool lw = team_lw_variant_ok(G, TT, H) && c->schedule != CUMIND_SCHED_TEAM_CLASSIC;
+    // layer-warpgroup mode (search_team.cu, KR > 0): hidden_dim 64, two dynamics layers; warps 0-3 of the CTA run the layers
+    // of all teams, the CTA consists of whole warpgroups and a team's warp count follows from the number of teams
+    bool lw = team_lw_variant_ok(G, TT, H) && n->desc.num_blocks == 2 && ntw <= 2 && c->schedule != CUMIND_SCHED_TEAM_CLASSIC;
     if (const char* e = getenv("CUMIND_TEAM_LW")) lw = lw && atoi(e) != 0;   // tuning only
     const int lw_warps = lw ? 4 : 0;
     const int RS = 68;
@@ -698,21 +703,22 @@ static int plan_team(const cumind_tree* t, const cumind_net* n, const cumind_sea
     auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     const size_t off_sqrt = al16(pack_bytes);
     const size_t off_recip = al16(off_sqrt + (size_t)n_sqrt * sizeof(double));
-    const size_t off_wg = al16(off_recip + (size_t)n_sqrt * sizeof(double));
-    const size_t wg_bytes = lw ? (size_t)4 * 2 * (TT / 4) * RS * sizeof(float) : 0;
-    const size_t off_teams = (off_wg + wg_bytes + 127) & ~(size_t)127;
-    const size_t team_base = lw ? al16((size_t)(2 * TT * RS + 3 * TT * pk.HP + 4 * TT) * 4)
+    const size_t off_teams = (off_recip + (size_t)n_sqrt * sizeof(double) + 127) & ~(size_t)127;
+    const size_t team_base = lw ? al16((size_t)(3 * TT * RS + 3 * TT * pk.HP + 4 * TT) * 4)
                                 : al16((size_t)(2 * H * XS + TT * (H + 4) + 3 * TT * pk.HP + 4 * TT) * 4);
     const size_t per_tree = (size_t)(S_max + 2) * sizeof(int) + (size_t)N * 44;  // path + selection cache + hot W + hot records
     const size_t kMax = 227 * 1024;
     if (off_teams + team_base + per_tree + 256 > kMax) { why = "one tree does not fit the team kernel's shared memory"; return 1; }
     int n_team = c->teams_per_cta > 0 ? c->teams_per_cta : (tps + TT - 1) / TT;
     if (n_team < 1) n_team = 1;
-    if (n_team > (lw ? 3 : 7)) n_team = lw ? 3 : 7;
-    // the automatic choice keeps the CTA at <= 512 threads (128 registers per thread); with the layer warpgroup at <= 448
-    const int max_threads = lw ? (c->teams_per_cta > 0 ? 640 : 512) : (c->teams_per_cta > 0 ? 1024 : 512);
-    while (n_team > 1 && (lw_warps + n_team * team_warps) * 32 > max_threads) --n_team;
-    if ((lw_warps + n_team * team_warps) * 32 > (lw ? 640 : 1024)) { why = "team does not fit a CTA"; return 1; }
+    if (lw && c->teams_per_cta <= 0 && TT == 8) n_team = (tps + 7) / 8;
+    if (n_team > (lw ? 4 : 7)) n_team = lw ? 4 : 7;
+    if (!lw) {
+        // the automatic choice keeps the CTA at <= 512 threads (128 registers per thread)
+        const int max_threads = c->teams_per_cta > 0 ? 1024 : 512;
+        while (n_team > 1 && n_team * team_warps * 32 > max_threads) --n_team;
+        if (n_team * team_warps * 32 > 1024) { why = "team does not fit a CTA"; return 1; }
+    }
     // trees per batch: spread the SM's trees evenly over its teams, within TT and within shared memory
     int tpt = 0;
     for (;; --n_team) {
@@ -728,12 +734,16 @@ static int plan_team(const cumind_tree* t, const cumind_net* n, const cumind_sea
         if (n_team == 1) { why = "one tree does not fit the team kernel's shared memory"; return 1; }
     }
     if (tpt < 1) tpt = 1;
+    if (lw) {
+        team_warps = team_lw_team_warps(n_team);
+        nmw = team_warps - ntw;
+    }
     const size_t off_path = team_base;
     const size_t off_nxt = al16(off_path + (size_t)tpt * (S_max + 2) * sizeof(int));
     const size_t off_hotw = al16(off_nxt + (size_t)tpt * N * sizeof(int));
     const size_t off_hot = al16(off_hotw + (size_t)tpt * N * sizeof(double));
     const size_t team_bytes = (off_hot + (size_t)tpt * N * 32 + 127) & ~(size_t)127;
-    const size_t total = off_teams + (size_t)n_team * team_bytes + 16;
+    const size_t total = off_teams + (size_t)n_team * team_bytes + 16 + (lw ? 32 * (size_t)n_team : 0);
     if (total > kMax) { why = "internal: team scratch exceeds shared memory"; return 1; }
     const int n_batches = (B + tpt - 1) / tpt;
     int grid = (n_batches + n_team - 1) / n_team;
@@ -769,9 +779,7 @@ static int plan_team(const cumind_tree* t, const cumind_net* n, const cumind_sea
     p.n_sqrt = n_sqrt;
     p.clk = nullptr;
     p.pdl = 0;
-    p.lw = 0;
-    if (lw) { const int th = pl.block; p.lw = th <= 256 ? 40 : (th <= 384 ? 28 : (th <= 512 ? 16 : 8)); }   // = the instantiation launch_lw picks
-    p.off_wg = (unsigned)off_wg;
+    p.lw = lw ? 64 : 0;
     p.tile = 0;
     p.stagger = 0;
     if (const char* e = getenv("CUMIND_TEAM_TILE")) p.tile = atoi(e);        // tuning only

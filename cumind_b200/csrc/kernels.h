@@ -68,14 +68,14 @@ struct TeamParams {
     int stagger;               // SM cycles between the starts of the teams of one CTA
     // shared-memory carve-up (bytes); off_path / off_nxt / off_hotw / off_hot are relative to the team's scratch
     unsigned off_sqrt, off_recip, off_teams, team_bytes, off_bar, off_path, off_nxt, off_hotw, off_hot;
-    int lw;                    // layer-warpgroup mode: weight pairs of k < lw resident in the registers of warps 0-3 (0 = classic)
-    unsigned off_wg;           // layer warpgroup: per-warp ping-pong rows (networks with more than two layers)
+    int lw;                    // layer-warpgroup mode (warps 0-3 run the dynamics layers with register-resident weights); 0 = classic
     int n_sqrt;
     long long* clk;            // [grid][16] phase clocks (diagnostic) or nullptr
     int pdl;                   // host only: launch with programmatic stream serialization
 };
 bool team_variant_ok(int G, int TT);
 bool team_lw_variant_ok(int G, int TT, int H);   // a layer-warpgroup instantiation exists
+int team_lw_team_warps(int n_team);
 cudaError_t launch_search_team(int G, const TeamParams& p, int grid, int block, size_t smem, cudaStream_t st);
 
 // tree_steps.cu — one launch per phase (warp per tree, any H / A)

@@ -179,47 +179,66 @@ CM_DEVICE void team_layer(const float* __restrict__ W, const float* __restrict__
 template <int NT, int KR, int RS>
 CM_DEVICE void wg_layer(const float2 (&wr)[KR > 0 ? KR : 1], const float* __restrict__ Wl, float2 bias, const float* __restrict__ xin,
                         float* __restrict__ xout, float* __restrict__ hid, size_t hstride, int n_valid, int lane) {
-    float2 acc[NT];
+    // trees in groups of GT: GT independent FMA chains issue round-robin (an FFMA2 result is needed again GT instructions
+    // later), and only GT activation rows are in flight at a time, which is what keeps the live registers within budget
+    constexpr int GT = NT < 4 ? NT : 4;
+    static_assert(NT % GT == 0, "tree slots per layer warp must be a multiple of the group size");
 #pragma unroll
-    for (int t = 0; t < NT; ++t) acc[t] = make_float2(0.0f, 0.0f);
+    for (int g0 = 0; g0 < NT; g0 += GT) {
+        const float* xg = xin + g0 * RS;
+        float2 acc[GT];
 #pragma unroll
-    for (int k4 = 0; k4 < 64; k4 += 4) {
-        float4 a[NT];
+        for (int t = 0; t < GT; ++t) acc[t] = make_float2(0.0f, 0.0f);
+        // the rows are read PD blocks of 4 k ahead of their use: under load a shared-memory access takes several times
+        // the issue time of one block's FFMA2s
+        constexpr int PD = 2, NB = PD + 1;
+        float4 a[NB][GT];
 #pragma unroll
-        for (int t = 0; t < NT; ++t) a[t] = *reinterpret_cast<const float4*>(xin + t * RS + k4);
+        for (int b = 0; b < PD; ++b)
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            const int k = k4 + kk;
-            float2 w;
-            if (k < KR) w = wr[k < KR ? k : 0];
-            else w = *reinterpret_cast<const float2*>(Wl + k * 64);
+            for (int t = 0; t < GT; ++t) a[b][t] = *reinterpret_cast<const float4*>(xg + t * RS + 4 * b);
 #pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                const float xv = kk == 0 ? a[t].x : (kk == 1 ? a[t].y : (kk == 2 ? a[t].z : a[t].w));
-                acc[t] = ffma2(xv, w, acc[t]);
+        for (int b = 0; b < 16; ++b) {
+            if (b + PD < 16) {
+#pragma unroll
+                for (int t = 0; t < GT; ++t) a[(b + PD) % NB][t] = *reinterpret_cast<const float4*>(xg + t * RS + 4 * (b + PD));
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int k = 4 * b + kk;
+                float2 w;
+                if (k < KR) w = wr[k < KR ? k : 0];
+                else w = *reinterpret_cast<const float2*>(Wl + k * 64);
+#pragma unroll
+                for (int t = 0; t < GT; ++t) {
+                    const float4 av = a[b % NB][t];
+                    const float xv = kk == 0 ? av.x : (kk == 1 ? av.y : (kk == 2 ? av.z : av.w));
+                    acc[t] = ffma2(xv, w, acc[t]);
+                }
             }
         }
-    }
 #pragma unroll
-    for (int t = 0; t < NT; ++t) {
-        const float2 r = *reinterpret_cast<const float2*>(xin + t * RS + 2 * lane);
-        float2 y;
-        y.x = fadd(frelu(fadd(acc[t].x, bias.x)), r.x);
-        y.y = fadd(frelu(fadd(acc[t].y, bias.y)), r.y);
-        *reinterpret_cast<float2*>(xout + t * RS + 2 * lane) = y;
-        if (hid != nullptr && t < n_valid) *reinterpret_cast<float2*>(hid + (size_t)t * hstride) = y;
+        for (int t = 0; t < GT; ++t) {
+            const float2 r = *reinterpret_cast<const float2*>(xg + t * RS + 2 * lane);
+            float2 y;
+            y.x = fadd(frelu(fadd(acc[t].x, bias.x)), r.x);
+            y.y = fadd(frelu(fadd(acc[t].y, bias.y)), r.y);
+            *reinterpret_cast<float2*>(xout + (g0 + t) * RS + 2 * lane) = y;
+            if (hid != nullptr && g0 + t < n_valid) *reinterpret_cast<float2*>(hid + (size_t)(g0 + t) * hstride) = y;
+        }
     }
 }
 
 // G lanes per tree; TT tree slots per team; lane tile of the network warps = TQ trees x NV neurons;
 // HS = compile-time hidden size (64: H == Hp == 64, loops without branches) or 0 (any H % 4 == 0).
-// KR > 0: LAYER WARPGROUP mode (hidden_dim 64 only).  Warps 0-3 of the CTA do nothing but the dynamics layers, for
-// every team in turn, with the weight pairs of k < KR resident in their registers (wg_layer); the network warps of
-// a team gather the parent rows row-major, hand them over (named barriers X0R / X2R), and compute heads + backup as
-// before.  The layers then cost the shared-memory pipe half of what the register-tiled product of team_layer does
-// (no operand transposes, one broadcast LDS.128 per 4 k and tree), and one team's layers never run against the
-// other's.  KR = 0: the network warps compute the layers themselves (team_layer).
-template <int G, int TT, int TQ, int NV, int HS, int KR>
+// KR > 0: LAYER WARPGROUP mode (hidden_dim 64, two dynamics layers).  Warps 0-3 of the CTA do nothing but the dynamics
+// layers, for every team in turn: warps 0,1 hold layer 0 and warps 2,3 layer 1 as 64 weight pairs per lane in registers
+// (wg_layer; the register file is re-divided between the roles with setmaxnreg).  The network warps of a team gather
+// the parent rows row-major, hand them over (named barriers X0R -> X1R -> X2R), and compute heads + backup as before.
+// The layers then read nothing but their activation rows from shared memory (one broadcast LDS.128 per 4 k and tree),
+// a third of the wavefronts of the register-tiled product of team_layer, and the two stages pipeline across teams.
+// KR = 0: the network warps compute the layers themselves (team_layer).
+template <int G, int TT, int TQ, int NV, int HS, int KR, int AUXREG = 104>
 CM_DEVICE void search_team_body(const TeamParams& p) {
     constexpr int TPW = 32 / G;       // trees per tree warp
     constexpr int XS = TT + 4;        // row stride of the activation tiles (floats)
@@ -245,8 +264,20 @@ CM_DEVICE void search_team_body(const TeamParams& p) {
     const bool is_tree = !is_layerwg && wt < p.ntw;
 
     // ---- stage parameters (TMA bulk) + sqrt / reciprocal tables ------------------------------------
+    // layer-warpgroup hand-overs (KR > 0), four mbarriers per team after the staging barrier:
+    //   X0R "gathered rows in x0" (one arrival per network warp)  ->  X1R[half] "rows after layer 0 in x1" (one arrival)
+    //   ->  X2R "rows after layer 1 in xt" (two arrivals); each completes once per simulation, so its parity is the job count & 1
+    uint64_t* hand = bar + 1;
     if (tid == 0) {
         tc_mbar_init(bar, 1);
+        if constexpr (KR > 0) {
+            for (int tm = 0; tm < p.n_team; ++tm) {
+                tc_mbar_init(hand + 4 * tm + 0, (uint32_t)p.nmw);
+                tc_mbar_init(hand + 4 * tm + 1, 1);
+                tc_mbar_init(hand + 4 * tm + 2, 1);
+                tc_mbar_init(hand + 4 * tm + 3, 2);
+            }
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -273,10 +304,10 @@ CM_DEVICE void search_team_body(const TeamParams& p) {
 
     // team scratch: x0,x1 [H][XS] | xt [TT][H+4] | lg[2],eb [TT][HP] | sel [4][TT] | path [tpt][S_max+2] | nxt [tpt][N] | hot W [tpt][N] | hot records [tpt][N]
     unsigned char* my = smem + p.off_teams + (size_t)team * p.team_bytes;
-    // KR > 0: x0 [TT][RS] (gathered rows, row-major) | xt [TT][RS] (rows after the last layer) | lg ...
+    // KR > 0: x0 [TT][RS] (gathered rows, row-major) | x1 [TT][RS] (after layer 0) | xt [TT][RS] (after layer 1) | lg ...
     float* x0 = reinterpret_cast<float*>(my);
-    float* x1 = KR > 0 ? x0 : x0 + (size_t)H * XS;
-    float* xt = KR > 0 ? x0 + (size_t)TT * RS : x1 + (size_t)H * XS;
+    float* x1 = KR > 0 ? x0 + (size_t)TT * RS : x0 + (size_t)H * XS;
+    float* xt = KR > 0 ? x1 + (size_t)TT * RS : x1 + (size_t)H * XS;
     float* lg_t = xt + (size_t)TT * (H + 4);              // logits + value of simulation s in buffer s & 1 (the root's in buffer 1)
     float* eb_t = lg_t + 2 * TT * HP;
     int* sel = reinterpret_cast<int*>(eb_t + TT * HP);   // [3][TT] parent_e, action, path length
@@ -286,9 +317,6 @@ CM_DEVICE void search_team_body(const TeamParams& p) {
     HotSel* hs_t = reinterpret_cast<HotSel*>(my + p.off_hot);
     const int bar_team = 1 + team, bar_mlp = 1 + p.n_team + team;
     const int cnt_team = team_warps * 32, cnt_mlp = p.nmw * 32;
-    // layer warpgroup hand-over: X0R = "the gathered rows of team i are in x0" (network warps arrive, layer warps wait),
-    // X2R = "the new hidden rows of team i are in xt" (layer warps arrive, network warps wait)
-    const int cnt_x = p.nmw * 32 + LWW * 32;
     const size_t hstride = (size_t)(S_max + 1) * H;
     const bool clk_on = p.clk != nullptr && team == 0 && lane == 0 && (wt == 0 || wt == p.ntw);
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, tmark = 0;
@@ -313,65 +341,71 @@ CM_DEVICE void search_team_body(const TeamParams& p) {
         while (clock64() < t_go) {}
     }
     if constexpr (KR > 0) {
+        // Register reallocation between the roles (setmaxnreg, whole warpgroups; the pool is what the launch allocated):
+        // 16 warps are launched with 128 registers per thread (four warps per SM sub-partition, 16 384 registers each);
+        // the layer warps grow to 200 — a full layer of weight pairs is 128 of them — and the twelve other warps shrink
+        // to AUXREG = 104, which is what fits beside one layer warp per sub-partition (32 * (200 + 3 * 104) = 16 384).
+        // 12 warps (one team) are launched with 168 and the eight other warps shrink to 152 (32 * (200 + 2 * 152)).
         if (is_layerwg) {
-            constexpr int NT = TT / 4;            // tree slots per layer warp
-            const int ts0 = warp * NT;
-            float2 wr0[KR], wr1[KR];
-            const float* W0 = w_s + p.pk.layer_w(0) + 2 * lane;
-            const float* W1 = w_s + p.pk.layer_w(L > 1 ? 1 : 0) + 2 * lane;
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 200;" ::: "memory");
+            // warps 0,1: layer 0 of tree slots [0, NT) / [NT, 2 NT); warps 2,3: layer 1 of the same halves.  Each warp keeps
+            // ITS layer's 64 weight pairs in registers for the whole launch; a team's rows go x0 -> (warps 0,1) -> x1 ->
+            // (warps 2,3) -> xt, and while warps 2,3 finish one team warps 0,1 already run the other.
+            constexpr int NT = TT / 2;
+            const int stage = warp >> 1, half = warp & 1;
+            const int ts0 = half * NT;
+            float2 wr[64];
+            const float* Wl = w_s + p.pk.layer_w(stage) + 2 * lane;
 #pragma unroll
-            for (int k = 0; k < KR; ++k) {
-                wr0[k] = *reinterpret_cast<const float2*>(W0 + k * 64);
-                wr1[k] = *reinterpret_cast<const float2*>(W1 + k * 64);
-            }
-            float* xa = reinterpret_cast<float*>(smem + p.off_wg) + (size_t)warp * 2 * NT * RS;   // per-warp ping-pong rows (L > 2)
-            float* xb = xa + NT * RS;
+            for (int k = 0; k < 64; ++k) wr[k] = *reinterpret_cast<const float2*>(Wl + k * 64);
+            const float2 bias = *reinterpret_cast<const float2*>(w_s + p.pk.layer_b(stage) + 2 * lane);
             const int team_stride = gridDim.x * p.n_team;
-            const bool wclk = p.clk != nullptr && warp == 0 && lane == 0;
+            const bool wclk = p.clk != nullptr && half == 0 && lane == 0;
             long long lc0 = 0, lc1 = 0;
+            uint32_t job = 0;   // jobs done per team so far: the parity of every hand-over barrier
             for (int first = blockIdx.x * p.n_team; first < p.n_batches; first += team_stride) {
-                for (int s = 0; s < p.S; ++s) {
+                for (int s = 0; s < p.S; ++s, ++job) {
                     for (int tm = 0; tm < p.n_team; ++tm) {
                         const int batch = first + tm;
                         if (batch >= p.n_batches) break;
                         const int t_begin = batch * p.tpt;
                         const int n_here = (p.tv.B - t_begin) < p.tpt ? (p.tv.B - t_begin) : p.tpt;
-                        unsigned char* tsc = smem + p.off_teams + (size_t)tm * p.team_bytes;
-                        const float* x0t = reinterpret_cast<const float*>(tsc) + ts0 * RS;
-                        float* x2t = reinterpret_cast<float*>(tsc) + (size_t)TT * RS + ts0 * RS;
-                        float* hid = p.tv.hidden + ((size_t)(t_begin + ts0) * (S_max + 1) + (size_t)(s + 1)) * H + 2 * lane;
+                        float* tsc = reinterpret_cast<float*>(smem + p.off_teams + (size_t)tm * p.team_bytes);
+                        const float* x0t = tsc + ts0 * RS;
+                        float* x1t = tsc + (size_t)TT * RS + ts0 * RS;
+                        float* x2t = tsc + (size_t)2 * TT * RS + ts0 * RS;
+                        uint64_t* hb = hand + 4 * tm;
                         const long long tw0 = wclk ? clock64() : 0;
-                        named_bar_sync(1 + 2 * p.n_team + tm, cnt_x);   // X0R
-                        const long long tw1 = wclk ? clock64() : 0;
-                        const float* in = x0t;
-                        for (int l = 0; l < L; ++l) {
-                            const bool last = l == L - 1;
-                            float* out = last ? x2t : ((l & 1) ? xb : xa);
-                            const float2 bias = *reinterpret_cast<const float2*>(w_s + p.pk.layer_b(l) + 2 * lane);
-                            float* h = last ? hid : nullptr;
-                            const int nv = n_here - ts0;
-                            if (l == 0) wg_layer<NT, KR, RS>(wr0, W0, bias, in, out, h, (size_t)(S_max + 1) * H, nv, lane);
-                            else if (l == 1) wg_layer<NT, KR, RS>(wr1, W1, bias, in, out, h, (size_t)(S_max + 1) * H, nv, lane);
-                            else {
-                                const float2 none[1] = {make_float2(0.f, 0.f)};
-                                wg_layer<NT, 0, RS>(none, w_s + p.pk.layer_w(l) + 2 * lane, bias, in, out, h, (size_t)(S_max + 1) * H, nv, lane);
-                            }
+                        if (stage == 0) {
+                            tc_mbar_wait(hb + 0, job & 1u);                    // X0R: gathered rows of team tm
+                            const long long tw1 = wclk ? clock64() : 0;
+                            wg_layer<NT, 64, RS>(wr, Wl, bias, x0t, x1t, nullptr, 0, 0, lane);
                             __syncwarp();
-                            in = out;
+                            if (lane == 0) tc_mbar_arrive(hb + 1 + half);      // X1R[half]
+                            if (wclk) { const long long tw2 = clock64(); lc0 += tw1 - tw0; lc1 += tw2 - tw1; }
+                        } else {
+                            tc_mbar_wait(hb + 1 + half, job & 1u);
+                            const long long tw1 = wclk ? clock64() : 0;
+                            float* hid = p.tv.hidden + ((size_t)(t_begin + ts0) * (S_max + 1) + (size_t)(s + 1)) * H + 2 * lane;
+                            wg_layer<NT, 64, RS>(wr, Wl, bias, x1t, x2t, hid, (size_t)(S_max + 1) * H, n_here - ts0, lane);
+                            __syncwarp();
+                            if (lane == 0) tc_mbar_arrive(hb + 3);             // X2R
+                            if (wclk) { const long long tw2 = clock64(); lc0 += tw1 - tw0; lc1 += tw2 - tw1; }
                         }
-                        __syncwarp();
-                        asm volatile("bar.arrive %0, %1;" ::"r"(1 + 3 * p.n_team + tm), "r"(cnt_x) : "memory");   // X2R
-                        if (wclk) { const long long tw2 = clock64(); lc0 += tw1 - tw0; lc1 += tw2 - tw1; }
                     }
                 }
             }
-            if (wclk) { p.clk[(size_t)blockIdx.x * 16 + 7] = lc0; p.clk[(size_t)blockIdx.x * 16 + 15] = lc1; }
+            // clock slots: layer-0 warp 0 -> {7: waiting for rows, 15: computing}; layer-1 warp 2 -> added to the same slots is
+            // avoided: it reports through the tree / network wait clocks instead
+            if (wclk && stage == 0) { p.clk[(size_t)blockIdx.x * 16 + 7] = lc0; p.clk[(size_t)blockIdx.x * 16 + 15] = lc1; }
             return;
         }
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUXREG) : "memory");
     }
     // (leaf - 1) / A by multiplication: exact for leaf - 1 < 2^32 / A
     const unsigned magic_A = A > 1 ? (unsigned)((0x100000000ULL + (unsigned)A - 1u) / (unsigned)A) : 0u;
     const int team_global = blockIdx.x * p.n_team + team, team_stride = gridDim.x * p.n_team;
+    uint32_t job = 0;   // layer-warpgroup mode: simulations this team has handed over so far (hand-over barrier parity)
     for (int batch = team_global; batch < p.n_batches; batch += team_stride) {
         const int t_begin = batch * p.tpt;
         const int n_here = (p.tv.B - t_begin) < p.tpt ? (p.tv.B - t_begin) : p.tpt;
@@ -532,7 +566,7 @@ CM_DEVICE void search_team_body(const TeamParams& p) {
             float* hid0 = p.tv.hidden + (size_t)t_begin * hstride;
             const uint32_t hs_a = smem_addr(hs_t), hw_a = smem_addr(hw_t), nxt_a = smem_addr(nxt_t), path_a = smem_addr(path_t);
             const uint32_t sq_a = smem_addr(sq_s), rc_a = smem_addr(rc_s);
-            const BackupLanes bl = backup_lanes(TT, p.nmw, mw, lane);
+            const BackupLanes bl = backup_lanes(p.tpt, p.nmw, mw, lane);   // the path entries of the team's trees over all network lanes
 
             // ---- root: x0 = root hidden (also hidden row 0), heads -> logits --------------------------
             for (int i = mlane; i < TT * H4; i += nml) {
@@ -586,9 +620,10 @@ CM_DEVICE void search_team_body(const TeamParams& p) {
                         *reinterpret_cast<float4*>(x0 + (size_t)ts * RS + 4 * c) = make_float4(fadd(h4.x, e4.x), fadd(h4.y, e4.y), fadd(h4.z, e4.z), fadd(h4.w, e4.w));
                     }
                     __syncwarp();
-                    asm volatile("bar.arrive %0, %1;" ::"r"(1 + 2 * p.n_team + team), "r"(cnt_x) : "memory");   // X0R: rows handed to the layer warpgroup
+                    if (lane == 0) tc_mbar_arrive(hand + 4 * team);          // X0R: rows handed to the layer warpgroup
                     CM_CLK(c0, __float_as_int(x0[0]))
-                    named_bar_sync(1 + 3 * p.n_team + team, cnt_x);                                            // X2R: new hidden rows in xt
+                    tc_mbar_wait(hand + 4 * team + 3, job & 1u);             // X2R: new hidden rows in xt
+                    ++job;
                     CM_CLK(c4, __float_as_int(xt[0]))
                 } else {
                 // gather: x0[j][ts] = hidden[ts][parent_e][j] + Emb[action][j]   (network.py:229-230).
@@ -669,7 +704,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_team_kernel(const TeamParams p
 // thread count rounded up to whole warpgroups, which would give a 14-warp CTA 128 registers instead of 144).
 template <int G, int TT, int TQ, int NV, int HS, int NREG, int KR>
 __global__ void __maxnreg__(NREG) search_team_lw_kernel(const TeamParams p) {
-    search_team_body<G, TT, TQ, NV, HS, KR>(p);
+    search_team_body<G, TT, TQ, NV, HS, KR, (NREG == 128 ? 104 : 152)>(p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -704,17 +739,15 @@ static cudaError_t launch_t(const TeamParams& p, int grid, int block, size_t sme
 
 // layer-warpgroup instantiations: hidden_dim 64, G in {2,4,8}; register-resident k per block size (KR)
 bool team_lw_variant_ok(int G, int TT, int H) { return H == 64 && (TT == 8 || TT == 16) && (G == 2 || G == 4 || G == 8); }
+// warps per team in layer-warpgroup mode: the CTA must consist of whole warpgroups (4 layer warps + n_team * team warps)
+int team_lw_team_warps(int n_team) { return n_team == 1 ? 8 : (n_team == 2 ? 6 : (n_team == 3 ? 4 : 3)); }
 
 template <int G, int TT>
 static cudaError_t launch_lw(const TeamParams& p, int grid, int block, size_t smem, cudaStream_t st) {
     constexpr int TQ = TT == 16 ? 4 : 2;
-    // The register file is 16 384 registers per SM sub-partition and warps are dealt round-robin to the four of them:
-    // registers per thread = 16384 / (32 * ceil(warps / 4)), rounded down to a multiple of 8.  The resident k (KR) is
-    // what that budget leaves after the accumulators, the x rows in flight and the backup arithmetic.
-    if (block <= 256) return launch_one_lw<G, TT, TQ, 2, 64, 224, 40>(p, grid, block, smem, st);   // e.g. one team, 3 network warps
-    if (block <= 384) return launch_one_lw<G, TT, TQ, 2, 64, 168, 28>(p, grid, block, smem, st);   // one team, or two teams with 3 network warps
-    if (block <= 512) return launch_one_lw<G, TT, TQ, 2, 64, 128, 16>(p, grid, block, smem, st);   // two teams
-    if (block <= 640) return launch_one_lw<G, TT, TQ, 2, 64, 96, 8>(p, grid, block, smem, st);     // three teams
+    // 16 warps launched with 128 registers per thread, 12 warps with 168 (setmaxnreg re-divides them inside the kernel)
+    if (block == 512) return launch_one_lw<G, TT, TQ, 2, 64, 128, 64>(p, grid, block, smem, st);
+    if (block == 384) return launch_one_lw<G, TT, TQ, 2, 64, 168, 64>(p, grid, block, smem, st);
     return cudaErrorInvalidValue;
 }
 

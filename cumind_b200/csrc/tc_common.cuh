@@ -29,6 +29,10 @@ CM_DEVICE void tc_mbar_wait(uint64_t* bar, uint32_t phase) {
             : "memory");
     } while (!ok);
 }
+// one arrival (release at CTA scope: the arriving thread's earlier writes, and those it has observed, are visible to a waiter)
+CM_DEVICE void tc_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
 CM_DEVICE void tc_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
                  "l"(src), "r"(bytes), "r"(smem_addr(bar))

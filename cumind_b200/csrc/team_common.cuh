@@ -85,9 +85,10 @@ CM_DEVICE int select_chase(uint32_t nxt_addr, uint32_t path_addr, int g, bool ac
 // rounded quotient when the numerator is 0, NaN or within [2^-900, 2^900] (`exact` reports whether it was).
 // -0 is folded into +0 (Python compares them equal), NaN maps to +inf for child 0 and -inf otherwise (max()
 // never replaces its first candidate by a NaN and never replaces a NaN first candidate).
+// The exploration term ((c_puct*prior)*sqrt(N_parent)) / (1 + n) of Node.ucb_score (mcts.py:65); it does not depend on
+// the value being backed up.
 template <bool IEEE>
-CM_DEVICE long long score_key(double q, double cp, double r, int n, double sq, bool first, bool& exact) {
-    const long long PINF = 0x7ff0000000000000LL, NINF = (long long)0xfff0000000000000ULL;
+CM_DEVICE double explo_term(double cp, double r, int n, double sq, bool& exact) {
     const double num = __dmul_rn(cp, sq);
     const double d = (double)(1 + n);
     double t;
@@ -102,11 +103,20 @@ CM_DEVICE long long score_key(double q, double cp, double r, int n, double sq, b
         const unsigned lo = (unsigned)__double2loint(num);
         exact = ((hi >> 20) - 123u) < 1800u || (hi | lo) == 0u || hi > 0x7ff00000u || (hi == 0x7ff00000u && lo != 0u) || n == 0;
     }
+    return t;
+}
+// q + t as the order-preserving key (see score_key)
+CM_DEVICE long long key_of(double q, double t, int n, bool first) {
+    const long long PINF = 0x7ff0000000000000LL, NINF = (long long)0xfff0000000000000ULL;
     long long b = __double_as_longlong(__dadd_rn(q, t));
     const long long mag = b & 0x7fffffffffffffffLL;
     b = mag > PINF ? (first ? PINF : NINF) : (mag == 0 ? 0LL : b);
     b = (n == 0) ? PINF : b;
     return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+template <bool IEEE>
+CM_DEVICE long long score_key(double q, double cp, double r, int n, double sq, bool first, bool& exact) {
+    return key_of(q, explo_term<IEEE>(cp, r, n, sq, exact), n, first);
 }
 
 // Markstein sequence of div_small: a / d from r = RN(1/d); the correctly rounded quotient when markstein_ok(a)

@@ -164,7 +164,7 @@ def test_team_search_vs_oracle_all_geometries(shape, geom, classic):
     mcts.teams_per_cta, mcts.net_warps_per_team, mcts.trees_per_team, mcts.lanes_per_tree = geom
     plan = mcts.plan(B)
     assert plan["schedule"] == "team", plan
-    if H == 64 and geom[3] in (0, 4):
+    if H == 64 and geom[3] in (0, 4) and A <= 4:
         assert (plan["layer_warpgroup_resident_k"] > 0) == (not classic), plan
     probs, visits = mcts.search_batch(h, noise=noise)
     _assert_trees_equal(mcts, o, S, A)

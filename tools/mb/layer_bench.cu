@@ -191,6 +191,133 @@ __global__ void __launch_bounds__(384, 1) k_layer(const float* Wg, long long* ou
     if (tid < 64) sink[blockIdx.x * 64 + tid] = x0[tid * 4] + x1[tid * 4] + x2[tid * 4];
 }
 
+
+// ---- the product's wg_layer (search_team.cu): lane = neuron pair, x row-major broadcast, KR resident weight pairs ----
+template <int NT, int KR, int UNROLL_ALL>
+__device__ __forceinline__ void wg_layer(const float2 (&wr)[KR > 0 ? KR : 1], const float* __restrict__ Wl, float2 bias,
+                                         const float* __restrict__ xin, float* __restrict__ xout, int lane) {
+    float2 acc[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc[t] = make_float2(0.f, 0.f);
+    if constexpr (UNROLL_ALL) {
+#pragma unroll
+        for (int k4 = 0; k4 < 64; k4 += 4) {
+            float4 a[NT];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) a[t] = *reinterpret_cast<const float4*>(xin + t * RS + k4);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int k = k4 + kk;
+                float2 w;
+                if (k < KR) w = wr[k < KR ? k : 0];
+                else w = *reinterpret_cast<const float2*>(Wl + k * 64);
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const float xv = kk == 0 ? a[t].x : (kk == 1 ? a[t].y : (kk == 2 ? a[t].z : a[t].w));
+                    acc[t] = ffma2(xv, w, acc[t]);
+                }
+            }
+        }
+    } else {
+        // resident blocks unrolled, the rest a rolled loop (small code)
+#pragma unroll
+        for (int k4 = 0; k4 < KR; k4 += 4) {
+            float4 a[NT];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) a[t] = *reinterpret_cast<const float4*>(xin + t * RS + k4);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const float xv = kk == 0 ? a[t].x : (kk == 1 ? a[t].y : (kk == 2 ? a[t].z : a[t].w));
+                    acc[t] = ffma2(xv, wr[(k4 + kk) < KR ? (k4 + kk) : 0], acc[t]);
+                }
+        }
+#pragma unroll 2
+        for (int k4 = KR; k4 < 64; k4 += 4) {
+            float4 a[NT];
+            float2 w[4];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) a[t] = *reinterpret_cast<const float4*>(xin + t * RS + k4);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float2*>(Wl + (k4 + kk) * 64);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const float xv = kk == 0 ? a[t].x : (kk == 1 ? a[t].y : (kk == 2 ? a[t].z : a[t].w));
+                    acc[t] = ffma2(xv, w[kk], acc[t]);
+                }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        const float2 r = *reinterpret_cast<const float2*>(xin + t * RS + 2 * lane);
+        float2 y;
+        y.x = fmaxf(acc[t].x + bias.x, 0.f) + r.x;
+        y.y = fmaxf(acc[t].y + bias.y, 0.f) + r.y;
+        *reinterpret_cast<float2*>(xout + t * RS + 2 * lane) = y;
+    }
+}
+
+// 4 layer warps (+ `noise` warps that hammer shared memory and the FP64 pipe the way the aux warps do)
+template <int NT, int KR, int UNROLL_ALL, int NREG>
+__global__ void __maxnreg__(NREG) k_wg(const float* Wg, long long* out, float* sink, int iters) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* W = sm;
+    float* xb = sm + 2 * H * H + 2 * H;
+    for (int i = tid; i < 2 * H * H + 2 * H; i += blockDim.x) W[i] = Wg[i];
+    for (int i = tid; i < 3 * 32 * RS; i += blockDim.x) xb[i] = 0.001f * (i % 97);
+    __syncthreads();
+    if (warp >= 4) {   // noise warps
+        double d = 1.0 + lane;
+        float f = 0;
+        const float* q = xb + 2 * 32 * RS;
+        for (int it = 0; it < iters * 40; ++it) {
+            d = d * 1.0000001 + 0.5;
+            f += q[(lane * 17 + it) & 1023];
+            d = d * 0.9999999 + f;
+        }
+        if (d == 0.123) sink[0] = (float)d;
+        return;
+    }
+    float2 wr0[KR > 0 ? KR : 1], wr1[KR > 0 ? KR : 1];
+    const float* W0 = W + 2 * lane; const float* W1 = W + H * H + 2 * lane;
+#pragma unroll
+    for (int k = 0; k < KR; ++k) { wr0[k] = *reinterpret_cast<const float2*>(W0 + k * 64); wr1[k] = *reinterpret_cast<const float2*>(W1 + k * 64); }
+    const float2 b0 = *reinterpret_cast<const float2*>(W + 2 * H * H + 2 * lane), b1 = *reinterpret_cast<const float2*>(W + 2 * H * H + H + 2 * lane);
+    float* x0 = xb + warp * NT * RS; float* x1 = xb + 32 * RS + warp * NT * RS;
+    const long long t0c = clock64();
+    for (int it = 0; it < iters; ++it) {
+        wg_layer<NT, KR, UNROLL_ALL>(wr0, W0, b0, x0, x1, lane);
+        __syncwarp();
+        wg_layer<NT, KR, UNROLL_ALL>(wr1, W1, b1, x1, x0, lane);
+        __syncwarp();
+    }
+    const long long t1c = clock64();
+    if (lane == 0) out[blockIdx.x * 8 + warp] = t1c - t0c;
+    if (tid < 64) sink[blockIdx.x * 64 + tid] = x0[tid] + x1[tid];
+}
+
+template <int NT, int KR, int UNROLL_ALL, int NREG>
+void run_wg(const char* name, const float* Wg, long long* out, float* sink) {
+    const int iters = 200;
+    for (int noise : {0, 4, 10}) {
+        const size_t smem = (size_t)(2 * H * H + 2 * H + 3 * 32 * RS) * 4;
+        cudaFuncSetAttribute(k_wg<NT, KR, UNROLL_ALL, NREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaMemset(out, 0, 148 * 8 * 8);
+        k_wg<NT, KR, UNROLL_ALL, NREG><<<148, 128 + 32 * noise, smem>>>(Wg, out, sink, iters);
+        cudaError_t e = cudaDeviceSynchronize();
+        long long h[148 * 8];
+        cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+        double s = 0;
+        for (int b = 0; b < 148; ++b) for (int g = 0; g < 4; ++g) s += (double)h[b * 8 + g];
+        printf("%-64s noise warps=%2d: %8.1f cycles per job (2 layers x %d trees per warp)  [%s]\n", name, noise, s / (148.0 * 4 * iters), NT,
+               cudaGetErrorString(e));
+    }
+}
+
 template <int V>
 void run(const char* name, const float* Wg, long long* out, float* sink) {
     const int iters = 200;
@@ -222,5 +349,12 @@ int main() {
     run<2>("V2 reg W (lane = neuron), x k-major broadcast, FFMA2 over tree pairs", Wg, out, sink);
     run<3>("V3 reg W pairs, x row-major broadcast, 2 warps per layer, pipelined", Wg, out, sink);
     run<4>("V4 reg W pairs reloaded per layer, 4 warps per layer", Wg, out, sink);
+    run_wg<4, 16, 1, 128>("W5 product wg_layer NT=4 KR=16 unrolled, 128 regs", Wg, out, sink);
+    run_wg<4, 16, 0, 128>("W6 NT=4 KR=16, non-resident part as a rolled loop", Wg, out, sink);
+    run_wg<4, 0, 0, 128>("W7 NT=4 KR=0 rolled loop", Wg, out, sink);
+    run_wg<8, 16, 1, 128>("W8 NT=8 KR=16 unrolled, 128 regs", Wg, out, sink);
+    run_wg<8, 16, 0, 128>("W9 NT=8 KR=16 rolled", Wg, out, sink);
+    run_wg<4, 28, 1, 168>("W10 NT=4 KR=28 unrolled, 168 regs", Wg, out, sink);
+    run_wg<4, 28, 0, 168>("W11 NT=4 KR=28 rolled rest, 168 regs", Wg, out, sink);
     return 0;
 }
