@@ -27,7 +27,7 @@ EXPORTS = [
 
 NET_FP32_EXACT = 0
 NET_BF16_TC = 1
-TREE_REFERENCE = 0
+TREE_REFERENCE, TREE_MINMAX_DISCOUNT = 0, 1
 SCHED_AUTO, SCHED_WARP, SCHED_TEAM, SCHED_TEAM_CLASSIC = 0, 1, 2, 3
 
 
@@ -41,14 +41,14 @@ class SearchCfg(C.Structure):
                 ("exploration_fraction", C.c_double), ("dirichlet_alpha", C.c_double), ("noise_mode", C.c_int32),
                 ("net_mode", C.c_int32), ("tree_mode", C.c_int32), ("lanes_per_tree", C.c_int32), ("seed", C.c_uint64),
                 ("tree_index_base", C.c_uint64), ("schedule", C.c_int32), ("teams_per_cta", C.c_int32),
-                ("net_warps_per_team", C.c_int32), ("trees_per_team", C.c_int32)]
+                ("net_warps_per_team", C.c_int32), ("trees_per_team", C.c_int32), ("discount", C.c_double)]
 
 
 class TreeView(C.Structure):
     _fields_ = [("B", C.c_int32), ("S_max", C.c_int32), ("A", C.c_int32), ("H", C.c_int32), ("N", C.c_int32),
                 ("nodes", C.c_void_p), ("child_eidx", C.c_void_p), ("root_prior", C.c_void_p), ("exp_node", C.c_void_p),
                 ("hidden", C.c_void_p), ("path", C.c_void_p), ("path_len", C.c_void_p), ("leaf", C.c_void_p),
-                ("n_expanded", C.c_void_p), ("depth_sum", C.c_void_p)]
+                ("n_expanded", C.c_void_p), ("depth_sum", C.c_void_p), ("reward", C.c_void_p), ("minmax", C.c_void_p)]
 
 
 class CuMindNativeError(RuntimeError):

@@ -472,7 +472,7 @@ extern "C" int cumind_softmax(const float* d_logits, int32_t B, int32_t A, float
 // tree slab
 // ------------------------------------------------------------------------------------------------
 struct SlabOffsets {
-    size_t nodes, eidx, rprior, exp_node, hidden, path, path_len, leaf, n_exp, depth, leaf_value, total;
+    size_t nodes, eidx, rprior, exp_node, hidden, path, path_len, leaf, n_exp, depth, leaf_value, reward, minmax, total;
 };
 static SlabOffsets slab_offsets(int64_t B, int64_t S, int64_t A, int64_t H) {
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -490,6 +490,8 @@ static SlabOffsets slab_offsets(int64_t B, int64_t S, int64_t A, int64_t H) {
     o.n_exp = p;      p = al(p + B * sizeof(int32_t));
     o.depth = p;      p = al(p + B * sizeof(long long));
     o.leaf_value = p; p = al(p + B * sizeof(float));
+    o.reward = p;     p = al(p + B * N * sizeof(float));
+    o.minmax = p;     p = al(p + B * 2 * sizeof(double));
     o.total = p;
     return o;
 }
@@ -523,6 +525,8 @@ extern "C" int cumind_tree_create(int32_t B, int32_t S_max, int32_t A_tree, int3
     t->tv.n_expanded = (int32_t*)(b + o.n_exp);
     t->tv.depth_sum = (long long*)(b + o.depth);
     t->leaf_value = (float*)(b + o.leaf_value);
+    t->tv.reward = (float*)(b + o.reward);
+    t->tv.minmax = (double*)(b + o.minmax);
     t->bytes = o.total;
     *out = t;
     return 0;
@@ -546,6 +550,8 @@ extern "C" int cumind_tree_get_view(const cumind_tree* t, cumind_tree_view* out)
     out->leaf = t->tv.leaf;
     out->n_expanded = t->tv.n_expanded;
     out->depth_sum = (int64_t*)t->tv.depth_sum;
+    out->reward = t->tv.reward;
+    out->minmax = t->tv.minmax;
     return 0;
 }
 
@@ -562,7 +568,9 @@ static int check_search(const char* fn, const cumind_tree* t, const cumind_net* 
     if (n->desc.hidden_dim != t->tv.H) return fail(std::string(fn) + ": tree was created for a different hidden_dim");
     if (c->noise_mode < 0 || c->noise_mode > 2) return fail("noise_mode must be 0, 1 or 2");
     if (c->noise_mode == 1 && !d_noise) return fail("noise_mode 1 needs d_noise");
-    if (c->tree_mode != CUMIND_TREE_REFERENCE) return fail("tree_mode not available in this build");
+    if (c->tree_mode != CUMIND_TREE_REFERENCE && c->tree_mode != CUMIND_TREE_MINMAX_DISCOUNT) return fail("unknown tree_mode");
+    if (c->tree_mode == CUMIND_TREE_MINMAX_DISCOUNT && c->net_mode != CUMIND_NET_FP32_EXACT)
+        return fail("CUMIND_TREE_MINMAX_DISCOUNT runs in CUMIND_NET_FP32_EXACT mode only");
     if (check_mode(n, c->net_mode, true)) return 1;
     return 0;
 }
@@ -582,6 +590,8 @@ static StepParams step_params(const cumind_tree* t, const cumind_net* n, const c
     p.noise_mode = c->noise_mode;
     p.seed = c->seed;
     p.tree_base = c->tree_index_base;
+    p.tree_mode = c->tree_mode;
+    p.discount = c->discount;
     return p;
 }
 
@@ -803,13 +813,16 @@ extern "C" int cumind_search_stepwise(cumind_tree* t, const cumind_net* n, const
     cudaStream_t st = (cudaStream_t)stream;
     const StepParams p = step_params(t, n, c);
     CM_CUDA(launch_init_root(p, d_root_hidden, d_noise, st));
+    const bool mm = c->tree_mode == CUMIND_TREE_MINMAX_DISCOUNT;
     for (int s = 0; s < c->num_simulations; ++s) {
-        CM_CUDA(launch_select(p, st));
+        if (mm) CM_CUDA(launch_select_mm(p, st));
+        else CM_CUDA(launch_select(p, st));
         if (c->net_mode == CUMIND_NET_BF16_TC)
             CM_CUDA(launch_expand_tc(n->d_tcpack, n->tpk, n->sm_count, t->tv, t->leaf_value, st));
         else
             CM_CUDA(launch_expand(p, t->leaf_value, st));
-        CM_CUDA(launch_backup(p, t->leaf_value, st));
+        if (mm) CM_CUDA(launch_backup_mm(p, t->leaf_value, st));
+        else CM_CUDA(launch_backup(p, t->leaf_value, st));
     }
     CM_CUDA(launch_finalize(p, d_out_visits, d_out_probs, d_out_root_value, st));
     g_launches += 2 + 3ull * c->num_simulations;
@@ -831,6 +844,8 @@ static int search_impl(cumind_tree* t, const cumind_net* n, const float* d_root_
     // (measured in profiles/README.md), and it is more accurate.  cumind_search_stepwise always
     // honours net_mode (tcgen05 expansion kernel in bf16 mode).
     if (c->schedule < 0 || c->schedule > CUMIND_SCHED_TEAM_CLASSIC) return fail("unknown schedule");
+    if (c->tree_mode == CUMIND_TREE_MINMAX_DISCOUNT)   // the optional mode exists on the one-launch-per-phase kernels only
+        return cumind_search_stepwise(t, n, d_root_hidden, c, d_noise, d_out_visits, d_out_probs, d_out_root_value, stream);
     if (c->schedule != CUMIND_SCHED_WARP) {
         TeamPlan tp;
         if (plan_team(t, n, c, tp, why) == 0 && (c->schedule >= CUMIND_SCHED_TEAM || team_is_preferred(tp, n->sm_count))) {

@@ -228,6 +228,8 @@ struct TreeView {
     int32_t* leaf;        // [B]
     int32_t* n_expanded;  // [B]
     long long* depth_sum; // [B]
+    float* reward;        // [B][N]   CUMIND_TREE_MINMAX_DISCOUNT only
+    double* minmax;       // [B][2]   CUMIND_TREE_MINMAX_DISCOUNT only
 };
 
 struct NetView {

@@ -87,11 +87,16 @@ struct StepParams {
     double c_puct, frac, one_minus_frac, alpha;
     int noise_mode;
     unsigned long long seed, tree_base;
+    int tree_mode;     // CUMIND_TREE_*
+    double discount;   // CUMIND_TREE_MINMAX_DISCOUNT
 };
 cudaError_t launch_init_root(const StepParams& p, const float* root_hidden, const double* noise, cudaStream_t st);
 cudaError_t launch_select(const StepParams& p, cudaStream_t st);
 cudaError_t launch_expand(const StepParams& p, float* leaf_value, cudaStream_t st);
 cudaError_t launch_backup(const StepParams& p, const float* leaf_value, cudaStream_t st);
+// CUMIND_TREE_MINMAX_DISCOUNT (optional mode, see include/cumind_b200.h): select and backup of that mode
+cudaError_t launch_select_mm(const StepParams& p, cudaStream_t st);
+cudaError_t launch_backup_mm(const StepParams& p, const float* leaf_value, cudaStream_t st);
 cudaError_t launch_finalize(const StepParams& p, int32_t* out_visits, double* out_probs, double* out_root_value, cudaStream_t st);
 cudaError_t launch_dirichlet(double* noise, int B, int A, double alpha, unsigned long long seed,
                              unsigned long long tree_base, cudaStream_t st);

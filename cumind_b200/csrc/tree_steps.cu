@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) init_root_kernel(const St
             rprior[a] = pd;
             store_node(nodes + 1 + a, 0.0, 0, p32);
             eidx[1 + a] = -1;
+            if (p.tree_mode == CUMIND_TREE_MINMAX_DISCOUNT) p.tv.reward[tt * p.tv.N + 1 + a] = 0.0f;
         }
         if (lane == 0) {
             store_node(nodes, 0.0, 0, 1.0f);
@@ -65,6 +66,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) init_root_kernel(const St
             p.tv.depth_sum[t] = 0;
             p.tv.path_len[t] = 0;
             p.tv.leaf[t] = 0;
+            if (p.tree_mode == CUMIND_TREE_MINMAX_DISCOUNT) {
+                p.tv.reward[tt * p.tv.N] = 0.0f;
+                p.tv.minmax[2 * tt] = dinf();
+                p.tv.minmax[2 * tt + 1] = -dinf();
+            }
         }
     }
 }
@@ -125,7 +131,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) expand_kernel(const StepP
     }
     if (active) {
         for (int j = lane; j < H; j += 32) hidden[(size_t)k * H + j] = cur[j];
-        heads<32>(p.pack + p.pk.heads_w, p.pack + p.pk.heads_b, cur, H, HP, A_net + 1, lg, lane);
+        // policy logits, value and (min-max mode) the dynamics reward: head columns 0..A_net-1, A_net, A_net+1
+        heads<32>(p.pack + p.pk.heads_w, p.pack + p.pk.heads_b, cur, H, HP, A_net + (p.tree_mode == CUMIND_TREE_MINMAX_DISCOUNT ? 2 : 1), lg, lane);
     }
     __syncwarp();
     const float ssum = softmax_prepare<32>(lg, eb, A_net, lane, active);
@@ -134,14 +141,107 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) expand_kernel(const StepP
         for (int a = lane; a < A; a += 32) {
             store_node(nodes + cbase + a, 0.0, 0, __fdiv_rn(eb[a], ssum));
             eidx[cbase + a] = -1;
+            if (p.tree_mode == CUMIND_TREE_MINMAX_DISCOUNT) p.tv.reward[tt * p.tv.N + cbase + a] = 0.0f;
         }
         if (lane == 0) {
             eidx[leaf] = k;
             p.tv.exp_node[tt * (p.tv.S_max + 1) + k] = leaf;
             p.tv.n_expanded[t] = k + 1;
             leaf_value[t] = lg[A_net];
+            if (p.tree_mode == CUMIND_TREE_MINMAX_DISCOUNT) p.tv.reward[tt * p.tv.N + leaf] = lg[A_net + 1];
         }
     }
+}
+
+// ---- CUMIND_TREE_MINMAX_DISCOUNT: the optional textbook rules (oracle/cumind_oracle.c cmo_search_one_mm) --------------
+// score = vs + ((c_puct*prior)*sqrt(N_parent))/(1+n), vs = 0 if n == 0 else normalise(reward + discount*(W/n)); IEEE
+// float64 operations in that order.  Returned as an order-preserving integer key with the rules of Python's max()
+// (-0 == +0; a NaN wins only as the first candidate).
+CM_DEVICE long long mm_score_key(const Node nd, double prior, double reward, double sqrtN, double c_puct, double discount, double mn,
+                                 double mx, bool first) {
+    const long long PINF = 0x7ff0000000000000LL, NINF = (long long)0xfff0000000000000ULL;
+    const double explo = __ddiv_rn(__dmul_rn(__dmul_rn(c_puct, prior), sqrtN), (double)(1 + nd.visit));
+    double vs = 0.0;
+    if (nd.visit != 0) {
+        const double x = __dadd_rn(reward, __dmul_rn(discount, __ddiv_rn(nd.value_sum, (double)nd.visit)));
+        vs = mx > mn ? __ddiv_rn(__dsub_rn(x, mn), __dsub_rn(mx, mn)) : x;
+    }
+    long long b = __double_as_longlong(__dadd_rn(vs, explo));
+    const long long mag = b & 0x7fffffffffffffffLL;
+    b = mag > PINF ? (first ? PINF : NINF) : (mag == 0 ? 0LL : b);
+    return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+
+// selection: from the root down while the node is expanded; lanes share the children of the current node, the first
+// maximum in action order wins (warp arg-max on (key, lower action))
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) select_mm_kernel(const StepParams p) {
+    const int lane = threadIdx.x & 31;
+    const int t = warp_tree_index();
+    if (t >= p.tv.B) return;
+    const size_t tt = (size_t)t;
+    const int A = p.tv.A;
+    const Node* nodes = p.tv.nodes + tt * p.tv.N;
+    const int32_t* eidx = p.tv.child_eidx + tt * p.tv.N;
+    const float* reward = p.tv.reward + tt * p.tv.N;
+    const double* rprior = p.tv.root_prior + tt * A;
+    const double mn = p.tv.minmax[2 * tt], mx = p.tv.minmax[2 * tt + 1];
+    int* path = p.tv.path + tt * (p.tv.S_max + 2);
+    int node = 0, plen = 0;
+    int e = eidx[0];
+    while (e >= 0) {
+        const int base = 1 + e * A;
+        const double sqrtN = __dsqrt_rn((double)load_node(nodes + node).visit);
+        long long best = 0;
+        int best_a = 0x7fffffff;
+        for (int a = lane; a < A; a += 32) {
+            const Node nd = load_node(nodes + base + a);
+            const double pr = node == 0 ? rprior[a] : (double)nd.prior;
+            const long long key = mm_score_key(nd, pr, (double)reward[base + a], sqrtN, p.c_puct, p.discount, mn, mx, a == 0);
+            if (best_a == 0x7fffffff || key > best) { best = key; best_a = a; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const long long ok = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oa = __shfl_xor_sync(0xffffffffu, best_a, off);
+            if (oa != 0x7fffffff && (best_a == 0x7fffffff || ok > best || (ok == best && oa < best_a))) { best = ok; best_a = oa; }
+        }
+        if (lane == 0) path[plen] = node;
+        ++plen;
+        node = base + best_a;
+        e = eidx[node];
+    }
+    if (lane == 0) {
+        p.tv.path_len[t] = plen;
+        p.tv.leaf[t] = node;
+        p.tv.depth_sum[t] += plen;
+    }
+}
+
+// backup: the leaf first (it is counted), then its ancestors up to the root; G <- reward + discount*G on the way
+__global__ void backup_mm_kernel(const StepParams p, const float* __restrict__ leaf_value) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.tv.B) return;
+    const size_t tt = (size_t)t;
+    Node* nodes = p.tv.nodes + tt * p.tv.N;
+    const float* reward = p.tv.reward + tt * p.tv.N;
+    const int* path = p.tv.path + tt * (p.tv.S_max + 2);
+    const int plen = p.tv.path_len[t], leaf = p.tv.leaf[t];
+    double mn = p.tv.minmax[2 * tt], mx = p.tv.minmax[2 * tt + 1];
+    double G = (double)leaf_value[t];
+    for (int i = plen; i >= 0; --i) {
+        const int nd = i == plen ? leaf : path[i];
+        Node r = load_node(nodes + nd);
+        r.value_sum = __dadd_rn(r.value_sum, G);
+        r.visit += 1;
+        store_node(nodes + nd, r.value_sum, r.visit, r.prior);
+        const double rew = (double)reward[nd];
+        const double q = __dadd_rn(rew, __dmul_rn(p.discount, __ddiv_rn(r.value_sum, (double)r.visit)));
+        if (q < mn) mn = q;
+        if (q > mx) mx = q;
+        G = __dadd_rn(rew, __dmul_rn(p.discount, G));
+    }
+    p.tv.minmax[2 * tt] = mn;
+    p.tv.minmax[2 * tt + 1] = mx;
 }
 
 // ---- backup (mcts.py:199-203) -------------------------------------------------------------------
@@ -288,6 +388,14 @@ cudaError_t launch_expand(const StepParams& p, float* leaf_value, cudaStream_t s
 }
 cudaError_t launch_backup(const StepParams& p, const float* leaf_value, cudaStream_t st) {
     backup_kernel<<<warp_grid(p.tv.B), kWarpsPerBlock * 32, 0, st>>>(p, leaf_value);
+    return cudaGetLastError();
+}
+cudaError_t launch_select_mm(const StepParams& p, cudaStream_t st) {
+    select_mm_kernel<<<warp_grid(p.tv.B), kWarpsPerBlock * 32, 0, st>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_backup_mm(const StepParams& p, const float* leaf_value, cudaStream_t st) {
+    backup_mm_kernel<<<(p.tv.B + 127) / 128, 128, 0, st>>>(p, leaf_value);
     return cudaGetLastError();
 }
 cudaError_t launch_finalize(const StepParams& p, int32_t* out_visits, double* out_probs, double* out_root_value, cudaStream_t st) {

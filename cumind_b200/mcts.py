@@ -96,6 +96,8 @@ class _TreeSlab:
             "hidden": get(v.hidden, B * S1 * H * 4, np.float32, (B, S1, H)),
             "n_expanded": get(v.n_expanded, B * 4, np.int32, (B,)),
             "depth_sum": get(v.depth_sum, B * 8, np.int64, (B,)),
+            "reward": get(v.reward, B * N * 4, np.float32, (B, N)),     # CUMIND_TREE_MINMAX_DISCOUNT only (else uninitialised)
+            "minmax": get(v.minmax, B * 2 * 8, np.float64, (B, 2)),
         }
 
     def __del__(self):
@@ -121,6 +123,9 @@ class MCTS:
         self.net_warps_per_team = 0
         self.trees_per_team = 0
         self.stepwise = False            # True: one launch per phase (cumind_search_stepwise)
+        # "reference" (mcts.py semantics, the default and the parity mode) or "minmax_discount": the OPTIONAL textbook rules
+        # (min-max-normalised Q, reward + config.discount in the backup, leaf counted) — see CUMIND_TREE_MINMAX_DISCOUNT
+        self.tree_mode = getattr(config, "tree_mode", "reference")
         self.last_cfg: Optional[_native.SearchCfg] = None
 
     # ---- helpers -------------------------------------------------------------------------------
@@ -143,7 +148,10 @@ class MCTS:
         cfg.dirichlet_alpha = float(c.dirichlet_alpha)
         cfg.noise_mode = noise_mode
         cfg.net_mode = self.network.net_mode
-        cfg.tree_mode = _native.TREE_REFERENCE
+        if self.tree_mode not in ("reference", "minmax_discount"):
+            raise ValueError(f"unknown tree_mode {self.tree_mode!r}")
+        cfg.tree_mode = _native.TREE_MINMAX_DISCOUNT if self.tree_mode == "minmax_discount" else _native.TREE_REFERENCE
+        cfg.discount = float(getattr(c, "discount", 1.0))
         cfg.lanes_per_tree = int(self.lanes_per_tree)
         cfg.schedule = int(self.schedule)
         cfg.teams_per_cta = int(self.teams_per_cta)

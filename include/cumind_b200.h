@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CUMIND_ABI_VERSION 2
+#define CUMIND_ABI_VERSION 3
 
 /* ------------------------------------------------------------------------------------------
  * Network descriptor + flat parameter blob.
@@ -67,9 +67,18 @@ enum {
 
 /* Tree-policy mode. */
 enum {
-    CUMIND_TREE_REFERENCE = 0  /* exactly mcts.py: +inf for n==0, no min-max Q, undiscounted
+    CUMIND_TREE_REFERENCE = 0, /* exactly mcts.py: +inf for n==0, no min-max Q, undiscounted
                                   backup of parents only, root backed up twice (mcts.py:51-65,
-                                  157-203).                                                   */
+                                  157-203).  The default, and the only mode parity with the
+                                  reference is defined on.                                   */
+    CUMIND_TREE_MINMAX_DISCOUNT = 1
+                               /* OPTIONAL textbook-MuZero rules the reference does NOT implement (they are what
+                                  mcts.py:51-65, 199-203 deviate from): score = normalise(reward + discount*W/n)
+                                  (0 while unvisited) + ((c_puct*prior)*sqrt(N_parent))/(1+n) with per-tree min-max
+                                  bounds of the backed-up q values; the backup runs from the leaf (counted) to the
+                                  root (once) with G <- reward + discount*G.  Defined by oracle/cumind_oracle.c
+                                  (cmo_search_mm) and oracle/mcts_minmax.py; float64 statistics, IEEE operations in
+                                  the order written there.  Runs on the one-launch-per-phase kernels.            */
 };
 
 typedef struct cumind_search_cfg {
@@ -92,6 +101,7 @@ typedef struct cumind_search_cfg {
     int32_t teams_per_cta;        /* team schedule: 0 = auto, else 1..7                      */
     int32_t net_warps_per_team;   /* team schedule: 0 = auto (4), else 1..8                  */
     int32_t trees_per_team;       /* team schedule: 0 = auto, else tree slots used per batch */
+    double  discount;             /* config.discount (config.py:49); read by CUMIND_TREE_MINMAX_DISCOUNT only */
 } cumind_search_cfg;
 
 /* How cumind_search maps the work onto the GPU (all produce identical results):
@@ -181,6 +191,8 @@ typedef struct cumind_tree_view {
     int32_t* leaf;         /* [B]          scratch: slot of the selected leaf                */
     int32_t* n_expanded;   /* [B]          expansions so far (root included)                 */
     int64_t* depth_sum;    /* [B]          sum of path lengths over all simulations          */
+    float*   reward;       /* [B,N]        CUMIND_TREE_MINMAX_DISCOUNT: the dynamics reward of each expanded node */
+    double*  minmax;       /* [B,2]        CUMIND_TREE_MINMAX_DISCOUNT: bounds {min, max} of the backed-up q values */
 } cumind_tree_view;
 int cumind_tree_get_view(const cumind_tree* tree, cumind_tree_view* out);
 

@@ -459,3 +459,139 @@ CMO_EXPORT int cmo_search(const cumind_net_desc* d, const float* P, const float*
     free(scratch); free(path);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* OPTIONAL tree mode CUMIND_TREE_MINMAX_DISCOUNT (include/cumind_b200.h) — NOT the reference.    */
+/* The reference's MCTS (mcts.py:51-65, 157-203) has no min-max normalisation, no discount, no   */
+/* reward in the backup and never counts the leaf; BASELINE.json's north_star names the textbook */
+/* MuZero rules as a mode, and this is its definition (parity for this mode is against THIS      */
+/* restatement and oracle/mcts_minmax.py; there is no reference implementation to pin it to).    */
+/*   score(child)  = vs + ((c_puct*prior)*sqrt(N_parent))/(1+n),  N_parent = parent.visit_count   */
+/*                   vs = 0 if n == 0 else normalise(reward + discount*(W/n))                     */
+/*   normalise(x)  = (x - mn)/(mx - mn) if mx > mn else x      (mn, mx: per-tree bounds)          */
+/*   select        = first maximum in action order (Python max), from the root down to a leaf    */
+/*   expand        = hidden, reward = dynamics(parent.hidden, action); priors, value = prediction */
+/*   backup        = for node in reversed(path incl. the leaf): W += G; n += 1;                   */
+/*                   q = reward + discount*(W/n); mn = q if q < mn; mx = q if q > mx;             */
+/*                   G = reward + discount*G         (the root's reward is 0, it is counted once) */
+/* All statistics float64, one correctly rounded operation each, in the order written.          */
+/* ------------------------------------------------------------------------------------------ */
+static inline double cmo_mm_norm(double x, double mn, double mx) {
+    return mx > mn ? (x - mn) / (mx - mn) : x;
+}
+static inline double cmo_mm_score(int32_t n, double W, double prior, double reward, int32_t n_parent, double c_puct,
+                                  double discount, double mn, double mx) {
+    double explo = ((c_puct * prior) * sqrt((double)n_parent)) / (double)(1 + n);
+    double vs = 0.0;
+    if (n != 0) vs = cmo_mm_norm(reward + discount * (W / (double)n), mn, mx);
+    return vs + explo;
+}
+
+static int64_t cmo_search_one_mm(const cumind_net_desc* d, const cmo_layout* lo, const float* P,
+                                 const float* root_h, int S, int S_max, int A_tree, double c_puct, double discount,
+                                 double frac, const double* noise,
+                                 int32_t* visit, double* value_sum, float* prior, double* root_prior, float* reward,
+                                 double* minmax, int32_t* child_eidx, int32_t* exp_node, float* hidden,
+                                 int32_t* path, float* scratch) {
+    int H = d->hidden_dim, A_net = d->action_space_size;
+    int N = 1 + A_tree * (S_max + 1);
+    float* logits = scratch + 3 * H;
+    float* probs = logits + A_net;
+    for (int i = 0; i < N; ++i) { visit[i] = 0; value_sum[i] = 0.0; prior[i] = 0.0f; reward[i] = 0.0f; child_eidx[i] = -1; }
+    for (int i = 0; i <= S_max; ++i) exp_node[i] = -1;
+    double mn = INFINITY, mx = -INFINITY;
+    cmo_prediction_row(d, lo, P, root_h, logits, NULL);
+    cmo_softmax(logits, A_net, probs);
+    prior[0] = 1.0f;
+    child_eidx[0] = 0;
+    exp_node[0] = 0;
+    memcpy(hidden, root_h, sizeof(float) * H);
+    for (int a = 0; a < A_tree; ++a) {
+        prior[1 + a] = probs[a];
+        double p = (double)probs[a];
+        if (noise) p = p * (1.0 - frac) + noise[a] * frac;
+        root_prior[a] = p;
+    }
+    int n_exp = 1;
+    int64_t depth_sum = 0;
+    for (int s = 0; s < S; ++s) {
+        int node = 0, plen = 0;
+        while (child_eidx[node] >= 0) {
+            int base = 1 + child_eidx[node] * A_tree;
+            int best = 0;
+            double best_score = 0.0;
+            for (int a = 0; a < A_tree; ++a) {
+                int c = base + a;
+                double pr = (node == 0) ? root_prior[a] : (double)prior[c];
+                double sc = cmo_mm_score(visit[c], value_sum[c], pr, (double)reward[c], visit[node], c_puct, discount, mn, mx);
+                if (a == 0 || sc > best_score) { best = a; best_score = sc; }
+            }
+            path[plen++] = node;
+            node = base + best;
+        }
+        depth_sum += plen;
+        int parent_e = (node - 1) / A_tree;
+        int action = (node - 1) % A_tree;
+        float* leaf_h = hidden + (size_t)n_exp * H;
+        float rew;
+        cmo_dynamics_row(d, lo, P, hidden + (size_t)parent_e * H, action, leaf_h, &rew, scratch);
+        float value;
+        cmo_prediction_row(d, lo, P, leaf_h, logits, &value);
+        cmo_softmax(logits, A_net, probs);
+        reward[node] = rew;
+        child_eidx[node] = n_exp;
+        exp_node[n_exp] = node;
+        for (int a = 0; a < A_tree; ++a) prior[1 + n_exp * A_tree + a] = probs[a];
+        n_exp++;
+        double G = (double)value;
+        for (int i = plen; i >= 0; --i) {          /* the leaf first, then its ancestors up to the root */
+            int nd = i == plen ? node : path[i];
+            value_sum[nd] = value_sum[nd] + G;
+            visit[nd] += 1;
+            double r = (double)reward[nd];
+            double q = r + discount * (value_sum[nd] / (double)visit[nd]);
+            if (q < mn) mn = q;
+            if (q > mx) mx = q;
+            G = r + discount * G;
+        }
+    }
+    minmax[0] = mn;
+    minmax[1] = mx;
+    return depth_sum;
+}
+
+CMO_EXPORT int cmo_search_mm(const cumind_net_desc* d, const float* P, const float* root_hidden, int B,
+                             int S, int S_max, int A_cfg, double c_puct, double discount, double frac,
+                             const double* noise, int32_t* visit, double* value_sum, float* prior, double* root_prior,
+                             float* reward, double* minmax, int32_t* child_eidx, int32_t* exp_node, float* hidden,
+                             int32_t* out_visits, double* out_probs, double* out_root_value, int64_t* depth_sum) {
+    if (!cmo_valid(d) || S < 0 || S > S_max || A_cfg <= 0) return 1;
+    cmo_layout lo; cmo_make_layout(d, &lo);
+    int H = d->hidden_dim, A_net = d->action_space_size;
+    int A_tree = A_cfg < A_net ? A_cfg : A_net;
+    int N = 1 + A_tree * (S_max + 1);
+    int32_t* path = (int32_t*)malloc(sizeof(int32_t) * (S_max + 2));
+    float* scratch = (float*)malloc(sizeof(float) * (3 * H + 2 * A_net));
+    for (int b = 0; b < B; ++b) {
+        int64_t ds = cmo_search_one_mm(d, &lo, P, root_hidden + (size_t)b * H, S, S_max, A_tree, c_puct, discount, frac,
+                                       noise ? noise + (size_t)b * A_tree : NULL,
+                                       visit + (size_t)b * N, value_sum + (size_t)b * N, prior + (size_t)b * N,
+                                       root_prior + (size_t)b * A_tree, reward + (size_t)b * N, minmax + (size_t)b * 2,
+                                       child_eidx + (size_t)b * N, exp_node + (size_t)b * (S_max + 1),
+                                       hidden + (size_t)b * (S_max + 1) * H, path, scratch);
+        if (depth_sum) depth_sum[b] = ds;
+        const int32_t* v = visit + (size_t)b * N;
+        int64_t total = 0;
+        for (int a = 0; a < A_tree; ++a) total += v[1 + a];
+        for (int a = 0; a < A_cfg; ++a) {
+            int32_t c = a < A_tree ? v[1 + a] : 0;
+            if (out_visits) out_visits[(size_t)b * A_cfg + a] = c;
+            if (out_probs)
+                out_probs[(size_t)b * A_cfg + a] = total == 0 ? 1.0 / (double)A_cfg : (double)c / (double)total;
+        }
+        if (out_root_value)
+            out_root_value[b] = v[0] == 0 ? 0.0 : value_sum[(size_t)b * N] / (double)v[0];
+    }
+    free(scratch); free(path);
+    return 0;
+}

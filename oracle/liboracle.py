@@ -148,3 +148,38 @@ def search(desc: NetDesc, params: np.ndarray, root_hidden: np.ndarray, num_simul
     assert rc == 0, rc
     out["A"] = A
     return out
+
+
+def search_minmax(desc: NetDesc, params: np.ndarray, root_hidden: np.ndarray, num_simulations: int, action_space_size: int,
+                  c_puct: float, discount: float, exploration_fraction: float = 0.25, noise: Optional[np.ndarray] = None,
+                  s_max: Optional[int] = None) -> Dict[str, np.ndarray]:
+    """cmo_search_mm: the OPTIONAL min-max-normalised / discounted tree mode (not the reference's semantics; defined in
+    cumind_oracle.c).  Same arrays as search() plus reward [B,N] float32 and minmax [B,2] float64."""
+    root_hidden = np.ascontiguousarray(root_hidden, dtype=np.float32)
+    params = np.ascontiguousarray(params, dtype=np.float32)
+    B, H = root_hidden.shape
+    S = int(num_simulations)
+    S_max = S if s_max is None else int(s_max)
+    A_cfg = int(action_space_size)
+    A = min(A_cfg, desc.action_space_size)
+    N = 1 + A * (S_max + 1)
+    if noise is not None:
+        noise = np.ascontiguousarray(noise, dtype=np.float64)
+        assert noise.shape == (B, A)
+    out = {
+        "visit": np.empty((B, N), np.int32), "value_sum": np.empty((B, N), np.float64),
+        "prior": np.empty((B, N), np.float32), "root_prior": np.empty((B, A), np.float64),
+        "reward": np.empty((B, N), np.float32), "minmax": np.empty((B, 2), np.float64),
+        "child_eidx": np.empty((B, N), np.int32), "exp_node": np.empty((B, S_max + 1), np.int32),
+        "hidden": np.zeros((B, S_max + 1, H), np.float32),
+        "out_visits": np.empty((B, A_cfg), np.int32), "out_probs": np.empty((B, A_cfg), np.float64),
+        "out_root_value": np.empty((B,), np.float64), "depth_sum": np.empty((B,), np.int64),
+    }
+    rc = lib().cmo_search_mm(C.byref(desc), _p(params), _p(root_hidden), C.c_int(B), C.c_int(S), C.c_int(S_max), C.c_int(A_cfg),
+                             C.c_double(c_puct), C.c_double(discount), C.c_double(exploration_fraction), _p(noise),
+                             _p(out["visit"]), _p(out["value_sum"]), _p(out["prior"]), _p(out["root_prior"]),
+                             _p(out["reward"]), _p(out["minmax"]), _p(out["child_eidx"]), _p(out["exp_node"]), _p(out["hidden"]),
+                             _p(out["out_visits"]), _p(out["out_probs"]), _p(out["out_root_value"]), _p(out["depth_sum"]))
+    assert rc == 0, rc
+    out["A"] = A
+    return out

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), name
     assert set(names) == set(_native.EXPORTS)
-    assert lib.cumind_abi_version() == 2
+    assert lib.cumind_abi_version() == 3
 
 
 def test_param_count_and_tree_bytes_without_a_gpu():
