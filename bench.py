@@ -310,7 +310,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
     agent.network.load_state(P.unflatten(blob, OBS_SHAPE, A, H, L, CC))
     agent.update_target_network()
     agent.mcts.lanes_per_tree = args.lanes
-    agent.mcts.schedule = {"auto": 0, "warp": 1, "team": 2}[args.schedule]
+    agent.mcts.schedule = {"auto": 0, "warp": 1, "team": 2, "tensor": 4}[args.schedule]
     agent.mcts.teams_per_cta, agent.mcts.net_warps_per_team, agent.mcts.trees_per_team = args.teams, args.net_warps, args.trees_per_team
     net, mcts = agent.network, agent.mcts
     dev = torch.device("cuda", local_rank)
@@ -443,7 +443,7 @@ def run_native(args, rank: int, world: int, local_rank: int):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("search_fused_dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "search_team_kernel" if mcts.plan(B)["schedule"] == "team" else "search_fused_kernel", "kernel_ms": kern_ms_mean, "algorithmic_bytes_per_sim": algorithmic_bytes_per_sim(dbar),
+                "kernel": {"team": "search_team_kernel", "warp": "search_fused_kernel", "tensor-core": "search_tc_kernel"}.get(mcts.plan(B)["schedule"], "stepwise"), "kernel_ms": kern_ms_mean, "algorithmic_bytes_per_sim": algorithmic_bytes_per_sim(dbar),
                 "mean_path_length": dbar, "peak_source": peak_src, "encoder_ms": enc_ms_mean,
                 "kernel_ms_how": "K launches of the search kernel alone after the timed steps (CUDA events, same L2 flush); encoder_ms = step - kernel"}
     if WORKLOAD.startswith("atari"):
@@ -544,7 +544,7 @@ def main():
                     help="global batch sharded across the ranks (strong scaling; BASELINE configs[3] uses 65536)")
     ap.add_argument("--sims", type=int, default=50)
     ap.add_argument("--lanes", type=int, default=0, help="lanes per tree (0 = auto)")
-    ap.add_argument("--schedule", default="auto", choices=["auto", "warp", "team"], help="cumind_search_cfg.schedule")
+    ap.add_argument("--schedule", default="auto", choices=["auto", "warp", "team", "tensor"], help="cumind_search_cfg.schedule")
     ap.add_argument("--teams", type=int, default=0, help="team schedule: teams per CTA (0 = auto)")
     ap.add_argument("--net-warps", type=int, default=0, help="team schedule: network warps per team (0 = auto)")
     ap.add_argument("--trees-per-team", type=int, default=0, help="team schedule: tree slots per team (0 = auto)")
@@ -554,8 +554,12 @@ def main():
     ap.add_argument("--sustain", type=float, default=2.5, help="seconds of back-to-back steps after the timed region (0 = skip)")
     ap.add_argument("--workload", default="cartpole", choices=["cartpole", "cartpole-h128", "atari", "atari-literal"],
                     help="cartpole = BASELINE configs[1] (the bench line); atari = configs[2], measured for profiles/ only")
+    ap.add_argument("--dtype", default="", choices=["", "float32", "bfloat16"], help="override the workload's model_dtype (bfloat16 = tcgen05 network)")
     args = ap.parse_args()
     set_workload(args.workload)
+    if args.dtype:
+        global MODEL_DTYPE
+        MODEL_DTYPE = args.dtype
     if args.workload != "cartpole":
         args.no_cpu = True
         if args.trees == 4096 and args.workload.startswith("atari"):

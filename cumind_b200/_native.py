@@ -28,7 +28,7 @@ EXPORTS = [
 NET_FP32_EXACT = 0
 NET_BF16_TC = 1
 TREE_REFERENCE, TREE_MINMAX_DISCOUNT = 0, 1
-SCHED_AUTO, SCHED_WARP, SCHED_TEAM, SCHED_TEAM_CLASSIC = 0, 1, 2, 3
+SCHED_AUTO, SCHED_WARP, SCHED_TEAM, SCHED_TEAM_CLASSIC, SCHED_TENSOR = 0, 1, 2, 3, 4
 
 
 class NetDesc(C.Structure):

@@ -829,6 +829,15 @@ extern "C" int cumind_search_stepwise(cumind_tree* t, const cumind_net* n, const
     return 0;
 }
 
+// CUMIND_NET_BF16_TC: the tensor-core search kernel when asked for, or under AUTO when the batch is large enough for it
+// to beat the fp32 kernels (include/cumind_b200.h, CUMIND_SCHED_TENSOR)
+static bool use_tensor_search(const cumind_tree* t, const cumind_net* n, const cumind_search_cfg* c) {
+    if (c->net_mode != CUMIND_NET_BF16_TC || !n->tc_ok || c->tree_mode != CUMIND_TREE_REFERENCE) return false;
+    if (c->schedule == CUMIND_SCHED_TENSOR) return true;
+    if (c->schedule != CUMIND_SCHED_AUTO) return false;
+    return (long long)t->tv.B > (long long)CUMIND_TENSOR_MIN_TREES_PER_SM * n->sm_count;
+}
+
 // pdl: d_root_hidden is written by the kernel launched just before on `stream`, which calls pdl_launch_dependents():
 // the search kernel is launched with programmatic stream serialization so that its prologue overlaps that kernel.
 static int search_impl(cumind_tree* t, const cumind_net* n, const float* d_root_hidden, const cumind_search_cfg* c,
@@ -838,17 +847,42 @@ static int search_impl(cumind_tree* t, const cumind_net* n, const float* d_root_
     if (!d_root_hidden || !d_out_visits || !d_out_probs) return fail("cumind_search: NULL device pointer");
     FusedPlan pl;
     std::string why;
-    // The fused kernels compute the in-search MLP in fp32-exact arithmetic.  They are also what
-    // CUMIND_NET_BF16_TC runs when the parameters fit their shared-memory staging: at these layer widths
-    // one fused launch beats 3 launches per simulation through the tensor-core expansion kernel
-    // (measured in profiles/README.md), and it is more accurate.  cumind_search_stepwise always
-    // honours net_mode (tcgen05 expansion kernel in bf16 mode).
-    if (c->schedule < 0 || c->schedule > CUMIND_SCHED_TEAM_CLASSIC) return fail("unknown schedule");
+    // CUMIND_NET_FP32_EXACT: the fused kernels below (pinned-order fp32 SIMT network).  CUMIND_NET_BF16_TC: the fused
+    // tensor-core kernel (search_tc.cu: tcgen05 MMAs per simulation, 128 trees per CTA).
+    if (c->schedule < 0 || c->schedule > CUMIND_SCHED_TENSOR) return fail("unknown schedule");
+    if (c->schedule == CUMIND_SCHED_TENSOR && c->net_mode != CUMIND_NET_BF16_TC) return fail("CUMIND_SCHED_TENSOR needs CUMIND_NET_BF16_TC");
     if (c->tree_mode == CUMIND_TREE_MINMAX_DISCOUNT)   // the optional mode exists on the one-launch-per-phase kernels only
         return cumind_search_stepwise(t, n, d_root_hidden, c, d_noise, d_out_visits, d_out_probs, d_out_root_value, stream);
+    if (use_tensor_search(t, n, c)) {
+        SearchTcParams q{};
+        q.tv = t->tv;
+        q.pack = n->d_tcpack;
+        q.pk = n->tpk;
+        q.pack_f32 = n->d_pack;
+        q.pkf = n->pk;
+        q.root_hidden = d_root_hidden;
+        q.noise = d_noise;
+        q.out_visits = d_out_visits;
+        q.out_probs = d_out_probs;
+        q.out_root_value = d_out_root_value;
+        q.S = c->num_simulations;
+        q.A_cfg = c->action_space_size;
+        q.c_puct = c->c_puct;
+        q.frac = c->exploration_fraction;
+        q.one_minus_frac = 1.0 - c->exploration_fraction;
+        q.alpha = c->dirichlet_alpha;
+        q.noise_mode = c->noise_mode;
+        q.seed = c->seed;
+        q.tree_base = c->tree_index_base;
+        q.n_sqrt = 2 * t->tv.S_max + 4;
+        q.pdl = pdl ? 1 : 0;
+        CM_CUDA(launch_search_tc(q, n->sm_count, (cudaStream_t)stream));
+        g_launches += 1;
+        return 0;
+    }
     if (c->schedule != CUMIND_SCHED_WARP) {
         TeamPlan tp;
-        if (plan_team(t, n, c, tp, why) == 0 && (c->schedule >= CUMIND_SCHED_TEAM || team_is_preferred(tp, n->sm_count))) {
+        if (plan_team(t, n, c, tp, why) == 0 && (c->schedule == CUMIND_SCHED_TEAM || c->schedule == CUMIND_SCHED_TEAM_CLASSIC || team_is_preferred(tp, n->sm_count))) {
             tp.p.root_hidden = d_root_hidden;
             tp.p.noise = d_noise;
             tp.p.out_visits = d_out_visits;
@@ -897,9 +931,13 @@ extern "C" int cumind_search_plan(const cumind_tree* t, const cumind_net* n, con
     if (!t || !n || !c || !out) return fail("cumind_search_plan: NULL argument");
     std::string why;
     for (int i = 0; i < 8; ++i) out[i] = 0;
+    if (use_tensor_search(t, n, c)) {
+        out[0] = 4; out[1] = 1; out[3] = (t->tv.B + 127) / 128; out[4] = 128;   // fused tensor-core kernel: one thread per tree
+        return 0;
+    }
     if (c->schedule != CUMIND_SCHED_WARP) {
         TeamPlan tp;
-        if (plan_team(t, n, c, tp, why) == 0 && (c->schedule >= CUMIND_SCHED_TEAM || team_is_preferred(tp, n->sm_count))) {
+        if (plan_team(t, n, c, tp, why) == 0 && (c->schedule == CUMIND_SCHED_TEAM || c->schedule == CUMIND_SCHED_TEAM_CLASSIC || team_is_preferred(tp, n->sm_count))) {
             out[0] = CUMIND_SCHED_TEAM; out[1] = tp.G; out[2] = tp.p.tpt; out[3] = tp.grid; out[4] = tp.block;
             out[5] = (int32_t)tp.smem; out[6] = tp.p.n_team; out[7] = tp.p.nmw + 256 * tp.p.lw;
             return 0;

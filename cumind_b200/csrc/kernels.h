@@ -122,6 +122,27 @@ cudaError_t launch_recurrent_tc(const unsigned char* pack, const TcPackLayout& p
 cudaError_t launch_expand_tc(const unsigned char* pack, const TcPackLayout& pk, int sm_count, const TreeView& tv, float* leaf_value,
                              cudaStream_t st);
 
+// search_tc.cu — the whole search in one launch with the per-simulation network on tcgen05 (CUMIND_NET_BF16_TC)
+struct SearchTcParams {
+    TreeView tv;
+    const unsigned char* pack;   // TcPackLayout bytes (bf16 weight tiles, fp32 biases and embedding)
+    TcPackLayout pk;
+    const float* pack_f32;       // PackLayout (fp32): the root prediction is computed in pinned-order fp32
+    PackLayout pkf;
+    const float* root_hidden;    // [B][H]
+    const double* noise;         // [B][A] or nullptr
+    int32_t* out_visits;         // [B][A_cfg]
+    double* out_probs;           // [B][A_cfg]
+    double* out_root_value;      // [B] or nullptr
+    int S, A_cfg;
+    double c_puct, frac, one_minus_frac, alpha;
+    int noise_mode;
+    unsigned long long seed, tree_base;
+    int n_sqrt;                  // entries of the sqrt / reciprocal tables (2 S_max + 4)
+    int pdl;                     // host only: programmatic dependent launch
+};
+cudaError_t launch_search_tc(const SearchTcParams& p, int sm_count, cudaStream_t st);
+
 // conv_tc.cu — image encoder as implicit GEMM on tcgen05 (bf16 mode)
 bool conv_tc_supported(const cumind_net_desc& d);
 ConvTcPackLayout make_conv_tc_pack_layout(const cumind_net_desc& d);

@@ -252,7 +252,7 @@ class MCTS:
         cfg = self._cfg(0)
         _native.check(self._lib.cumind_search_plan(tree.handle, self.network._handle, C.byref(cfg), C.byref(out)))
         v = [int(x) for x in out]
-        plan = {"fused": 1 if v[0] else 0, "schedule": {0: "stepwise", 1: "warp", 2: "team"}[v[0]], "lanes_per_tree": v[1],
+        plan = {"fused": 1 if v[0] else 0, "schedule": {0: "stepwise", 1: "warp", 2: "team", 4: "tensor-core"}[v[0]], "lanes_per_tree": v[1],
                 "grid": v[3], "block": v[4], "smem_bytes": v[5]}
         if v[0] == _native.SCHED_TEAM:
             plan.update(trees_per_team=v[2], teams_per_cta=v[6], net_warps_per_team=v[7] % 256, layer_warpgroup_resident_k=v[7] // 256)

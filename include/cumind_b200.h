@@ -108,11 +108,21 @@ typedef struct cumind_search_cfg {
  *   WARP  search_fused.cu: every group of `lanes_per_tree` lanes runs the whole search of one tree
  *   TEAM  search_team.cu : warp-specialised teams (tree-walk warps + network warps); with
  *         hidden_dim 64 the dynamics layers of all teams run on a dedicated layer warpgroup whose weights are
- *         partly register-resident */
+ *         register-resident
+ * CUMIND_NET_BF16_TC adds
+ *   TENSOR search_tc.cu : 128 trees per CTA (thread = tree = row of a UMMA tile), dynamics + prediction of every
+ *         simulation as tcgen05 MMAs with TMEM accumulators; results are those of the bf16 network, not bit-pinned.
+ *         AUTO picks it when the batch is large enough for it to win (more than CUMIND_TENSOR_MIN_TREES_PER_SM trees
+ *         per SM: measured per search 0.73 / 0.92 / 1.85 ms against 0.83 / 1.72 / 3.29 ms for the fp32 kernels at 16 384 /
+ *         32 768 / 65 536 trees, and 0.73 against 0.53 ms at 8 192); below that AUTO keeps the
+ *         fp32-exact fused kernels, which are faster there and exact — cumind_search_plan reports the choice, and
+ *         schedule = CUMIND_SCHED_TENSOR forces the tensor-core kernel at any size. */
+#define CUMIND_TENSOR_MIN_TREES_PER_SM 80
 #define CUMIND_SCHED_AUTO 0
 #define CUMIND_SCHED_WARP 1
 #define CUMIND_SCHED_TEAM 2
 #define CUMIND_SCHED_TEAM_CLASSIC 3 /* TEAM without the layer warpgroup (the network warps compute the layers) */
+#define CUMIND_SCHED_TENSOR 4       /* CUMIND_NET_BF16_TC only: search_tc.cu, the per-simulation network on tcgen05 */
 
 typedef struct cumind_net  cumind_net;   /* opaque: packed parameters on one device  */
 typedef struct cumind_tree cumind_tree;  /* opaque: view over a caller-owned SoA slab */
