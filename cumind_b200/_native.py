@@ -23,6 +23,7 @@ EXPORTS = [
     "cumind_launch_count", "cumind_selftest_division", "cumind_adamw_step", "cumind_adamw_step_dev", "cumind_net_update_params_device",
     "cumind_sumtree_create", "cumind_sumtree_destroy", "cumind_sumtree_tree_size", "cumind_sumtree_clear", "cumind_sumtree_update",
     "cumind_sumtree_sample", "cumind_sumtree_read", "cumind_search_from_obs", "cumind_net_reserve",
+    "cumind_train_supported", "cumind_train_work_bytes", "cumind_train_loss_grad",
 ]
 
 NET_FP32_EXACT = 0
@@ -114,6 +115,10 @@ def load():
     lib.cumind_adamw_step.argtypes = [vp, vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, C.c_int64, f32, vp]
     lib.cumind_adamw_step_dev.argtypes = [vp, vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, vp, f32, vp]
     lib.cumind_net_update_params_device.argtypes = [vp, vp, sz, vp]
+    lib.cumind_train_supported.argtypes = [C.POINTER(NetDesc), i32]
+    lib.cumind_train_work_bytes.argtypes = [C.POINTER(NetDesc), i32]
+    lib.cumind_train_work_bytes.restype = C.c_size_t
+    lib.cumind_train_loss_grad.argtypes = [C.POINTER(NetDesc), vp, vp, vp, vp, vp, vp, i32, i32, vp, sz, vp, vp, vp]
     i64 = C.c_int64
     lib.cumind_sumtree_create.argtypes = [i64, C.POINTER(vp)]
     lib.cumind_sumtree_destroy.argtypes = [vp]

@@ -1037,6 +1037,28 @@ extern "C" int cumind_adamw_step(float* d_params, const float* d_grads, float* d
     return 0;
 }
 
+// Trainer.compute_losses + nnx.value_and_grad (trainer.py:88-95, 172-205) for vector-observation networks: see train_fused.cu.
+extern "C" int cumind_train_supported(const cumind_net_desc* desc, int32_t K) {
+    return desc_valid(desc) && train_fused_supported(*desc, K) ? 1 : 0;
+}
+extern "C" size_t cumind_train_work_bytes(const cumind_net_desc* desc, int32_t B) {
+    if (!desc_valid(desc) || B <= 0) return 0;
+    return train_fused_work_bytes(*desc, B);
+}
+extern "C" int cumind_train_loss_grad(const cumind_net_desc* desc, const float* d_params, const float* d_obs, const int32_t* d_actions,
+                                      const float* d_value_targets, const float* d_policy_targets, const float* d_reward_targets, int32_t B,
+                                      int32_t K, void* d_work, size_t work_bytes, float* d_grad, float* d_losses4, void* stream) {
+    if (!desc_valid(desc) || !d_params || !d_obs || !d_actions || !d_value_targets || !d_policy_targets || !d_reward_targets || !d_work ||
+        !d_grad || !d_losses4 || B <= 0)
+        return fail("cumind_train_loss_grad: bad argument");
+    if (!train_fused_supported(*desc, K)) return fail("cumind_train_loss_grad: network shape not supported (see cumind_train_supported)");
+    if (work_bytes < train_fused_work_bytes(*desc, B)) return fail("cumind_train_loss_grad: work buffer too small");
+    CM_CUDA(launch_train_fwd_bwd(*desc, d_params, d_obs, d_actions, d_value_targets, d_policy_targets, d_reward_targets, B, K, (float*)d_work,
+                                 d_grad, d_losses4, (cudaStream_t)stream));
+    g_launches += 2;
+    return 0;
+}
+
 // Same step with the counter on the device (d_step is incremented first): the launch arguments do not
 // change between steps, so the whole train step can be replayed from a CUDA graph.
 extern "C" int cumind_adamw_step_dev(float* d_params, const float* d_grads, float* d_m, float* d_v, const uint8_t* d_mask, size_t n,

@@ -159,6 +159,12 @@ cudaError_t launch_adamw_dev_step(float* p, const float* g, float* m, float* v, 
 cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, const unsigned char* mask, size_t n, float lr, float b1,
                          float b2, float eps, float wd, long long step, float grad_scale, cudaStream_t st);
 
+// train_fused.cu — loss + gradient of the train step in one kernel (vector observations, hidden_dim 32 / 64)
+bool train_fused_supported(const cumind_net_desc& d, int K);
+size_t train_fused_work_bytes(const cumind_net_desc& d, int B);
+cudaError_t launch_train_fwd_bwd(const cumind_net_desc& d, const float* blob, const float* obs, const int32_t* actions, const float* tv,
+                                 const float* tp, const float* tr, int B, int K, float* work, float* grad, float* losses, cudaStream_t st);
+
 // replay.cu — TreeBuffer's sum tree on the device (memory.py:190-299)
 cudaError_t launch_sumtree_update(double* tree, long long n_nodes, int depth, const long long* idx, const double* pri, long long n,
                                   cudaStream_t st);

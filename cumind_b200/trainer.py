@@ -7,11 +7,13 @@
                                                       batch-1 call per sampled item
   Trainer.compute_losses()        trainer.py:172-205  value MSE, policy CE, reward MSE over a K-step unroll,
                                                       same value / policy target at every step, /(K+1), /K
-The unrolled forward/backward is dense library GEMM work (torch autograd over views of ONE flat fp32
-parameter tensor in the blob layout of include/cumind_b200.h); what is hand-written is the optimiser:
-`cumind_adamw_step` = optax.adamw fused with the 1/world scaling of the gradient, after one NCCL
-all-reduce of the flat gradient (the only collective in the product).  The updated blob is pushed to
-the search kernels with `cumind_net_update_params_device`.
+For vector-observation networks (hidden_dim 32 / 64: every BASELINE configuration) the loss and its gradient are ONE
+hand-written kernel, `cumind_train_loss_grad` (csrc/train_fused.cu: the whole K-step unroll forward and backward on
+chip, per-CTA partial gradients summed in a fixed order); image encoders and other widths go through torch autograd
+over views of the same flat fp32 parameter tensor (blob layout of include/cumind_b200.h).  The optimiser is
+`cumind_adamw_step` = optax.adamw fused with the 1/world scaling of the gradient, after one NCCL all-reduce of the
+flat gradient (the only collective in the product).  The updated blob is pushed to the search kernels with
+`cumind_net_update_params_device`.
 """
 
 from __future__ import annotations
@@ -156,6 +158,9 @@ class Trainer:
         self._mask = torch.as_tensor(trainable_mask(self._dims)).to(dev)
         self.use_cuda_graph = True
         self.graph_distributed = True   # torch.distributed: two graphs around an eager all-reduce
+        # the hand-written loss + gradient kernel (train_fused.cu) when the network shape is covered; False = torch autograd
+        self.use_fused_kernel = bool(self._lib.cumind_train_supported(C.byref(net._desc), int(config.num_unroll_steps)))
+        self._fused_buf: Dict[int, Any] = {}
         self._graph, self._graph_key, self._graph_out, self._static = None, None, None, None
         self._state_stale = False
 
@@ -198,8 +203,30 @@ class Trainer:
             return forward_losses(self._flat, self._dims, torch.as_tensor(np.asarray(observations, np.float32)).to(dev),
                                   torch.as_tensor(np.asarray(actions)).to(dev), t, self.config.num_unroll_steps)
 
+    def _fwd_bwd_fused(self, observations, actions, targets):
+        """cumind_train_loss_grad: the K-step unroll forward + backward in one kernel, gradient in blob layout."""
+        B, K = int(observations.shape[0]), int(self.config.num_unroll_steps)
+        buf = self._fused_buf.get(B)
+        if buf is None:
+            dev = self._flat.device
+            need = int(self._lib.cumind_train_work_bytes(C.byref(self.agent.network._desc), B))
+            buf = (torch.empty(need, dtype=torch.uint8, device=dev), torch.empty_like(self._flat), torch.empty(4, dtype=torch.float32, device=dev))
+            self._fused_buf = {B: buf}
+        work, grad, losses = buf
+        obs = observations.to(torch.float32).contiguous()
+        act = actions.to(torch.int32).contiguous()
+        tv, tp, tr = (targets[k].to(torch.float32).contiguous() for k in ("values", "policies", "rewards"))
+        _native.check(self._lib.cumind_train_loss_grad(
+            C.byref(self.agent.network._desc), C.c_void_p(self._flat.data_ptr()), C.c_void_p(obs.data_ptr()), C.c_void_p(act.data_ptr()),
+            C.c_void_p(tv.data_ptr()), C.c_void_p(tp.data_ptr()), C.c_void_p(tr.data_ptr()), B, K, C.c_void_p(work.data_ptr()), work.numel(),
+            C.c_void_p(grad.data_ptr()), C.c_void_p(losses.data_ptr()), _stream_ptr()))
+        self.last_grad = grad
+        return {"value_loss": losses[0], "policy_loss": losses[1], "reward_loss": losses[2], "total_loss": losses[3]}, grad
+
     def _fwd_bwd(self, observations, actions, targets):
-        """loss -> grad of the flat parameter blob (torch autograd over views of it)."""
+        """loss -> grad of the flat parameter blob (the fused kernel, or torch autograd over views of the blob)."""
+        if self.use_fused_kernel and tuple(actions.shape) == (observations.shape[0], int(self.config.num_unroll_steps)):
+            return self._fwd_bwd_fused(observations, actions, targets)
         leaf = self._flat.detach().requires_grad_(True)   # fresh autograd leaf over the same storage
         losses = forward_losses(leaf, self._dims, observations, actions, targets, self.config.num_unroll_steps)
         total = losses["value_loss"] + losses["policy_loss"] + losses["reward_loss"]

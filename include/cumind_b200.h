@@ -298,6 +298,19 @@ int cumind_adamw_step_dev(float* d_params, const float* d_grads, float* d_m, flo
                           int64_t* d_step /* device counter, incremented first */, float grad_scale, void* stream);
 int cumind_net_update_params_device(cumind_net* net, const float* d_params, size_t n_params, void* stream);
 
+/* Trainer.compute_losses + nnx.value_and_grad (trainer.py:88-95, 172-205) in one kernel for vector-observation networks
+ * (hidden_dim 32 or 64, num_blocks <= 3, K = num_unroll_steps in 1..16; cumind_train_supported says whether a shape is
+ * covered): K-step unroll, value MSE + policy cross-entropy at all K+1 states against the same targets, reward MSE at the
+ * K unrolled states, divided by K+1 / K+1 / K.  d_params / d_grad are flat fp32 blobs in the layout above;
+ * d_actions [B,K] int32, d_value_targets [B], d_policy_targets [B,A], d_reward_targets [B,K];
+ * d_losses4 = {value_loss, policy_loss, reward_loss, total}.  d_work: cumind_train_work_bytes() bytes of scratch (per-CTA
+ * partial gradients, summed in a fixed order: the result is reproducible).  Asynchronous on `stream`, graph-capturable. */
+int    cumind_train_supported(const cumind_net_desc* desc, int32_t K);
+size_t cumind_train_work_bytes(const cumind_net_desc* desc, int32_t B);
+int    cumind_train_loss_grad(const cumind_net_desc* desc, const float* d_params, const float* d_obs, const int32_t* d_actions,
+                              const float* d_value_targets, const float* d_policy_targets, const float* d_reward_targets,
+                              int32_t B, int32_t K, void* d_work, size_t work_bytes, float* d_grad, float* d_losses4, void* stream);
+
 /* Replay: the sum tree of TreeBuffer (src/cumind/data/memory.py:190-299) in device memory.
  * A flat float64 array of 2*tree_size-1 nodes, tree_size = the power of two >= capacity (memory.py:204-208).
  * cumind_sumtree_update applies `_update(tree_idx[k], priority[k])` (memory.py:249-253, 212-217) for k = 0..n-1 IN

@@ -116,6 +116,48 @@ def test_gpu_train_step_matches_the_oracle():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(1024, 2, 64, 2, 5, 4), (203, 4, 64, 2, 5, 4), (37, 3, 32, 1, 1, 7), (64, 2, 64, 3, 4, 11), (9, 14, 32, 2, 14, 64)],
+                         ids=lambda s: "B%dA%dH%dL%dK%dD%d" % s)
+def test_fused_loss_and_gradient_kernel_matches_the_oracle(shape):
+    """cumind_train_loss_grad (train_fused.cu: the whole unroll forward + backward in one kernel) against the float64
+    restatement oracle/train_np.py: the three losses within 1e-5, every gradient entry within 1e-4 relative (+ 1e-6 of the
+    largest entry), at the BASELINE configs[4] shape (batch 1024, K=5, H=64) and at ragged / other shapes; and the
+    result is reproducible (fixed summation order: two runs give identical bits)."""
+    import torch
+
+    from cumind_b200 import Agent, Config
+    from cumind_b200.trainer import MemoryBuffer, Trainer
+
+    B, A, H, L, K, D = shape
+    params, obs, actions, targets, _ = _problem(B=B, A=A, H=H, L=L, K=K, D=D, seed=B + H)
+    cfg = Config(hidden_dim=H, num_blocks=L, action_space_size=A, observation_shape=(D,), num_unroll_steps=K, num_simulations=3)
+    agent = Agent(cfg)
+    agent.load_state({"network_state": params, "optimizer_state": {"count": 0}})
+    tr = Trainer(agent, MemoryBuffer(4), cfg)
+    assert tr.use_fused_kernel
+    dev = tr._flat.device
+    t_obs, t_act = torch.as_tensor(obs).to(dev), torch.as_tensor(actions).to(dev)
+    t_tg = {k: torch.as_tensor(v).to(dev) for k, v in targets.items()}
+    out, grad = tr._fwd_bwd(t_obs, t_act, t_tg)
+    want_total, want_losses, want_grads = tn.loss_and_grad(params, obs, actions, targets, K)
+    for k in want_losses:
+        assert abs(float(out[k]) - want_losses[k]) <= 1e-5 * max(1.0, abs(want_losses[k])), (k, float(out[k]), want_losses[k])
+    assert abs(float(out["total_loss"]) - want_total) <= 1e-5 * max(1.0, abs(want_total))
+    g_gpu = grad.cpu().numpy().astype(np.float64)
+    g_ref = np.concatenate([np.asarray(a, np.float64).reshape(-1) for a in _leaves(want_grads, (D,))])
+    scale = np.abs(g_ref).max()
+    bad = np.abs(g_gpu - g_ref) > 1e-4 * np.abs(g_ref) + 1e-6 * scale
+    assert not bad.any(), (int(bad.sum()), np.where(bad)[0][:10], g_gpu[bad][:5], g_ref[bad][:5])
+    first = grad.clone()
+    _, again = tr._fwd_bwd(t_obs, t_act, t_tg)
+    assert torch.equal(first, again)
+    # and the autograd path (what image encoders use) computes the same thing
+    tr.use_fused_kernel = False
+    out_a, grad_a = tr._fwd_bwd(t_obs, t_act, t_tg)
+    assert np.all(np.abs(grad_a.cpu().numpy() - g_gpu) <= 2e-4 * np.abs(g_ref) + 2e-6 * scale)
+
+
+@pytest.mark.gpu
 def test_trainer_runs_from_replay_with_bootstrapped_targets_and_image_observations():
     from cumind_b200 import Agent, Config
     from cumind_b200.envs import CartPoleVec
