@@ -59,6 +59,11 @@ def set_workload(name: str):
         raise ValueError(name)
 
 
+def set_workload_raw(state):
+    global OBS_SHAPE, A, H, L, CC, WORKLOAD, MODEL_DTYPE
+    OBS_SHAPE, A, H, L, CC, WORKLOAD, MODEL_DTYPE = state
+
+
 def encoder_flops_per_obs() -> float:
     if len(OBS_SHAPE) == 1:
         return 2.0 * OBS_SHAPE[0] * H + 2.0 * (L - 1) * H * H
@@ -271,38 +276,36 @@ def run_reference(args, rank: int, world: int):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, per_gpu: int):
-    title = ("BASELINE configs[1]: CartPole-shaped synthetic self-play" if WORKLOAD == "cartpole" else
+def workload_config(args, per_gpu: int, total_trees: int = 0):
+    title = ("BASELINE configs[3]: large-batch search, %d CartPole-shaped trees sharded over the GPUs" % total_trees if total_trees == 65536 and WORKLOAD == "cartpole" else
+             "CartPole-shaped trees, %d in total sharded over the GPUs (strong scaling)" % total_trees if total_trees > 0 and WORKLOAD == "cartpole" else
+             "BASELINE configs[1]: CartPole-shaped synthetic self-play" if WORKLOAD == "cartpole" else
              "CartPole-shaped, shipped-checkpoint width" if WORKLOAD == "cartpole-h128" else f"BASELINE configs[2] ({WORKLOAD}): image observations")
-    mode = "fp32-exact network" if MODEL_DTYPE == "float32" else "bf16 tensor-core (tcgen05) network"
+    mode = "fp32-exact network" if MODEL_DTYPE == "float32" else "bf16 tensor-core (tcgen05) network mode (search kernel: see plan)"
     return {"workload": f"{title}, B={per_gpu} trees per GPU, S={args.sims} simulations, "
                         f"obs {OBS_SHAPE}, A={A}, hidden_dim={H}, num_blocks={L}, {mode}, injected Dirichlet({ALPHA}) noise, c_puct={C_PUCT}",
             "trees_per_gpu": per_gpu, "num_simulations": args.sims, "parallelism": f"trees sharded by environment x{args.gpus}, no collective",
             "l2": "between timed steps a 256 MiB device buffer is written (L2 flush) and a second 256 MiB buffer is read (drains the dirty lines); per-step CUDA events"}
 
 
-def run_native(args, rank: int, world: int, local_rank: int):
+def measure_search(args, rank: int, world: int, local_rank: int, dist, sampler, K: int, W: int, sustain: float, total_trees: int,
+                   trees: int):
+    """One workload (the globals set by set_workload): device-resident steps, the search kernel alone, the sustained leg and
+    the end-to-end path.  Every rank runs it; the returned dict is complete on every rank (timings are max over ranks)."""
     import torch
 
     from cumind_b200 import Config, _native
     from cumind_b200 import params as P
     from cumind_b200.agent import Agent
 
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-
-        dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    S, K, W = args.sims, args.steps, args.warmup
-    tree_base = rank * args.trees
-    if args.total_trees > 0:
+    S = args.sims
+    tree_base = rank * trees
+    if total_trees > 0:
         from cumind_b200.dist import shard_bounds
 
-        lo_, hi_ = shard_bounds(args.total_trees, rank, world)
-        args.trees, tree_base = hi_ - lo_, lo_
-    B = args.trees
+        lo_, hi_ = shard_bounds(total_trees, rank, world)
+        trees, tree_base = hi_ - lo_, lo_
+    B = trees
     _, blob, obs, noise = make_inputs(B, rank)
     cfg = Config(hidden_dim=H, num_blocks=L, num_simulations=S, action_space_size=A, observation_shape=OBS_SHAPE, c_puct=C_PUCT,
                  dirichlet_alpha=ALPHA, exploration_fraction=FRAC, conv_channels=CC, model_dtype=MODEL_DTYPE)
@@ -336,10 +339,8 @@ def run_native(args, rank: int, world: int, local_rank: int):
     if args.phase_clocks:
         if rank == 0:
             print(json.dumps(phase_clocks(mcts, net.representation_network(d_obs), d_noise, tree_base, S)), flush=True)
-        return
+        return None
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     k_start = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
@@ -348,7 +349,8 @@ def run_native(args, rank: int, world: int, local_rank: int):
         dist.barrier()
     torch.cuda.synchronize()
     launches0 = _native.launch_count()
-    sampler.live = True
+    if sampler is not None:
+        sampler.live = True
     wall0 = time.perf_counter()
     for i in range(K):
         starts[i].record()
@@ -372,13 +374,13 @@ def run_native(args, rank: int, world: int, local_rank: int):
     torch.cuda.synchronize()
     kern_ms = [s.elapsed_time(e) for s, e in zip(k_start, k_end)]
     enc_ms = [max(a - b, 0.0) for a, b in zip(step_ms, kern_ms)]
-    # sustained leg: the same step back to back for >= args.sustain seconds (clocks under load for the samplers)
+    # sustained leg: the same step back to back for >= `sustain` seconds (clocks under load for the samplers)
     sustained = None
-    if args.sustain > 0:
+    if sustain > 0:
         n_sus, s0, s1 = 0, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_sus = time.perf_counter()
         s0.record()
-        while time.perf_counter() - t_sus < args.sustain:
+        while time.perf_counter() - t_sus < sustain:
             for _ in range(50):
                 step_dev()
             n_sus += 50
@@ -387,8 +389,9 @@ def run_native(args, rank: int, world: int, local_rank: int):
         torch.cuda.synchronize()
         sus_ms = s0.elapsed_time(s1)
         sustained = {"seconds": sus_ms * 1e-3, "steps": n_sus, "ms_per_step": sus_ms / n_sus,
-                     "note": "the timed step back to back without the L2 flush (working set 62 MB, L2-resident); not the headline"}
-    sampler.live = False
+                     "note": "the timed step back to back without the L2 flush (the trees stay L2-resident); not the headline"}
+    if sampler is not None:
+        sampler.live = False
     dump = mcts.dump_trees()
     dbar = float(dump["depth_sum"].mean()) / S
     visits_ok = bool(np.all(dump["visit"][:, 0] == 2 * S))
@@ -410,7 +413,6 @@ def run_native(args, rank: int, world: int, local_rank: int):
         actions, probs = agent.select_actions(obs, training=False, noise=noise)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - e0
-    sampler.stop_flag = True
 
     t = torch.tensor([total_ms, e2e_s * 1e3, statistics.mean(kern_ms), statistics.mean(enc_ms)], dtype=torch.float64, device=dev)
     if sustained is not None:
@@ -424,56 +426,141 @@ def run_native(args, rank: int, world: int, local_rank: int):
     t_trees = torch.tensor([B], dtype=torch.int64, device=dev)
     if dist is not None:
         dist.all_reduce(t_trees)
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
     sims_per_step = int(t_trees.item()) * S
     value = sims_per_step * K / (total_ms * 1e-3)
     e2e_value = sims_per_step * K / (e2e_ms * 1e-3)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+    peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+    peak, peak_src = (float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else (FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)")
     bytes_per_launch = algorithmic_bytes_per_sim(dbar) * B * S
     achieved = bytes_per_launch / (kern_ms_mean * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and WORKLOAD == "cartpole" and B == 4096:
         traffic = json.load(open(tpath)).get("search_fused_dram_bytes_per_launch")
+    plan = mcts.plan(B)
+    kernel_name = {"team": "search_team_kernel", "warp": "search_fused_kernel", "tensor-core": "search_tc_kernel"}.get(plan["schedule"], "stepwise")
+    # SM-side view of the same kernel: the fp32 fused multiply-adds of the in-search network against the FFMA peak of the part
+    # (148 SMs x 128 lanes x 2 flop x SM clock; MEASURED_PEAKS.json has no fp32 entry)
+    fma_peak = 148 * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
+    fma_tflops = (2.0 * L * H * H + 2.0 * H * (A + 1)) * B * S / (kern_ms_mean * 1e-3) / 1e12
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": {"team": "search_team_kernel", "warp": "search_fused_kernel", "tensor-core": "search_tc_kernel"}.get(mcts.plan(B)["schedule"], "stepwise"), "kernel_ms": kern_ms_mean, "algorithmic_bytes_per_sim": algorithmic_bytes_per_sim(dbar),
+                "kernel": kernel_name, "kernel_ms": kern_ms_mean, "algorithmic_bytes_per_sim": algorithmic_bytes_per_sim(dbar),
                 "mean_path_length": dbar, "peak_source": peak_src, "encoder_ms": enc_ms_mean,
-                "kernel_ms_how": "K launches of the search kernel alone after the timed steps (CUDA events, same L2 flush); encoder_ms = step - kernel"}
+                "kernel_ms_how": "K launches of the search kernel alone after the timed steps (CUDA events, same L2 flush); encoder_ms = step - kernel",
+                "sm_side": {"unit": "TFLOP/s", "achieved": fma_tflops, "peak": fma_peak, "frac": fma_tflops / fma_peak,
+                            "what": "fp32 FMA work of dynamics + prediction per simulation (2LH^2 + 2H(A+1) flop) / kernel time, against 148 SMs x 128 FFMA lanes x 2 x max SM clock"}}
     if WORKLOAD.startswith("atari"):
         # image workload: the conv trunk dominates and is tensor-pipe bound
-        tf_peak = float(json.load(open(peaks_path)).get("bf16_tflops", 1590.0)) if os.path.exists(peaks_path) else 1590.0
+        tf_peak = float(peaks.get("bf16_tflops", 1590.0))
         tf = encoder_flops_per_obs() * B / (enc_ms_mean * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf / tf_peak, "traffic": None,
-                    "kernel": "conv_tc_kernel (all launches of one initial_inference)", "kernel_ms": enc_ms_mean,
-                    "flops_per_obs": encoder_flops_per_obs(), "search_ms": kern_ms_mean, "mean_path_length": dbar,
-                    "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops)" if os.path.exists(peaks_path) else "fallback"}
+                    "kernel": "conv_tc kernels (all launches of one initial_inference)", "kernel_ms": enc_ms_mean,
+                    "flops_per_obs": encoder_flops_per_obs(), "search_ms": kern_ms_mean, "search_kernel": kernel_name, "mean_path_length": dbar,
+                    "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks else "fallback"}
     line = {
         "metric": "batched MCTS simulations/sec", "value": value, "unit": "simulations/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
-        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong" if args.total_trees > 0 else "weak", "vs_baseline": None, "dtype": "fp32" if MODEL_DTYPE == "float32" else "bf16",
-        "data": "synthetic", "config": workload_config(args, per_gpu=B),
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong" if total_trees > 0 else "weak", "vs_baseline": None, "dtype": "fp32" if MODEL_DTYPE == "float32" else "bf16",
+        "data": "synthetic", "config": workload_config(args, per_gpu=B, total_trees=total_trees),
         "e2e": {"value": e2e_value, "unit": "simulations/s", "h2d_bytes_per_step": int(obs.nbytes + noise.nbytes),
                 "d2h_bytes_per_step": int(actions.nbytes + probs.nbytes), "ms_per_step": e2e_ms / K},
         "gpu_launches": int(launches),
         "roofline": roofline,
-        "clocks": sampler.summary(),
-        "plan": mcts.plan(B), "wall_s": wall, "root_visits_ok": visits_ok,
+        "plan": plan, "wall_s": wall, "root_visits_ok": visits_ok,
     }
     if sustained is not None:
         sustained["value"] = sims_per_step / (sustained["ms_per_step"] * 1e-3)
         line["sustained"] = sustained
-    if not args.no_cpu and world >= 1:
-        line["cpu_baseline"] = cpu_baseline(S, args.cpu_seconds)
-        line["cpu_baseline_c"] = {"value": c_oracle_rate(S), "unit": "simulations/s", "cores": 1, "kind": "port",
-                                  "sample": "oracle/cumind_oracle.c, 512 trees, one thread (pinned fp32 order)"}
-    print(json.dumps(line), flush=True)
+    del agent, flush, drain
+    torch.cuda.empty_cache()
+    return line
+
+
+def measure_train(rank: int, world: int, local_rank: int, dist, K: int, W: int):
+    """BASELINE configs[4]: one MuZero train step = K=5 unroll over a replay batch of 1024 per GPU (loss + gradient kernel),
+    one NCCL all-reduce of the flat gradient when world > 1, AdamW, parameter push to the search kernels — through
+    Trainer.train_step (host batch in, host losses out)."""
+    import torch
+
+    from cumind_b200 import Agent, Config
+    from cumind_b200.trainer import MemoryBuffer, Trainer
+
+    Ku, At, Dt, Bt, Ht = 5, 2, 4, 1024, 64
+    cfg = Config(hidden_dim=Ht, num_blocks=2, action_space_size=At, observation_shape=(Dt,), num_unroll_steps=Ku, batch_size=Bt)
+    agent = Agent(cfg)
+    trainer = Trainer(agent, MemoryBuffer(8), cfg)
+    rng = np.random.default_rng(100 + rank)
+    batch = (rng.standard_normal((Bt, Dt)).astype(np.float32), rng.integers(0, At, size=(Bt, Ku)).astype(np.int32),
+             {"values": rng.standard_normal(Bt).astype(np.float32), "rewards": rng.standard_normal((Bt, Ku)).astype(np.float32),
+              "policies": rng.dirichlet([0.5] * At, size=Bt).astype(np.float32)})
+    for _ in range(max(W, 3)):
+        trainer.train_step(batch)
+    torch.cuda.synchronize()
     if dist is not None:
+        dist.barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    t0.record()
+    for _ in range(K):
+        info = trainer.train_step(batch)
+    t1.record()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - w0) * 1e3 / K
+    ms = torch.tensor([t0.elapsed_time(t1) / K, wall_ms], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_dev, ms_wall = float(ms[0]), float(ms[1])
+    return {"workload": f"BASELINE configs[4]: train step, K={Ku} unroll, replay batch {Bt} per GPU, hidden_dim={Ht}, AdamW, "
+                        + ("one NCCL all-reduce of the flat gradient" if world > 1 else "single GPU (no collective)"),
+            "metric": "train steps through Trainer.train_step (host batch in, host losses out)", "ms_per_step": ms_wall,
+            "device_ms_per_step": ms_dev, "n_gpus": world, "global_batch": Bt * world, "trajectories_per_s": Bt * world / (ms_wall * 1e-3),
+            "loss_grad_kernel": "train_fwd_bwd_kernel (hand-written)" if trainer.use_fused_kernel else "torch autograd",
+            "params": int(trainer._flat.numel()), "loss": info["total_loss"]}
+
+
+def run_native(args, rank: int, world: int, local_rank: int):
+    import torch
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    line = measure_search(args, rank, world, local_rank, dist, sampler, args.steps, args.warmup, args.sustain, args.total_trees, args.trees)
+    sampler.stop_flag = True
+    if line is None:
+        return
+    line["clocks"] = sampler.summary()
+    line["clocks"]["note"] = "NVML, 25 ms period, over the timed steps and the sustained leg"
+    # ---- the other BASELINE configurations, measured after the headline (same process, same box) ---------------------
+    if args.secondary and WORKLOAD == "cartpole" and args.total_trees == 0:
+        secondary = {}
+        keep = (OBS_SHAPE, A, H, L, CC, WORKLOAD, MODEL_DTYPE)
+        ks = max(5, min(args.steps, 10))
+
+        def brief(d):
+            return {k: d[k] for k in ("value", "unit", "ms_per_step", "scaling", "dtype", "config", "e2e", "roofline", "plan", "root_visits_ok")}
+        try:
+            set_workload("atari")
+            secondary["configs[2]"] = brief(measure_search(args, rank, world, local_rank, dist, None, ks, 3, 0.0, 0, 1024))
+        finally:
+            set_workload_raw(keep)
+        if world > 1:
+            secondary["configs[3]"] = brief(measure_search(args, rank, world, local_rank, dist, None, ks, 3, 0.0, 65536, 0))
+        secondary["configs[4]"] = measure_train(rank, world, local_rank, dist, 50, 5)
+        line["secondary"] = secondary
+    if rank == 0:
+        if not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(args.sims, args.cpu_seconds)
+            line["cpu_baseline_c"] = {"value": c_oracle_rate(args.sims), "unit": "simulations/s", "cores": 1, "kind": "port",
+                                      "sample": "oracle/cumind_oracle.c, 512 trees, one thread (pinned fp32 order)"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -551,6 +638,8 @@ def main():
     ap.add_argument("--phase-clocks", action="store_true", help="print the team kernel's per-phase SM cycles and exit")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-secondary", dest="secondary", action="store_false",
+                    help="skip the secondary legs (BASELINE configs[2], [3] when N > 1, [4]) measured after the headline")
     ap.add_argument("--sustain", type=float, default=2.5, help="seconds of back-to-back steps after the timed region (0 = skip)")
     ap.add_argument("--workload", default="cartpole", choices=["cartpole", "cartpole-h128", "atari", "atari-literal"],
                     help="cartpole = BASELINE configs[1] (the bench line); atari = configs[2], measured for profiles/ only")

@@ -341,8 +341,11 @@ class Trainer:
         self._count += 1
         self.train_step_count += 1
         self._state_stale = True
-        res = {f"train/{k}": float(v.detach()) for k, v in out.items() if k != "total_loss"}
-        res["total_loss"] = float(out["total_loss"].detach())
+        # ONE device-to-host read per step (the reference returns Python floats, trainer.py:102-107)
+        keys = [k for k in out if k != "total_loss"] + ["total_loss"]
+        vals = torch.stack([out[k].detach().reshape(()).float() for k in keys]).tolist()
+        res = {f"train/{k}": v for k, v in zip(keys[:-1], vals[:-1])}
+        res["total_loss"] = vals[-1]
         return res
 
     def sync_optimizer_state(self) -> None:
