@@ -49,6 +49,8 @@ class Agent:
                                      conv_channels=config.conv_channels, rngs=rngs, device=self.device, net_mode=net_mode)
         self.target_network = self.network.clone()
         self.optimizer = AdamW(config.learning_rate, config.weight_decay)
+        self._state_version = 0      # bumped by load_state: a Trainer bound to this agent reloads its device copies
+        self._trainer = None         # weakref to the Trainer that owns the live optimizer state, if any
         if existing_state:
             self.load_state(existing_state)
         else:
@@ -149,9 +151,13 @@ class Agent:
         self.target_network.load_state(self.network.state())
 
     def save_state(self) -> Dict[str, Any]:
+        trainer = self._trainer() if self._trainer is not None else None
+        if trainer is not None and getattr(trainer, "_state_stale", False):
+            trainer.sync_optimizer_state()   # the AdamW moments live on the device while training
         return {"network_state": self.network.state(), "optimizer_state": self.optimizer_state}
 
     def load_state(self, state: Dict[str, Any]) -> None:
         self.network.load_state(state["network_state"])
         self.optimizer_state = state["optimizer_state"]
         self.update_target_network()
+        self._state_version += 1

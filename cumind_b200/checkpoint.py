@@ -9,6 +9,8 @@ nested dict of float32 arrays that `CuMindNetwork.load_state` / `Agent.load_stat
 
 Writing: `save_checkpoint` pickles the same nested dict of NumPy arrays (no flax classes, so the
 reference cannot read it back without a small adapter; `load_checkpoint` reads both formats).
+Both formats are read through a RESTRICTED unpickler (exact allow-list of containers, numbers and the NumPy array
+reconstruction; the reference's flax / jax / optax classes become inert stubs; anything else is refused).
 """
 
 from __future__ import annotations
@@ -21,16 +23,42 @@ import numpy as np
 
 
 class _Stub:
+    """Stand-in for every flax / jax / optax class in a reference checkpoint.  Records how it was built: NamedTuples such
+    as optax.ScaleByAdamState are pickled with NEWOBJ (`cls.__new__(cls, *fields)`, no __init__ call), dataclass-like
+    objects with REDUCE + BUILD."""
+
+    def __new__(cls, *args, **kwargs):
+        obj = object.__new__(cls)
+        obj.args, obj.kwargs, obj.state = args, kwargs, None
+        return obj
+
     def __init__(self, *args, **kwargs):
-        self.args, self.kwargs = args, kwargs
+        pass
 
     def __setstate__(self, state):
         self.state = state
 
 
+# exactly what a checkpoint needs: containers, numbers and the NumPy array reconstruction; nothing callable beyond that
+_ALLOWED = {
+    ("builtins", n) for n in ("dict", "list", "tuple", "set", "frozenset", "int", "float", "complex", "bool", "bytes", "bytearray", "str", "slice")
+} | {
+    ("collections", "OrderedDict"),
+    ("numpy", "ndarray"), ("numpy", "dtype"),
+    ("numpy._core.multiarray", "_reconstruct"), ("numpy.core.multiarray", "_reconstruct"),
+    ("numpy._core.multiarray", "scalar"), ("numpy.core.multiarray", "scalar"),
+    ("numpy._core.numeric", "_frombuffer"), ("numpy.core.numeric", "_frombuffer"),
+}
+_STUBBED_PREFIXES = ("flax", "jax", "jaxlib", "optax", "chex", "cumind")
+
+
 class _ReferenceUnpickler(pickle.Unpickler):
+    """Restricted unpickler: names on the allow-list resolve to the real object, classes of the reference's own
+    dependencies (flax / jax / optax / chex / cumind) become inert stubs, and anything else is refused — a checkpoint
+    is data, and a pickle that asks for eval / os.system / ... must not get it."""
+
     def find_class(self, module, name):
-        if module.startswith("numpy") or module == "builtins" or module == "collections":
+        if (module, name) in _ALLOWED:
             return super().find_class(module, name)
         if module == "jax._src.array" and name == "_reconstruct_array":
             def rebuild(fun, args, arr_state, aval_state):
@@ -38,7 +66,9 @@ class _ReferenceUnpickler(pickle.Unpickler):
                 arr.__setstate__(arr_state)
                 return arr
             return rebuild
-        return type(name, (_Stub,), {"__module__": module})
+        if module.split(".")[0] in _STUBBED_PREFIXES:
+            return type(name, (_Stub,), {"__module__": module})
+        raise pickle.UnpicklingError(f"checkpoint refers to {module}.{name}, which is not allowed in a checkpoint")
 
 
 def _plain(node: Any) -> Any:
@@ -46,7 +76,7 @@ def _plain(node: Any) -> Any:
     if isinstance(node, dict):
         return {k: _plain(v) for k, v in node.items() if k != "rngs"}
     if isinstance(node, _Stub):
-        st = getattr(node, "state", None)
+        st = node.state
         if isinstance(st, dict) and "_mapping" in st:          # nnx.State
             return _plain(st["_mapping"])
         if isinstance(st, tuple) and len(st) == 2 and isinstance(st[1], dict) and "value" in st[1]:  # VariableState
@@ -57,19 +87,48 @@ def _plain(node: Any) -> Any:
     return node
 
 
-def _adam_state(opt: Any) -> Dict[str, Any]:
-    """optax (ScaleByAdamState(count, mu, nu), EmptyState, EmptyState) -> {"count", "mu", "nu"} trees."""
-    try:
-        adam = opt[0]
-        fields = adam.kwargs or {}
-        args = adam.args
-        count = fields.get("count", args[0] if args else 0)
-        mu = fields.get("mu", args[1] if len(args) > 1 else None)
-        nu = fields.get("nu", args[2] if len(args) > 2 else None)
-        return {"count": int(np.asarray(count)) if count is not None else 0,
-                "mu": _plain(mu) if mu is not None else None, "nu": _plain(nu) if nu is not None else None}
-    except Exception:
+def _flat_moment(tree: Any, dims) -> np.ndarray:
+    """An AdamW moment tree (same structure as the parameters; BatchNorm statistics have no entry) -> blob layout."""
+    from . import params as P
+
+    out = np.zeros(P.param_count(*dims), dtype=np.float32)
+    o = 0
+    for path, shape in P._schema(*dims):
+        n = int(np.prod(shape))
+        node = tree
+        try:
+            for key in path:
+                node = node[key] if key in node else node[str(key)]
+            out[o:o + n] = np.asarray(node, dtype=np.float32).reshape(-1)
+        except (KeyError, TypeError):
+            if path[-1] not in ("mean", "var"):
+                raise ValueError(f"optimizer state has no entry for {'/'.join(map(str, path))}")
+        o += n
+    return out
+
+
+def _adam_state(opt: Any, network_tree: Dict[str, Any]) -> Dict[str, Any]:
+    """optax state of adamw = (ScaleByAdamState(count, mu, nu), EmptyState, EmptyState) -> {"count", "mu", "nu"} with the
+    moments as flat fp32 arrays in the blob layout (what Trainer and cumind_adamw_step use)."""
+    if opt is None:
         return {"count": 0, "mu": None, "nu": None}
+    if isinstance(opt, dict) and "count" in opt:           # this package's own format
+        return opt
+    adam = opt[0] if isinstance(opt, (tuple, list)) and len(opt) > 0 else opt
+    if not isinstance(adam, _Stub):
+        raise ValueError(f"unsupported optimizer state of type {type(adam).__name__}")
+    fields = dict(adam.kwargs)
+    for name, value in zip(("count", "mu", "nu"), adam.args):
+        fields.setdefault(name, value)
+    if isinstance(adam.state, dict):
+        fields.update({k: v for k, v in adam.state.items() if k in ("count", "mu", "nu")})
+    if not {"count", "mu", "nu"} <= set(fields):
+        raise ValueError("optimizer state does not look like optax.ScaleByAdamState(count, mu, nu)")
+    from . import params as P
+
+    dims = P.dims_of(network_tree)
+    return {"count": int(np.asarray(fields["count"])), "mu": _flat_moment(_plain(fields["mu"]), dims),
+            "nu": _flat_moment(_plain(fields["nu"]), dims)}
 
 
 def load_reference_checkpoint(path: str) -> Dict[str, Any]:
@@ -78,7 +137,8 @@ def load_reference_checkpoint(path: str) -> Dict[str, Any]:
         obj = _ReferenceUnpickler(f).load()
     if not isinstance(obj, dict) or "network_state" not in obj:
         raise ValueError(f"{path} is not a CuMind checkpoint")
-    return {"network_state": _plain(obj["network_state"]), "optimizer_state": _adam_state(obj.get("optimizer_state"))}
+    net = _plain(obj["network_state"])
+    return {"network_state": net, "optimizer_state": _adam_state(obj.get("optimizer_state"), net)}
 
 
 def save_checkpoint(state: Dict[str, Any], path: str) -> None:
@@ -91,13 +151,14 @@ def save_checkpoint(state: Dict[str, Any], path: str) -> None:
 def load_checkpoint(path: str) -> Dict[str, Any]:
     """Reads either this package's checkpoints or the reference's (checkpoint.py:31-47)."""
     with open(path, "rb") as f:
-        head = f.read(4096)
-    if b"cumind_b200/1" in head:
-        with open(path, "rb") as f:
-            obj = pickle.load(f)
+        obj = _ReferenceUnpickler(f).load()      # both formats go through the restricted unpickler
+    if isinstance(obj, dict) and obj.get("format") == "cumind_b200/1":
         obj.pop("format", None)
         return obj
-    return load_reference_checkpoint(path)
+    if not isinstance(obj, dict) or "network_state" not in obj:
+        raise ValueError(f"{path} is not a CuMind checkpoint")
+    net = _plain(obj["network_state"])
+    return {"network_state": net, "optimizer_state": _adam_state(obj.get("optimizer_state"), net)}
 
 
 def infer_dims(tree: Dict[str, Any]) -> Dict[str, Any]:

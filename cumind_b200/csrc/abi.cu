@@ -840,9 +840,11 @@ static bool use_tensor_search(const cumind_tree* t, const cumind_net* n, const c
 
 // pdl: d_root_hidden is written by the kernel launched just before on `stream`, which calls pdl_launch_dependents():
 // the search kernel is launched with programmatic stream serialization so that its prologue overlaps that kernel.
+// out_actions (may be NULL): first arg-max of the root visit counts, written by the fused kernels themselves
 static int search_impl(cumind_tree* t, const cumind_net* n, const float* d_root_hidden, const cumind_search_cfg* c,
                        const double* d_noise, int32_t* d_out_visits, double* d_out_probs, double* d_out_root_value,
-                       void* stream, bool pdl) {
+                       void* stream, bool pdl, int32_t* out_actions = nullptr, bool* wrote_actions = nullptr) {
+    if (wrote_actions) *wrote_actions = false;
     if (check_search("cumind_search", t, n, c, d_noise)) return 1;
     if (!d_root_hidden || !d_out_visits || !d_out_probs) return fail("cumind_search: NULL device pointer");
     FusedPlan pl;
@@ -865,6 +867,8 @@ static int search_impl(cumind_tree* t, const cumind_net* n, const float* d_root_
         q.out_visits = d_out_visits;
         q.out_probs = d_out_probs;
         q.out_root_value = d_out_root_value;
+        q.out_actions = out_actions;
+        if (wrote_actions) *wrote_actions = out_actions != nullptr;
         q.S = c->num_simulations;
         q.A_cfg = c->action_space_size;
         q.c_puct = c->c_puct;
@@ -888,6 +892,8 @@ static int search_impl(cumind_tree* t, const cumind_net* n, const float* d_root_
             tp.p.out_visits = d_out_visits;
             tp.p.out_probs = d_out_probs;
             tp.p.out_root_value = d_out_root_value;
+            tp.p.out_actions = out_actions;
+            if (wrote_actions) *wrote_actions = out_actions != nullptr;
             tp.p.pdl = pdl ? 1 : 0;
             CM_CUDA(launch_search_team(tp.G, tp.p, tp.grid, tp.block, tp.smem, (cudaStream_t)stream));
             g_launches += 1;
@@ -901,6 +907,8 @@ static int search_impl(cumind_tree* t, const cumind_net* n, const float* d_root_
     pl.p.out_visits = d_out_visits;
     pl.p.out_probs = d_out_probs;
     pl.p.out_root_value = d_out_root_value;
+    pl.p.out_actions = out_actions;
+    if (wrote_actions) *wrote_actions = out_actions != nullptr;
     pl.p.pdl = pdl ? 1 : 0;
     CM_CUDA(launch_search_fused(pl.G, pl.R, pl.p, pl.grid, pl.block, pl.smem, (cudaStream_t)stream));
     g_launches += 1;
@@ -962,6 +970,7 @@ extern "C" int cumind_search_phase_clocks(cumind_tree* t, const cumind_net* n, c
     tp.p.out_visits = d_out_visits;
     tp.p.out_probs = d_out_probs;
     tp.p.out_root_value = d_out_root_value;
+    tp.p.out_actions = nullptr;
     tp.p.clk = (long long*)d_clocks;
     CM_CUDA(launch_search_team(tp.G, tp.p, tp.grid, tp.block, tp.smem, (cudaStream_t)stream));
     g_launches += 1;
@@ -1204,6 +1213,24 @@ extern "C" int cumind_select_actions_host(cumind_tree* t, const cumind_net* n, c
     void *m_actions = mapped_ptr(h_actions), *m_probs = mapped_ptr(h_probs);
     const bool zero_copy = m_obs && m_actions && m_probs && (!with_noise || m_noise) && obs_bytes <= ((size_t)4 << 20) && obs_bytes % 16 == 0 &&
                            noise_bytes % 16 == 0 && ((uintptr_t)m_obs | (uintptr_t)m_noise) % 16 == 0;
+    // Small vector observations: no staging kernels at all — the encoder reads the observations and the search kernel the
+    // noise straight from the mapped host buffers, and the search kernel writes actions and probabilities straight back
+    // (posted PCIe writes); two launches instead of four.  Larger inputs are staged by one kernel each way.
+    const bool direct = zero_copy && n->desc.obs_ndim == 1 && obs_bytes <= ((size_t)256 << 10) && c->tree_mode == CUMIND_TREE_REFERENCE;
+    if (direct) {
+        int rc = cumind_initial_inference(n, (const float*)m_obs, B, d_hidden, nullptr, nullptr, c->net_mode, stream);
+        if (rc) return rc;
+        bool wrote = false;
+        rc = search_impl(t, n, d_hidden, c, with_noise ? (const double*)m_noise : nullptr, d_visits, (double*)m_probs, nullptr, stream, true,
+                         (int32_t*)m_actions, &wrote);
+        if (rc) return rc;
+        if (!wrote) {   // per-phase fallback kernels: no action output of their own
+            CM_CUDA(launch_argmax_first((const double*)m_probs, B, A_cfg, (int32_t*)m_actions, st));
+            g_launches += 1;
+        }
+        CM_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    }
     if (zero_copy) {
         CM_CUDA(launch_stage_in(m_obs, d_obs, obs_bytes, m_noise, d_noise, with_noise ? noise_bytes : 0, st));
         g_launches += 1;

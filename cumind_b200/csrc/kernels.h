@@ -14,6 +14,7 @@ struct FusedParams {
     int32_t* out_visits;       // [B][A_cfg]
     double* out_probs;         // [B][A_cfg]
     double* out_root_value;    // [B] or nullptr
+    int32_t* out_actions;      // [B] or nullptr: int(np.argmax(probs)) (agent.py:86), first maximum
     int S, A_cfg, A_net;
     double c_puct, frac, one_minus_frac, alpha;
     int noise_mode;
@@ -57,6 +58,7 @@ struct TeamParams {
     int32_t* out_visits;       // [B][A_cfg]
     double* out_probs;         // [B][A_cfg]
     double* out_root_value;    // [B] or nullptr
+    int32_t* out_actions;      // [B] or nullptr: int(np.argmax(probs)) (agent.py:86), first maximum
     int S, A_cfg, A_net;
     double c_puct, frac, one_minus_frac, alpha;
     int noise_mode;
@@ -134,6 +136,7 @@ struct SearchTcParams {
     int32_t* out_visits;         // [B][A_cfg]
     double* out_probs;           // [B][A_cfg]
     double* out_root_value;      // [B] or nullptr
+    int32_t* out_actions;        // [B] or nullptr: first arg-max of the visit counts
     int S, A_cfg;
     double c_puct, frac, one_minus_frac, alpha;
     int noise_mode;

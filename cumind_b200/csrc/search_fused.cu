@@ -235,6 +235,11 @@ __global__ void __launch_bounds__(512, 1) search_fused_kernel(const FusedParams 
             if (g == 0) {
                 const Node r = load_node(nodes);
                 if (p.out_root_value) p.out_root_value[t] = r.visit == 0 ? 0.0 : __ddiv_rn(r.value_sum, (double)r.visit);
+                if (p.out_actions) {   // first maximum of the visit counts = np.argmax of the probabilities
+                    int best = 0, bc = load_node(nodes + 1).visit;
+                    for (int a = 1; a < A; ++a) { const int c = load_node(nodes + 1 + a).visit; if (c > bc) { bc = c; best = a; } }
+                    p.out_actions[t] = (total == 0 || bc == 0) ? 0 : best;
+                }
                 p.tv.n_expanded[t] = p.S + 1;
                 p.tv.depth_sum[t] = depth;
             }

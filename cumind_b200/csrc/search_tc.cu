@@ -386,6 +386,11 @@ __global__ void __launch_bounds__(128) search_tc_kernel(const SearchTcParams p) 
             }
             const Node rt = load_node(nodes);
             if (p.out_root_value) p.out_root_value[r] = rt.visit == 0 ? 0.0 : __ddiv_rn(rt.value_sum, (double)rt.visit);
+            if (p.out_actions) {   // first maximum of the visit counts = np.argmax of the probabilities
+                int best = 0, bc = load_node(nodes + 1).visit;
+                for (int a = 1; a < A; ++a) { const int c = load_node(nodes + 1 + a).visit; if (c > bc) { bc = c; best = a; } }
+                p.out_actions[r] = bc == 0 ? 0 : best;
+            }
             p.tv.n_expanded[r] = p.S + 1;
             p.tv.depth_sum[r] = depth;
         }

@@ -550,6 +550,11 @@ CM_DEVICE void search_team_body(const TeamParams& p) {
                 if (g == 0) {
                     const int rn = hs[0].n;
                     if (p.out_root_value) p.out_root_value[t] = rn == 0 ? 0.0 : __ddiv_rn(hw[0], (double)rn);
+                    if (p.out_actions) {   // first maximum of the visit counts = np.argmax of the probabilities
+                        int best = 0, bc = hs[1].n;
+                        for (int a = 1; a < A; ++a) { const int c = hs[1 + a].n; if (c > bc) { bc = c; best = a; } }
+                        p.out_actions[t] = bc == 0 ? 0 : best;
+                    }
                     p.tv.n_expanded[t] = p.S + 1;
                     p.tv.depth_sum[t] = depth;
                 }

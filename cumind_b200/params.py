@@ -68,6 +68,19 @@ def _set(tree: Dict[Any, Any], path: Tuple[Any, ...], value) -> None:
     node[path[-1]] = value
 
 
+def dims_of(tree: Dict[str, Any]):
+    """(observation_shape, A, H, L, Cc) implied by a parameter tree; for image encoders only the channel count of the
+    observation is recoverable, which is all the blob layout depends on (height and width are reported as 0)."""
+    dyn = tree["dynamics_network"]
+    A, H = (int(v) for v in np.shape(_get(dyn, ("action_embedding", "embedding"))))
+    L = len(dyn["layers"])
+    enc = tree["representation_network"]["encoder"]
+    if "layers" in enc:
+        return (int(np.shape(_get(enc, ("layers", 0, "kernel")))[0]),), A, H, L, 32
+    k = np.shape(_get(enc, ("initial_conv", "kernel")))
+    return (0, 0, int(k[2])), A, H, L, int(k[3])
+
+
 def param_count(observation_shape, A, H, L, Cc) -> int:
     return int(sum(int(np.prod(s)) for _, s in _schema(observation_shape, A, H, L, Cc)))
 

@@ -45,24 +45,50 @@ class Trajectory(Sequence):
 
 
 class SelfPlay:
-    def __init__(self, agent, memory: Optional[Any] = None):
-        self.agent = agent
-        self.memory = memory
+    """`SelfPlay(config, agent, memory)` as the reference builds it (self_play.py:14-25); `SelfPlay(agent, memory=None)` is
+    accepted too (the config is then the agent's)."""
 
-    def run_episode(self, environment, max_steps: int = 10_000) -> List[Dict[str, Any]]:
-        """One episode of a gymnasium-style environment (reset() -> (obs, info); step(a) -> 5-tuple)."""
+    def __init__(self, *args, **kwargs):
+        names = ("config", "agent", "memory")
+        if args and (hasattr(args[0], "select_action") or hasattr(args[0], "select_actions")):   # SelfPlay(agent[, memory])
+            names = ("agent", "memory")
+        bound = dict(zip(names, args))
+        for k in kwargs:
+            if k not in ("config", "agent", "memory") or k in bound:
+                raise TypeError(f"SelfPlay() got an unexpected or duplicate argument {k!r}")
+        bound.update(kwargs)
+        if "agent" not in bound:
+            raise TypeError("SelfPlay() needs an agent")
+        self.agent = bound["agent"]
+        self.config = bound.get("config", getattr(self.agent, "config", None))
+        self.memory = bound.get("memory")
+
+    def run_episode(self, environment, max_steps: int = 10_000):
+        """One episode of a gymnasium-style environment (reset() -> (obs, info); step(a) -> 5-tuple).  Returns the
+        reference's tuple (total_reward, episode_steps, episode_data) — self_play.py:27-63."""
         episode: List[Dict[str, Any]] = []
         observation, _ = environment.reset()
         done = False
+        total_reward = 0.0
         while not done and len(episode) < max_steps:
             action, policy = self.agent.select_action(np.asarray(observation), training=True)
             next_observation, reward, terminated, truncated, _ = environment.step(action)
             done = bool(terminated or truncated)
             episode.append({"observation": observation, "action": action, "reward": reward, "policy": policy, "done": done})
             observation = next_observation
+            total_reward += reward
         if self.memory is not None:
             self.memory.add(episode)
-        return episode
+        return total_reward, len(episode), episode
+
+    def collect_samples(self, environment, num_episodes: int) -> None:
+        """self_play.py:65-76"""
+        for _ in range(num_episodes):
+            self.run_episode(environment)
+
+    def get_memory(self):
+        """self_play.py:78-84"""
+        return self.memory
 
     def run_batch(self, vec_env, num_steps: int, training: bool = True, philox_seed: Optional[int] = None) -> List[List[Trajectory]]:
         """Step `vec_env.num_envs` environments `num_steps` times.  Returns, per environment, the list of

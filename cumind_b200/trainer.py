@@ -22,6 +22,7 @@ import contextlib
 import ctypes as C
 import gc
 import os
+import weakref
 from datetime import datetime
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
@@ -150,11 +151,13 @@ class Trainer:
         dev = net.device
         self._flat = torch.as_tensor(net.blob.copy()).to(dev)      # parameters (blob layout); leaves alias it per step
         self.last_grad: Optional[torch.Tensor] = None
-        st = agent.optimizer_state if isinstance(agent.optimizer_state, dict) else {}
-        self._m = torch.as_tensor(np.asarray(st["mu"], np.float32)).to(dev) if st.get("mu") is not None and np.size(st["mu"]) == self._flat.numel() else torch.zeros_like(self._flat, requires_grad=False)
-        self._v = torch.as_tensor(np.asarray(st["nu"], np.float32)).to(dev) if st.get("nu") is not None and np.size(st["nu"]) == self._flat.numel() else torch.zeros_like(self._flat, requires_grad=False)
-        self._count = int(st.get("count", 0) or 0)
-        self._step_dev = torch.tensor([self._count], dtype=torch.int64, device=dev)
+        self._m = torch.zeros_like(self._flat, requires_grad=False)
+        self._v = torch.zeros_like(self._flat, requires_grad=False)
+        self._count = 0
+        self._step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._load_optimizer_state()
+        agent._trainer = weakref.ref(self)
+        self._agent_version = getattr(agent, "_state_version", 0)
         self._mask = torch.as_tensor(trainable_mask(self._dims)).to(dev)
         self.use_cuda_graph = True
         self.graph_distributed = True   # torch.distributed: two graphs around an eager all-reduce
@@ -162,6 +165,32 @@ class Trainer:
         self.use_fused_kernel = bool(self._lib.cumind_train_supported(C.byref(net._desc), int(config.num_unroll_steps)))
         self._fused_buf: Dict[int, Any] = {}
         self._graph, self._graph_key, self._graph_out, self._static = None, None, None, None
+        self._state_stale = False
+
+    def _load_optimizer_state(self) -> None:
+        """agent.optimizer_state ({"count", "mu", "nu"}, moments flat in blob layout or None) -> the device buffers, IN PLACE
+        (captured CUDA graphs keep pointing at them)."""
+        st = self.agent.optimizer_state if isinstance(self.agent.optimizer_state, dict) else {}
+        n = self._flat.numel()
+        with torch.no_grad():
+            for name, buf in (("mu", self._m), ("nu", self._v)):
+                val = st.get(name)
+                if val is None:
+                    buf.zero_()
+                    continue
+                arr = np.asarray(val, dtype=np.float32).reshape(-1)
+                if arr.size != n:
+                    raise ValueError(f"optimizer_state[{name!r}] has {arr.size} values, the parameter blob has {n}")
+                buf.copy_(torch.as_tensor(arr).to(buf.device))
+            self._count = int(st.get("count", 0) or 0)
+            self._step_dev.fill_(self._count)
+
+    def _reload_from_agent(self) -> None:
+        """The agent's state was replaced (Agent.load_state / load_checkpoint): parameters, AdamW moments and step count."""
+        with torch.no_grad():
+            self._flat.copy_(torch.as_tensor(self.agent.network.blob).to(self._flat.device))
+        self._load_optimizer_state()
+        self._agent_version = getattr(self.agent, "_state_version", 0)
         self._state_stale = False
 
     # ---- batch preparation (trainer.py:118-170) --------------------------------------------------
@@ -295,8 +324,9 @@ class Trainer:
             side.wait_stream(torch.cuda.current_stream())
             state = (self._flat.detach().clone(), self._m.clone(), self._v.clone(), self._step_dev.clone())
             with torch.cuda.stream(side):
-                for _ in range(3):                       # warm-up outside the capture (every rank: same three all-reduces)
-                    self._eager_step(*self._static)
+                for _ in range(3):                       # warm-up outside the capture, WITHOUT the collective: ranks may
+                    _, g = self._fwd_bwd(*self._static)  # re-capture on different steps (batch shapes), and an extra
+                    self._apply(g, world)                # all-reduce here would pair with another rank's real one
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             with torch.no_grad():
@@ -323,6 +353,8 @@ class Trainer:
 
     def train_step(self, batch: Optional[Tuple[Any, Any, Dict[str, Any]]] = None) -> Dict[str, float]:
         """One optimiser step.  `batch` = (observations, actions [B,K], targets) skips the replay sampling."""
+        if getattr(self.agent, "_state_version", 0) != self._agent_version:   # Agent.load_state since the last step
+            self._reload_from_agent()
         if batch is None:
             if not self.memory.is_ready(self.config.min_memory_size, self.config.min_memory_pct):
                 return {}
@@ -348,6 +380,21 @@ class Trainer:
         res["total_loss"] = vals[-1]
         return res
 
+    def run_training_loop(self, env: Any) -> None:
+        """trainer.py:44-81: num_episodes episodes of self-play, a train step every train_frequency episodes, the target
+        network every target_update_frequency train steps, a checkpoint every checkpoint_interval episodes."""
+        from .self_play import SelfPlay
+
+        self_play = SelfPlay(self.config, self.agent, self.memory)
+        for episode in range(1, int(self.config.num_episodes) + 1):
+            self_play.run_episode(env)
+            if episode % int(self.config.train_frequency) == 0:
+                self.train_step()
+                if self.train_step_count > 0 and self.train_step_count % int(self.config.target_update_frequency) == 0:
+                    self.agent.update_target_network()
+            if episode % int(self.config.checkpoint_interval) == 0:
+                self.save_checkpoint(episode)
+
     def sync_optimizer_state(self) -> None:
         """Copy the AdamW moments back into agent.optimizer_state (for save_state / checkpoints)."""
         self.agent.optimizer_state = {"count": self._count, "mu": self._m.cpu().numpy(), "nu": self._v.cpu().numpy()}
@@ -363,4 +410,4 @@ class Trainer:
 
     def load_checkpoint(self, path: str) -> None:
         self.agent.load_state(load_checkpoint(path))
-        self._flat.copy_(torch.as_tensor(self.agent.network.blob).to(self._flat.device))
+        self._reload_from_agent()

@@ -107,7 +107,8 @@ def test_batched_self_play_runs_the_fused_search_per_step():
                 steps += 1
             assert all(not s["done"] for s in ep[:-1])
     assert steps == 48 * 30
-    one = SelfPlay(agent).run_episode(_Single(), max_steps=12)
+    total, steps, one = SelfPlay(agent).run_episode(_Single(), max_steps=12)
+    assert steps == len(one) and total == sum(s["reward"] for s in one)
     assert 1 <= len(one) <= 12 and one[-1]["done"] in (True, False)
 
 

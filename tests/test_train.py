@@ -225,3 +225,63 @@ def test_distributed_two_graph_step_equals_the_eager_step():
         assert np.array_equal(runs[0][1], runs[1][1])
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_checkpoint_round_trip_resumes_the_same_trajectory(tmp_path):
+    """save -> load -> the next steps are bit-equal to an uninterrupted run: the AdamW moments and the step count travel
+    with the checkpoint (Trainer.load_checkpoint reloads them in place), Agent.save_state pulls them from the device, and a
+    direct Agent.load_state is picked up by the next train step."""
+    from cumind_b200 import Agent, Config
+    from cumind_b200.trainer import MemoryBuffer, Trainer
+
+    params, obs, actions, targets, (D, A, H, L, K) = _problem(B=48, A=2, H=32, L=2, K=4, D=4, seed=5)
+    cfg = Config(hidden_dim=H, num_blocks=L, action_space_size=A, observation_shape=(D,), num_unroll_steps=K, learning_rate=1e-2,
+                 weight_decay=1e-4, num_simulations=4, checkpoint_root_dir=str(tmp_path))
+    batch = (obs, actions, targets)
+    a1 = Agent(cfg)
+    a1.load_state({"network_state": params, "optimizer_state": {"count": 0}})
+    t1 = Trainer(a1, MemoryBuffer(4), cfg)
+    for _ in range(3):
+        t1.train_step(batch)
+    path = t1.save_checkpoint(3)
+    state = a1.save_state()                                   # not stale: the moments come from the device
+    assert state["optimizer_state"]["count"] == 3 and np.any(state["optimizer_state"]["mu"] != 0)
+    for _ in range(2):
+        t1.train_step(batch)
+    want = a1.network.blob.copy()
+    a2 = Agent(cfg)
+    t2 = Trainer(a2, MemoryBuffer(4), cfg)
+    t2.train_step(batch)                                      # some unrelated history, then resume from the file
+    t2.load_checkpoint(path)
+    assert t2._count == 3 and int(t2._step_dev.item()) == 3
+    for _ in range(2):
+        t2.train_step(batch)
+    assert np.array_equal(a2.network.blob, want)
+    # Agent.load_state directly: the trainer notices at the next step
+    a3 = Agent(cfg)
+    t3 = Trainer(a3, MemoryBuffer(4), cfg)
+    t3.train_step(batch)
+    a3.load_state(state)
+    for _ in range(2):
+        t3.train_step(batch)
+    assert np.array_equal(a3.network.blob, want)
+
+
+@pytest.mark.gpu
+def test_run_training_loop_follows_the_reference_schedule(tmp_path):
+    """trainer.py:44-81: train every train_frequency episodes, target network every target_update_frequency train steps,
+    checkpoint every checkpoint_interval episodes."""
+    from cumind_b200 import Agent, Config
+    from cumind_b200.trainer import MemoryBuffer, Trainer
+    from tests.test_selfplay import _Single
+
+    cfg = Config(hidden_dim=32, num_simulations=4, batch_size=8, td_steps=2, num_unroll_steps=2, min_memory_size=1, min_memory_pct=0.0,
+                 num_episodes=6, train_frequency=2, target_update_frequency=2, checkpoint_interval=3, checkpoint_root_dir=str(tmp_path))
+    agent = Agent(cfg)
+    tr = Trainer(agent, MemoryBuffer(100), cfg)
+    before = agent.target_network.blob.copy()
+    tr.run_training_loop(_Single())
+    assert tr.train_step_count == 3 and len(tr.memory) == 6
+    assert not np.array_equal(agent.target_network.blob, before)      # updated at train step 2
+    assert sorted(os.listdir(tr.checkpoint_dir)) == ["episode_00003.pkl", "episode_00006.pkl"]
