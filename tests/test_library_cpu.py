@@ -91,3 +91,25 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.delenv("CUMIND_B200_AUTOBUILD", raising=False)
     with pytest.raises(_native.CuMindNativeError, match="no CPU fallback"):
         _native.load()
+
+
+def test_jax_ffi_shim_is_guarded():
+    """cumind_b200/ffi: the XLA FFI handlers compile to an empty unit without jaxlib's headers, the Python front end
+    raises ImportError (with the reason) without jax, and nothing in the package imports it."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "cumind_b200", "ffi", "cumind_ffi.cc")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I" + os.path.join(root, "include"), src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = open(src).read()
+    for sym in ("cumind_initial_inference", "cumind_recurrent_inference", "cumind_search"):
+        assert sym in text
+    try:
+        import jax  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="jax"):
+            import cumind_b200.ffi.jax_ffi  # noqa: F401
+    for name in os.listdir(os.path.join(root, "cumind_b200")):
+        if name.endswith(".py"):
+            assert "jax_ffi" not in open(os.path.join(root, "cumind_b200", name)).read(), name
