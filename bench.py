@@ -511,10 +511,12 @@ def measure_train(rank: int, world: int, local_rank: int, dist, K: int, W: int):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_dev, ms_wall = float(ms[0]), float(ms[1])
     return {"workload": f"BASELINE configs[4]: train step, K={Ku} unroll, replay batch {Bt} per GPU, hidden_dim={Ht}, AdamW, "
-                        + ("one NCCL all-reduce of the flat gradient" if world > 1 else "single GPU (no collective)"),
+                        + ("gradient all-reduce over the GPUs" if world > 1 else "single GPU (no collective)"),
             "metric": "train steps through Trainer.train_step (host batch in, host losses out)", "ms_per_step": ms_wall,
             "device_ms_per_step": ms_dev, "n_gpus": world, "global_batch": Bt * world, "trajectories_per_s": Bt * world / (ms_wall * 1e-3),
             "loss_grad_kernel": "train_fwd_bwd_kernel (hand-written)" if trainer.use_fused_kernel else "torch autograd",
+            "allreduce": ("fused into AdamW over NVLink peer memory (p2p_allreduce_adamw_kernel), whole step one CUDA graph" if trainer._p2p is not None
+                          else ("NCCL all-reduce of the flat gradient between two CUDA graphs" if world > 1 else "none (1 GPU)")),
             "params": int(trainer._flat.numel()), "loss": info["total_loss"]}
 
 

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcumind_b200.so")
-SOURCES = ["abi.cu", "search_fused.cu", "search_team.cu", "tree_steps.cu", "network_fp32.cu", "conv_fp32.cu", "network_tc.cu", "search_tc.cu", "conv_tc.cu", "train.cu", "train_fused.cu", "replay.cu"]
+SOURCES = ["abi.cu", "search_fused.cu", "search_team.cu", "tree_steps.cu", "network_fp32.cu", "conv_fp32.cu", "network_tc.cu", "search_tc.cu", "conv_tc.cu", "train.cu", "train_fused.cu", "p2p_adamw.cu", "replay.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
 

@@ -24,6 +24,7 @@ EXPORTS = [
     "cumind_sumtree_create", "cumind_sumtree_destroy", "cumind_sumtree_tree_size", "cumind_sumtree_clear", "cumind_sumtree_update",
     "cumind_sumtree_sample", "cumind_sumtree_read", "cumind_search_from_obs", "cumind_net_reserve",
     "cumind_train_supported", "cumind_train_work_bytes", "cumind_train_loss_grad",
+    "cumind_p2p_create", "cumind_p2p_open", "cumind_p2p_grad_ptr", "cumind_p2p_allreduce_adamw", "cumind_p2p_error", "cumind_p2p_destroy", "cumind_p2p_reset",
 ]
 
 NET_FP32_EXACT = 0
@@ -115,6 +116,14 @@ def load():
     lib.cumind_adamw_step.argtypes = [vp, vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, C.c_int64, f32, vp]
     lib.cumind_adamw_step_dev.argtypes = [vp, vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, vp, f32, vp]
     lib.cumind_net_update_params_device.argtypes = [vp, vp, sz, vp]
+    lib.cumind_p2p_create.argtypes = [sz, i32, i32, C.POINTER(vp), vp]
+    lib.cumind_p2p_open.argtypes = [vp, vp]
+    lib.cumind_p2p_grad_ptr.argtypes = [vp]
+    lib.cumind_p2p_grad_ptr.restype = vp
+    lib.cumind_p2p_allreduce_adamw.argtypes = [vp, vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, vp, vp, vp]
+    lib.cumind_p2p_error.argtypes = [vp]
+    lib.cumind_p2p_reset.argtypes = [vp]
+    lib.cumind_p2p_destroy.argtypes = [vp]
     lib.cumind_train_supported.argtypes = [C.POINTER(NetDesc), i32]
     lib.cumind_train_work_bytes.argtypes = [C.POINTER(NetDesc), i32]
     lib.cumind_train_work_bytes.restype = C.c_size_t

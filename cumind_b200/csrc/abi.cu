@@ -1091,6 +1091,111 @@ extern "C" int cumind_net_update_params_device(cumind_net* n, const float* d_par
     return repack_device(n, st);
 }
 
+// ------------------------------------------------------------------------------------------------
+// gradient all-reduce over peer memory fused into AdamW (p2p_adamw.cu)
+// ------------------------------------------------------------------------------------------------
+struct cumind_p2p {
+    int rank, world;
+    size_t n;
+    float* d_grad;
+    long long* d_flags;
+    int* d_err;       // [0] error flag, [1] block counter
+    void* peer_grad[P2P_MAX_RANKS];
+    void* peer_flags[P2P_MAX_RANKS];
+    bool opened;
+};
+
+extern "C" int cumind_p2p_create(size_t n, int32_t rank, int32_t world, cumind_p2p** out, void* h_handles128) {
+    if (!out || !h_handles128 || n == 0 || world < 1 || world > P2P_MAX_RANKS || rank < 0 || rank >= world)
+        return fail("cumind_p2p_create: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "two IPC handles are exchanged as 128 bytes");
+    cumind_p2p* q = new cumind_p2p();
+    q->rank = rank; q->world = world; q->n = n; q->opened = false;
+    q->d_grad = nullptr; q->d_flags = nullptr; q->d_err = nullptr;
+    for (int r = 0; r < P2P_MAX_RANKS; ++r) q->peer_grad[r] = q->peer_flags[r] = nullptr;
+    cudaError_t e;
+    cudaIpcMemHandle_t hg, hf;
+    if ((e = cudaMalloc(&q->d_grad, n * sizeof(float))) != cudaSuccess || (e = cudaMemset(q->d_grad, 0, n * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&q->d_flags, 2 * P2P_MAX_RANKS * sizeof(long long))) != cudaSuccess ||
+        (e = cudaMemset(q->d_flags, 0, 2 * P2P_MAX_RANKS * sizeof(long long))) != cudaSuccess ||
+        (e = cudaMalloc(&q->d_err, 2 * sizeof(int))) != cudaSuccess || (e = cudaMemset(q->d_err, 0, 2 * sizeof(int))) != cudaSuccess ||
+        (e = cudaIpcGetMemHandle(&hg, q->d_grad)) != cudaSuccess || (e = cudaIpcGetMemHandle(&hf, q->d_flags)) != cudaSuccess ||
+        (e = cudaDeviceSynchronize()) != cudaSuccess) {
+        cudaFree(q->d_grad); cudaFree(q->d_flags); cudaFree(q->d_err);
+        delete q;
+        return fail_cuda("cumind_p2p_create", e);
+    }
+    memcpy(h_handles128, &hg, 64);
+    memcpy((char*)h_handles128 + 64, &hf, 64);
+    q->peer_grad[rank] = q->d_grad;
+    q->peer_flags[rank] = q->d_flags;
+    *out = q;
+    return 0;
+}
+
+// h_all_handles: world x 128 bytes, the output of every rank's cumind_p2p_create in rank order
+extern "C" int cumind_p2p_open(cumind_p2p* q, const void* h_all_handles) {
+    if (!q || !h_all_handles) return fail("cumind_p2p_open: NULL argument");
+    for (int r = 0; r < q->world; ++r) {
+        if (r == q->rank) continue;
+        cudaIpcMemHandle_t hg, hf;
+        memcpy(&hg, (const char*)h_all_handles + (size_t)r * 128, 64);
+        memcpy(&hf, (const char*)h_all_handles + (size_t)r * 128 + 64, 64);
+        CM_CUDA(cudaIpcOpenMemHandle(&q->peer_grad[r], hg, cudaIpcMemLazyEnablePeerAccess));
+        CM_CUDA(cudaIpcOpenMemHandle(&q->peer_flags[r], hf, cudaIpcMemLazyEnablePeerAccess));
+    }
+    q->opened = true;
+    return 0;
+}
+
+extern "C" float* cumind_p2p_grad_ptr(cumind_p2p* q) { return q ? q->d_grad : nullptr; }
+
+extern "C" int cumind_p2p_allreduce_adamw(cumind_p2p* q, float* d_params, float* d_m, float* d_v, const uint8_t* d_mask, size_t n, float lr,
+                                          float b1, float b2, float eps, float weight_decay, int64_t* d_step, float* d_sum_out, void* stream) {
+    if (!q || !d_params || !d_m || !d_v || !d_step || n != q->n) return fail("cumind_p2p_allreduce_adamw: bad argument");
+    if (!q->opened && q->world > 1) return fail("cumind_p2p_allreduce_adamw: peers not opened (cumind_p2p_open)");
+    P2PArgs a;
+    a.rank = q->rank; a.world = q->world;
+    for (int r = 0; r < P2P_MAX_RANKS; ++r) { a.peer_grad[r] = (const float*)q->peer_grad[r]; a.peer_flags[r] = (long long*)q->peer_flags[r]; }
+    a.sum_out = d_sum_out;
+    a.err = q->d_err;
+    a.count = q->d_err + 1;
+    CM_CUDA(launch_p2p_allreduce_adamw(a, d_params, d_m, d_v, d_mask, n, lr, b1, b2, eps, weight_decay, (long long*)d_step, (cudaStream_t)stream));
+    g_launches += 2;
+    return 0;
+}
+
+// forget the barrier epochs (after the step counter was set back, e.g. a checkpoint was loaded): call on every rank between two
+// host-side barriers
+extern "C" int cumind_p2p_reset(cumind_p2p* q) {
+    if (!q) return fail("cumind_p2p_reset: NULL argument");
+    CM_CUDA(cudaDeviceSynchronize());
+    CM_CUDA(cudaMemset(q->d_flags, 0, 2 * P2P_MAX_RANKS * sizeof(long long)));
+    CM_CUDA(cudaMemset(q->d_err, 0, 2 * sizeof(int)));
+    CM_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+
+// 1 when a rank barrier timed out since creation (synchronises the device)
+extern "C" int cumind_p2p_error(cumind_p2p* q) {
+    if (!q) return -1;
+    int e = 0;
+    if (cudaMemcpy(&e, q->d_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return e;
+}
+
+extern "C" int cumind_p2p_destroy(cumind_p2p* q) {
+    if (!q) return 0;
+    for (int r = 0; r < q->world; ++r) {
+        if (r == q->rank) continue;
+        if (q->peer_grad[r]) cudaIpcCloseMemHandle(q->peer_grad[r]);
+        if (q->peer_flags[r]) cudaIpcCloseMemHandle(q->peer_flags[r]);
+    }
+    cudaFree(q->d_grad); cudaFree(q->d_flags); cudaFree(q->d_err);
+    delete q;
+    return 0;
+}
+
 extern "C" int cumind_selftest_division(uint64_t n_per_thread, uint64_t seed, int32_t max_divisor, uint64_t* d_counts2,
                                         void* stream) {
     if (!d_counts2 || max_divisor <= 0) return fail("cumind_selftest_division: bad argument");

@@ -168,6 +168,19 @@ size_t train_fused_work_bytes(const cumind_net_desc& d, int B);
 cudaError_t launch_train_fwd_bwd(const cumind_net_desc& d, const float* blob, const float* obs, const int32_t* actions, const float* tv,
                                  const float* tp, const float* tr, int B, int K, float* work, float* grad, float* losses, cudaStream_t st);
 
+// p2p_adamw.cu — gradient all-reduce over NVLink peer memory fused into AdamW (one process per GPU, CUDA IPC)
+constexpr int P2P_MAX_RANKS = 16;
+struct P2PArgs {
+    int rank, world;
+    const float* peer_grad[P2P_MAX_RANKS];   // every rank's gradient buffer as mapped here (own buffer at [rank])
+    long long* peer_flags[P2P_MAX_RANKS];    // every rank's flag array [2][P2P_MAX_RANKS]
+    float* sum_out;                          // optional: the summed gradient (tests)
+    int* err;                                // set when a peer did not arrive within the spin bound
+    int* count;                              // blocks of this rank that finished reading (reset by the pre-kernel)
+};
+cudaError_t launch_p2p_allreduce_adamw(const P2PArgs& a, float* p, float* m, float* v, const unsigned char* mask, size_t n, float lr, float b1,
+                                       float b2, float eps, float wd, long long* d_step, cudaStream_t st);
+
 // replay.cu — TreeBuffer's sum tree on the device (memory.py:190-299)
 cudaError_t launch_sumtree_update(double* tree, long long n_nodes, int depth, const long long* idx, const double* pri, long long n,
                                   cudaStream_t st);

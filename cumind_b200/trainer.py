@@ -164,8 +164,60 @@ class Trainer:
         # the hand-written loss + gradient kernel (train_fused.cu) when the network shape is covered; False = torch autograd
         self.use_fused_kernel = bool(self._lib.cumind_train_supported(C.byref(net._desc), int(config.num_unroll_steps)))
         self._fused_buf: Dict[int, Any] = {}
+        # torch.distributed on one node: the gradient all-reduce fused into AdamW over NVLink peer memory (csrc/p2p_adamw.cu)
+        # instead of an NCCL call; False (or a failed set-up on any rank) = one NCCL all-reduce of the flat gradient
+        self.use_p2p_allreduce = True
+        self._p2p, self._p2p_grad, self._p2p_tried = None, None, False
         self._graph, self._graph_key, self._graph_out, self._static = None, None, None, None
         self._state_stale = False
+
+    def _setup_p2p(self) -> bool:
+        """CUDA IPC exchange of the per-rank gradient buffers (once).  Every rank must call this at the same point."""
+        import socket
+
+        import torch.distributed as dist
+
+        self._p2p_tried = True
+        world, rank = dist.get_world_size(), dist.get_rank()
+        handle = C.c_void_p()
+        raw = (C.c_ubyte * 128)()
+        ok = world <= 16
+        if ok:
+            with torch.cuda.device(self._flat.device):
+                ok = self._lib.cumind_p2p_create(self._flat.numel(), rank, world, C.byref(handle), C.cast(raw, C.c_void_p)) == 0
+        info = [None] * world
+        dist.all_gather_object(info, (socket.gethostname(), bool(ok), bytes(raw)))
+        same_node = len({h for h, _, _ in info}) == 1
+        if ok and same_node and all(o for _, o, _ in info):
+            blob = b"".join(b for _, _, b in info)
+            with torch.cuda.device(self._flat.device):
+                ok = self._lib.cumind_p2p_open(handle, C.c_char_p(blob)) == 0
+        else:
+            ok = False
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(ok))
+        if not all(flags):
+            if handle.value:
+                self._lib.cumind_p2p_destroy(handle)
+            return False
+        self._p2p = handle
+        n, ptr = self._flat.numel(), int(self._lib.cumind_p2p_grad_ptr(handle))
+
+        class _View:   # the rank's peer-visible gradient buffer as a torch tensor (no copy)
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+        self._p2p_grad = torch.as_tensor(_View(), device=self._flat.device)
+        dist.barrier()
+        return True
+
+    def _p2p_active(self) -> bool:
+        if not (self.use_p2p_allreduce and torch.distributed.is_available() and torch.distributed.is_initialized()):
+            return False
+        if torch.distributed.get_world_size() < 2 or torch.distributed.get_backend() != "nccl":
+            return False
+        if not self._p2p_tried:
+            self._setup_p2p()
+        return self._p2p is not None
 
     def _load_optimizer_state(self) -> None:
         """agent.optimizer_state ({"count", "mu", "nu"}, moments flat in blob layout or None) -> the device buffers, IN PLACE
@@ -192,6 +244,10 @@ class Trainer:
         self._load_optimizer_state()
         self._agent_version = getattr(self.agent, "_state_version", 0)
         self._state_stale = False
+        if self._p2p is not None:      # the step counter (= barrier epoch) may have gone back: every rank reloads at the same point
+            torch.distributed.barrier()
+            _native.check(self._lib.cumind_p2p_reset(self._p2p))
+            torch.distributed.barrier()
 
     # ---- batch preparation (trainer.py:118-170) --------------------------------------------------
     def _n_step_returns(self, batch: Sequence[List[Dict[str, Any]]]) -> np.ndarray:
@@ -232,7 +288,7 @@ class Trainer:
             return forward_losses(self._flat, self._dims, torch.as_tensor(np.asarray(observations, np.float32)).to(dev),
                                   torch.as_tensor(np.asarray(actions)).to(dev), t, self.config.num_unroll_steps)
 
-    def _fwd_bwd_fused(self, observations, actions, targets):
+    def _fwd_bwd_fused(self, observations, actions, targets, grad_out=None):
         """cumind_train_loss_grad: the K-step unroll forward + backward in one kernel, gradient in blob layout."""
         B, K = int(observations.shape[0]), int(self.config.num_unroll_steps)
         buf = self._fused_buf.get(B)
@@ -242,6 +298,8 @@ class Trainer:
             buf = (torch.empty(need, dtype=torch.uint8, device=dev), torch.empty_like(self._flat), torch.empty(4, dtype=torch.float32, device=dev))
             self._fused_buf = {B: buf}
         work, grad, losses = buf
+        if grad_out is not None:
+            grad = grad_out
         obs = observations.to(torch.float32).contiguous()
         act = actions.to(torch.int32).contiguous()
         tv, tp, tr = (targets[k].to(torch.float32).contiguous() for k in ("values", "policies", "rewards"))
@@ -252,15 +310,20 @@ class Trainer:
         self.last_grad = grad
         return {"value_loss": losses[0], "policy_loss": losses[1], "reward_loss": losses[2], "total_loss": losses[3]}, grad
 
-    def _fwd_bwd(self, observations, actions, targets):
-        """loss -> grad of the flat parameter blob (the fused kernel, or torch autograd over views of the blob)."""
+    def _fwd_bwd(self, observations, actions, targets, grad_out=None):
+        """loss -> grad of the flat parameter blob (the fused kernel, or torch autograd over views of the blob); written to
+        `grad_out` when given (the peer-visible buffer of the fused all-reduce)."""
         if self.use_fused_kernel and tuple(actions.shape) == (observations.shape[0], int(self.config.num_unroll_steps)):
-            return self._fwd_bwd_fused(observations, actions, targets)
+            return self._fwd_bwd_fused(observations, actions, targets, grad_out)
         leaf = self._flat.detach().requires_grad_(True)   # fresh autograd leaf over the same storage
         losses = forward_losses(leaf, self._dims, observations, actions, targets, self.config.num_unroll_steps)
         total = losses["value_loss"] + losses["policy_loss"] + losses["reward_loss"]
         total.backward()
         grad = leaf.grad
+        if grad_out is not None:
+            with torch.no_grad():
+                grad_out.copy_(grad)
+            grad = grad_out
         self.last_grad = grad
         return {**{k: v.detach() for k, v in losses.items()}, "total_loss": total.detach()}, grad
 
@@ -274,9 +337,27 @@ class Trainer:
                 opt.b2, opt.eps, opt.weight_decay, C.c_void_p(self._step_dev.data_ptr()), 1.0 / world, _stream_ptr()))
             self.agent.network.update_from_device(self._flat)
 
-    def _eager_step(self, observations, actions, targets) -> Dict[str, torch.Tensor]:
-        """loss -> grad -> (all-reduce) -> AdamW -> push parameters; every launch on the current stream."""
+    def _apply_p2p(self) -> None:
+        """cumind_p2p_allreduce_adamw: wait for every rank's gradient, sum over NVLink peer memory, AdamW, parameter push."""
+        opt = self.agent.optimizer
+        with torch.no_grad():
+            _native.check(self._lib.cumind_p2p_allreduce_adamw(
+                self._p2p, C.c_void_p(self._flat.data_ptr()), C.c_void_p(self._m.data_ptr()), C.c_void_p(self._v.data_ptr()),
+                C.c_void_p(self._mask.data_ptr()), self._flat.numel(), opt.learning_rate, opt.b1, opt.b2, opt.eps, opt.weight_decay,
+                C.c_void_p(self._step_dev.data_ptr()), None, _stream_ptr()))
+            self.agent.network.update_from_device(self._flat)
+
+    def _eager_step(self, observations, actions, targets, collective: bool = True) -> Dict[str, torch.Tensor]:
+        """loss -> grad -> (all-reduce) -> AdamW -> push parameters; every launch on the current stream.  collective=False
+        (graph warm-up) keeps the step local: a rank that re-captures alone must not issue collectives its peers do not."""
+        if collective and self._p2p_active():
+            out, _ = self._fwd_bwd(observations, actions, targets, grad_out=self._p2p_grad)
+            self._apply_p2p()
+            return out
         out, grad = self._fwd_bwd(observations, actions, targets)
+        if not collective:
+            self._apply(grad, 1)
+            return out
         world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size()
@@ -292,9 +373,10 @@ class Trainer:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             state = (self._flat.detach().clone(), self._m.clone(), self._v.clone(), self._step_dev.clone())
+            distributed = torch.distributed.is_available() and torch.distributed.is_initialized()
             with torch.cuda.stream(side):
-                for _ in range(3):                       # warm-up outside the capture (allocator, cuBLAS handles)
-                    self._eager_step(*self._static)
+                for _ in range(3):                       # warm-up outside the capture (allocator, cuBLAS handles); local when
+                    self._eager_step(*self._static, collective=not distributed)   # distributed (see _eager_step)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             with torch.no_grad():                        # undo the warm-up updates
@@ -364,8 +446,8 @@ class Trainer:
         actions = torch.as_tensor(np.asarray(batch[1])).to(dev)
         targets = {k: torch.as_tensor(np.asarray(v)).to(dev) for k, v in batch[2].items()}
         distributed = torch.distributed.is_available() and torch.distributed.is_initialized()
-        if self.use_cuda_graph and not distributed:
-            out = self._graph_step(observations, actions, targets)
+        if self.use_cuda_graph and (not distributed or self._p2p_active()):
+            out = self._graph_step(observations, actions, targets)      # ONE graph, the fused peer-memory all-reduce included
         elif self.use_cuda_graph and self.graph_distributed:
             out = self._graph_step_distributed(observations, actions, targets)
         else:

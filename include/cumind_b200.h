@@ -311,6 +311,26 @@ int    cumind_train_loss_grad(const cumind_net_desc* desc, const float* d_params
                               const float* d_value_targets, const float* d_policy_targets, const float* d_reward_targets,
                               int32_t B, int32_t K, void* d_work, size_t work_bytes, float* d_grad, float* d_losses4, void* stream);
 
+/* Data-parallel train step: the all-reduce of the flat gradient fused into AdamW over NVLink peer memory (p2p_adamw.cu),
+ * one process per GPU.  Every rank: cumind_p2p_create (allocates its gradient buffer and flag array, returns two CUDA IPC
+ * handles as 128 bytes) -> exchange the handles (torch.distributed.all_gather_object) -> cumind_p2p_open(all handles in
+ * rank order).  Each step: write the local gradient to cumind_p2p_grad_ptr (cumind_train_loss_grad can write there
+ * directly), then cumind_p2p_allreduce_adamw on every rank: waits for all ranks' gradients (flags in peer memory), sums
+ * them in rank order with P2P loads (every rank computes the identical sum), applies optax.adamw with the 1/world scaling
+ * to the local parameters, and returns only when no peer still reads this rank's buffer.  d_step as in
+ * cumind_adamw_step_dev (incremented first; doubles as the barrier epoch).  d_sum_out (may be NULL) receives the summed
+ * gradient.  Graph-capturable; a peer that never arrives sets cumind_p2p_error instead of hanging (bounded spin). */
+typedef struct cumind_p2p cumind_p2p;
+int    cumind_p2p_create(size_t n, int32_t rank, int32_t world, cumind_p2p** out, void* h_handles128);
+int    cumind_p2p_open(cumind_p2p* p2p, const void* h_all_handles /* world x 128 bytes */);
+float* cumind_p2p_grad_ptr(cumind_p2p* p2p);
+int    cumind_p2p_allreduce_adamw(cumind_p2p* p2p, float* d_params, float* d_m, float* d_v, const uint8_t* d_mask, size_t n,
+                                  float lr, float b1, float b2, float eps, float weight_decay, int64_t* d_step,
+                                  float* d_sum_out, void* stream);
+int    cumind_p2p_reset(cumind_p2p* p2p);   /* after the step counter was set back: every rank, between two host barriers */
+int    cumind_p2p_error(cumind_p2p* p2p);
+int    cumind_p2p_destroy(cumind_p2p* p2p);
+
 /* Replay: the sum tree of TreeBuffer (src/cumind/data/memory.py:190-299) in device memory.
  * A flat float64 array of 2*tree_size-1 nodes, tree_size = the power of two >= capacity (memory.py:204-208).
  * cumind_sumtree_update applies `_update(tree_idx[k], priority[k])` (memory.py:249-253, 212-217) for k = 0..n-1 IN
