@@ -377,14 +377,14 @@ CM_DEVICE void search_team_body(const TeamParams& p) {
                         uint64_t* hb = hand + 4 * tm;
                         const long long tw0 = wclk ? clock64() : 0;
                         if (stage == 0) {
-                            tc_mbar_wait(hb + 0, job & 1u);                    // X0R: gathered rows of team tm
+                            tc_mbar_wait_spin(hb + 0, job & 1u);                    // X0R: gathered rows of team tm
                             const long long tw1 = wclk ? clock64() : 0;
                             wg_layer<NT, 64, RS>(wr, Wl, bias, x0t, x1t, nullptr, 0, 0, lane);
                             __syncwarp();
                             if (lane == 0) tc_mbar_arrive(hb + 1 + half);      // X1R[half]
                             if (wclk) { const long long tw2 = clock64(); lc0 += tw1 - tw0; lc1 += tw2 - tw1; }
                         } else {
-                            tc_mbar_wait(hb + 1 + half, job & 1u);
+                            tc_mbar_wait_spin(hb + 1 + half, job & 1u);
                             const long long tw1 = wclk ? clock64() : 0;
                             float* hid = p.tv.hidden + ((size_t)(t_begin + ts0) * (S_max + 1) + (size_t)(s + 1)) * H + 2 * lane;
                             wg_layer<NT, 64, RS>(wr, Wl, bias, x1t, x2t, hid, (size_t)(S_max + 1) * H, n_here - ts0, lane);
@@ -627,7 +627,7 @@ CM_DEVICE void search_team_body(const TeamParams& p) {
                     __syncwarp();
                     if (lane == 0) tc_mbar_arrive(hand + 4 * team);          // X0R: rows handed to the layer warpgroup
                     CM_CLK(c0, __float_as_int(x0[0]))
-                    tc_mbar_wait(hand + 4 * team + 3, job & 1u);             // X2R: new hidden rows in xt
+                    tc_mbar_wait_spin(hand + 4 * team + 3, job & 1u);             // X2R: new hidden rows in xt
                     ++job;
                     CM_CLK(c4, __float_as_int(xt[0]))
                 } else {

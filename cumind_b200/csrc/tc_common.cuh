@@ -29,6 +29,20 @@ CM_DEVICE void tc_mbar_wait(uint64_t* bar, uint32_t phase) {
             : "memory");
     } while (!ok);
 }
+// The same wait as a pure spin on test_wait: try_wait may park the thread for a system-chosen time before it looks again,
+// which is fine for bulk copies and costs microseconds on a hand-over that is a few hundred cycles away.
+CM_DEVICE void tc_mbar_wait_spin(uint64_t* bar, uint32_t phase) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_addr(bar)), "r"(phase)
+            : "memory");
+    } while (!ok);
+}
 // one arrival (release at CTA scope: the arriving thread's earlier writes, and those it has observed, are visible to a waiter)
 CM_DEVICE void tc_mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
