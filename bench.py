@@ -114,7 +114,10 @@ def make_inputs(B: int, rank: int):
     params = synthetic_params(PARAM_SEED)
     blob = P.flatten(params, OBS_SHAPE, A, H, L, CC)
     rng_obs = np.random.default_rng(OBS_SEED + 1000 * rank)
-    obs = (rng_obs.standard_normal((B,) + OBS_SHAPE) if len(OBS_SHAPE) == 1 else rng_obs.random((B,) + OBS_SHAPE)).astype(np.float32)
+    if len(OBS_SHAPE) == 1:
+        obs = rng_obs.standard_normal((B,) + OBS_SHAPE).astype(np.float32)
+    else:   # image observations are emulator frames: uint8, scaled to [0, 1] (the device-resident leg holds the floats)
+        obs = rng_obs.integers(0, 256, size=(B,) + OBS_SHAPE, dtype=np.uint8).astype(np.float32) / np.float32(255)
     noise = np.random.default_rng(NOISE_SEED + 1000 * rank).dirichlet([ALPHA] * A, size=B)
     return params, blob, obs, noise
 
@@ -400,9 +403,15 @@ def measure_search(args, rank: int, world: int, local_rank: int, dist, sampler, 
     # the caller (an environment loop) writes its observations and noise into the agent's pinned host buffers; every
     # step the GPU reads them from there (H2D inside the timed region) and writes actions + probabilities back (D2H)
     hb = agent.host_buffers(B)
-    hb["obs"][...] = obs
+    if len(OBS_SHAPE) == 3:   # frames cross PCIe as the uint8 the emulator produced; the device scales them (same floats)
+        hb["obs_u8"][...] = np.rint(obs * np.float32(255)).astype(np.uint8)
+        assert np.array_equal(hb["obs_u8"].astype(np.float32) / np.float32(255), obs)
+        obs = hb["obs_u8"]
+    else:
+        hb["obs"][...] = obs
+        obs = hb["obs"]
     hb["noise"][...] = noise
-    obs, noise = hb["obs"], hb["noise"]
+    noise = hb["noise"]
     for _ in range(3):
         agent.select_actions(obs, training=False, noise=noise)
     torch.cuda.synchronize()

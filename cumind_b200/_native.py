@@ -19,6 +19,7 @@ EXPORTS = [
     "cumind_net_destroy", "cumind_initial_inference", "cumind_recurrent_inference", "cumind_prediction", "cumind_softmax",
     "cumind_tree_bytes", "cumind_tree_create", "cumind_tree_destroy", "cumind_tree_get_view", "cumind_search",
     "cumind_search_plan", "cumind_search_phase_clocks", "cumind_search_stepwise", "cumind_select_actions_work_bytes", "cumind_select_actions_host",
+    "cumind_select_actions_host_u8",
     "cumind_tree_init_root", "cumind_select", "cumind_expand", "cumind_backup", "cumind_finalize", "cumind_dirichlet",
     "cumind_launch_count", "cumind_selftest_division", "cumind_adamw_step", "cumind_adamw_step_dev", "cumind_net_update_params_device",
     "cumind_sumtree_create", "cumind_sumtree_destroy", "cumind_sumtree_tree_size", "cumind_sumtree_clear", "cumind_sumtree_update",
@@ -105,6 +106,7 @@ def load():
     lib.cumind_search_phase_clocks.argtypes = search_args[:-1] + [vp, vp]
     lib.cumind_search_plan.argtypes = [vp, vp, C.POINTER(SearchCfg), C.POINTER(i32 * 8)]
     lib.cumind_select_actions_host.argtypes = [vp, vp, vp, C.POINTER(SearchCfg), vp, vp, vp, vp, sz, vp]
+    lib.cumind_select_actions_host_u8.argtypes = [vp, vp, vp, C.POINTER(SearchCfg), vp, vp, vp, vp, sz, vp]
     lib.cumind_tree_init_root.argtypes = [vp, vp, vp, C.POINTER(SearchCfg), vp, vp]
     lib.cumind_select.argtypes = [vp, C.POINTER(SearchCfg), vp]
     lib.cumind_expand.argtypes = [vp, vp, C.POINTER(SearchCfg), vp, vp]

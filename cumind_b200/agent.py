@@ -81,6 +81,7 @@ class Agent:
             need = int(lib.cumind_select_actions_work_bytes(C.byref(net._desc), B, A_cfg))
             work = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
             pin = {"obs": torch.empty((B,) + tuple(net.observation_shape), dtype=torch.float32).pin_memory(),
+                   "obs_u8": torch.empty((B,) + tuple(net.observation_shape) if len(net.observation_shape) == 3 else (1,), dtype=torch.uint8).pin_memory(),
                    "actions": torch.empty((B,), dtype=torch.int32).pin_memory(),
                    "probs": torch.empty((B, A_cfg), dtype=torch.float64).pin_memory(),
                    "noise": torch.empty((B, A), dtype=torch.float64).pin_memory()}
@@ -96,7 +97,7 @@ class Agent:
         staging copy when they are passed back to it: environments write their observations straight into them."""
         A_cfg = int(self.config.action_space_size)
         views = self._host_plan(int(B), A_cfg, min(A_cfg, self.network.action_space_size))["np"]
-        return {"obs": views["obs"], "noise": views["noise"]}
+        return {"obs": views["obs"], "noise": views["noise"], "obs_u8": views["obs_u8"]}
 
     def select_actions(self, observations: np.ndarray, training: bool = False, noise: Optional[np.ndarray] = None,
                        philox_seed: Optional[int] = None, tree_index_base: int = 0) -> Tuple[np.ndarray, np.ndarray]:
@@ -105,7 +106,9 @@ class Agent:
         training=True draws root noise on the device (Philox) unless `noise` [B,A] is given, and
         samples the actions on the host from the returned probabilities."""
         net, lib = self.network, self.mcts._lib
-        obs = np.ascontiguousarray(observations, dtype=np.float32)
+        # uint8 image frames go to the device as bytes (a quarter of the PCIe traffic) and are scaled there: float32(u8) / 255
+        as_u8 = isinstance(observations, np.ndarray) and observations.dtype == np.uint8 and len(net.observation_shape) == 3
+        obs = np.ascontiguousarray(observations) if as_u8 else np.ascontiguousarray(observations, dtype=np.float32)
         B = obs.shape[0]
         if tuple(obs.shape[1:]) != tuple(net.observation_shape):
             raise ValueError(f"expected observations of shape (B, {net.observation_shape}), got {obs.shape}")
@@ -123,14 +126,15 @@ class Agent:
         plan = self._host_plan(B, A_cfg, A)
         views, ptr = plan["np"], plan["ptr"]
         # inputs written in place into host_buffers() are already in the pinned memory the GPU reads
-        if obs.ctypes.data != views["obs"].ctypes.data:
-            views["obs"][...] = obs
+        okey = "obs_u8" if as_u8 else "obs"
+        if obs.ctypes.data != views[okey].ctypes.data:
+            views[okey][...] = obs
         if noise is not None and not (isinstance(noise, np.ndarray) and noise.ctypes.data == views["noise"].ctypes.data):
             views["noise"][...] = noise
         def call():
-            _native.check(lib.cumind_select_actions_host(
-                tree.handle, net._handle, ptr["obs"], C.byref(cfg), ptr["noise"] if noise is not None else plan["null"],
-                ptr["actions"], ptr["probs"], plan["wbase"], plan["need"], _stream_ptr()))
+            fn = lib.cumind_select_actions_host_u8 if as_u8 else lib.cumind_select_actions_host
+            _native.check(fn(tree.handle, net._handle, ptr[okey], C.byref(cfg), ptr["noise"] if noise is not None else plan["null"],
+                             ptr["actions"], ptr["probs"], plan["wbase"], plan["need"], _stream_ptr()))
 
         if torch.cuda.current_device() == self._device_index:
             call()

@@ -1262,7 +1262,7 @@ extern "C" int cumind_sumtree_read(const cumind_sumtree* t, double* d_out, void*
 // ------------------------------------------------------------------------------------------------
 // Agent.select_action for a batch, host buffers in / out (agent.py:61-89)
 // ------------------------------------------------------------------------------------------------
-struct WorkOffsets { size_t obs, hidden, noise, visits, probs, actions, total; };
+struct WorkOffsets { size_t obs, hidden, noise, visits, probs, actions, obs_u8, total; };
 static WorkOffsets work_offsets(const cumind_net_desc* d, int64_t B, int64_t A_cfg) {
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t osz = d->obs_ndim == 1 ? (size_t)d->obs_shape[0] : (size_t)d->obs_shape[0] * d->obs_shape[1] * d->obs_shape[2];
@@ -1274,6 +1274,7 @@ static WorkOffsets work_offsets(const cumind_net_desc* d, int64_t B, int64_t A_c
     o.visits = p;  p = al(p + B * A_cfg * sizeof(int32_t));
     o.probs = p;   p = al(p + B * A_cfg * sizeof(double));
     o.actions = p; p = al(p + B * sizeof(int32_t));
+    o.obs_u8 = p;  p = al(p + B * osz);
     o.total = p;
     return o;
 }
@@ -1292,10 +1293,28 @@ static void* mapped_ptr(const void* h) {
     return a.devicePointer;
 }
 
+static int select_actions_host_impl(cumind_tree* t, const cumind_net* n, const float* h_obs, const uint8_t* h_obs_u8, const cumind_search_cfg* c,
+                                    const double* h_noise, int32_t* h_actions, double* h_probs, void* d_work, size_t work_bytes, void* stream);
+
 extern "C" int cumind_select_actions_host(cumind_tree* t, const cumind_net* n, const float* h_obs, const cumind_search_cfg* c,
                                           const double* h_noise, int32_t* h_actions, double* h_probs, void* d_work,
                                           size_t work_bytes, void* stream) {
-    if (!t || !n || !c || !h_obs || !h_actions || !h_probs || !d_work) return fail("cumind_select_actions_host: NULL argument");
+    if (!h_obs) return fail("cumind_select_actions_host: NULL argument");
+    return select_actions_host_impl(t, n, h_obs, nullptr, c, h_noise, h_actions, h_probs, d_work, work_bytes, stream);
+}
+
+// The same call for uint8 observations (image frames as the emulator produces them): a quarter of the bytes over PCIe; the
+// device computes float32(u8) / 255 correctly rounded, i.e. exactly what the caller's `frames.astype(np.float32) / 255` gives.
+extern "C" int cumind_select_actions_host_u8(cumind_tree* t, const cumind_net* n, const uint8_t* h_obs_u8, const cumind_search_cfg* c,
+                                             const double* h_noise, int32_t* h_actions, double* h_probs, void* d_work,
+                                             size_t work_bytes, void* stream) {
+    if (!h_obs_u8) return fail("cumind_select_actions_host_u8: NULL argument");
+    return select_actions_host_impl(t, n, nullptr, h_obs_u8, c, h_noise, h_actions, h_probs, d_work, work_bytes, stream);
+}
+
+static int select_actions_host_impl(cumind_tree* t, const cumind_net* n, const float* h_obs, const uint8_t* h_obs_u8, const cumind_search_cfg* c,
+                                    const double* h_noise, int32_t* h_actions, double* h_probs, void* d_work, size_t work_bytes, void* stream) {
+    if (!t || !n || !c || !h_actions || !h_probs || !d_work) return fail("cumind_select_actions_host: NULL argument");
     const int B = t->tv.B, A_cfg = c->action_space_size;
     const WorkOffsets o = work_offsets(&n->desc, B, A_cfg);
     if (work_bytes < o.total) return fail("cumind_select_actions_host: work buffer too small");
@@ -1316,6 +1335,23 @@ extern "C" int cumind_select_actions_host(cumind_tree* t, const cumind_net* n, c
     const bool with_noise = c->noise_mode == 1;
     void *m_obs = mapped_ptr(h_obs), *m_noise = with_noise ? mapped_ptr(h_noise) : nullptr;
     void *m_actions = mapped_ptr(h_actions), *m_probs = mapped_ptr(h_probs);
+    if (h_obs_u8) {   // uint8 frames: copy engine for the frames (large), then convert on the device; the rest as for pageable buffers
+        unsigned char* d_u8 = w + o.obs_u8;
+        CM_CUDA(cudaMemcpyAsync(d_u8, h_obs_u8, (size_t)B * osz, cudaMemcpyHostToDevice, st));
+        if (with_noise) CM_CUDA(cudaMemcpyAsync(d_noise, h_noise, noise_bytes, cudaMemcpyHostToDevice, st));
+        CM_CUDA(launch_u8_to_f32(d_u8, d_obs, (size_t)B * osz, st));
+        g_launches += 1;
+        int rc = cumind_initial_inference(n, d_obs, B, d_hidden, nullptr, nullptr, c->net_mode, stream);
+        if (rc) return rc;
+        rc = search_impl(t, n, d_hidden, c, with_noise ? d_noise : nullptr, d_visits, d_probs, nullptr, stream, n->desc.obs_ndim == 1);
+        if (rc) return rc;
+        CM_CUDA(launch_argmax_first(d_probs, B, A_cfg, d_actions, st));
+        g_launches += 1;
+        CM_CUDA(cudaMemcpyAsync(h_actions, d_actions, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CM_CUDA(cudaMemcpyAsync(h_probs, d_probs, (size_t)B * A_cfg * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CM_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    }
     const bool zero_copy = m_obs && m_actions && m_probs && (!with_noise || m_noise) && obs_bytes <= ((size_t)4 << 20) && obs_bytes % 16 == 0 &&
                            noise_bytes % 16 == 0 && ((uintptr_t)m_obs | (uintptr_t)m_noise) % 16 == 0;
     // Small vector observations: no staging kernels at all — the encoder reads the observations and the search kernel the

@@ -104,6 +104,7 @@ cudaError_t launch_dirichlet(double* noise, int B, int A, double alpha, unsigned
                              unsigned long long tree_base, cudaStream_t st);
 cudaError_t launch_selftest_div(unsigned long long n_per_thread, unsigned long long seed, int max_d, unsigned long long* counts,
                                 cudaStream_t st);
+cudaError_t launch_u8_to_f32(const unsigned char* in, float* out, size_t n, cudaStream_t st);
 cudaError_t launch_argmax_first(const double* probs, int B, int A, int32_t* actions, cudaStream_t st);
 cudaError_t launch_stage_in(const void* h_a, void* d_a, size_t n_a, const void* h_b, void* d_b, size_t n_b, cudaStream_t st);
 cudaError_t launch_stage_out(const double* probs, int B, int A, int32_t* d_actions, int32_t* h_actions, double* h_probs, cudaStream_t st);

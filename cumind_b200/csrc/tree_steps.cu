@@ -319,6 +319,25 @@ __global__ void stage_out_kernel(const double* __restrict__ probs, int B, int A,
     }
 }
 
+// uint8 observations (image frames) -> float32 / 255, correctly rounded: the same value as observation.astype(float32) / 255
+__global__ void u8_to_f32_kernel(const uchar4* __restrict__ in, float4* __restrict__ out, size_t n4, const unsigned char* __restrict__ in1,
+                                 float* __restrict__ out1, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const uchar4 v = in[i];
+        out[i] = make_float4(__fdiv_rn((float)v.x, 255.0f), __fdiv_rn((float)v.y, 255.0f), __fdiv_rn((float)v.z, 255.0f), __fdiv_rn((float)v.w, 255.0f));
+    }
+    for (size_t i = 4 * n4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out1[i] = __fdiv_rn((float)in1[i], 255.0f);
+}
+cudaError_t launch_u8_to_f32(const unsigned char* in, float* out, size_t n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const size_t n4 = (((uintptr_t)in & 3) == 0) ? n / 4 : 0;
+    size_t blocks = (n / 4 + 255) / 256 + 1;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    u8_to_f32_kernel<<<(int)blocks, 256, 0, st>>>((const uchar4*)in, (float4*)out, n4, in, out, n);
+    return cudaGetLastError();
+}
+
 // Self-test of div_small (the table-driven division of the fused select): random and structured
 // numerators against the IEEE division, bitwise.  counts[0] = mismatches, counts[1] = cases.
 __global__ void selftest_div_kernel(unsigned long long n_per_thread, unsigned long long seed, int max_d,

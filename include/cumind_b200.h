@@ -265,6 +265,14 @@ int cumind_select_actions_host(cumind_tree* tree, const cumind_net* net, const f
                                int32_t* h_actions, double* h_probs, void* d_work, size_t work_bytes,
                                void* stream);
 
+/* The same call for uint8 observations (image frames): h_obs_u8 [B,*obs_shape] uint8; the device computes
+ * float32(u8) / 255 correctly rounded — what `frames.astype(np.float32) / 255` gives on the host — so the results equal
+ * cumind_select_actions_host on those floats, with a quarter of the bytes crossing PCIe. */
+int cumind_select_actions_host_u8(cumind_tree* tree, const cumind_net* net, const uint8_t* h_obs_u8,
+                                  const cumind_search_cfg* cfg, const double* h_noise,
+                                  int32_t* h_actions, double* h_probs, void* d_work, size_t work_bytes,
+                                  void* stream);
+
 /* Fine-grained phases (one launch each).  Reference anchors:
  *   cumind_tree_init_root : mcts.py:126-136  (root prediction softmax, expand, noise)
  *   cumind_select         : mcts.py:165-171  (Node.select_child / ucb_score, 51-76)

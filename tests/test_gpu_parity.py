@@ -641,6 +641,38 @@ def test_baseline_config2_full_shape_bf16_agent_against_exact():
     assert np.mean(np.abs(p_t - p_e)) <= 0.03, float(np.mean(np.abs(p_t - p_e)))
 
 
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+@pytest.mark.parametrize("shape,B", [((84, 84, 3), 37), ((21, 13, 5), 9), ((10, 10, 4), 130)], ids=["atari", "odd", "small"])
+def test_uint8_frames_equal_the_scaled_float_observations(shape, B, dtype):
+    """cumind_select_actions_host_u8: uint8 frames in, scaled on the device by float32(u8) / 255 — bit for bit the call
+    with frames.astype(float32) / 255 (what a caller of the reference's agent feeds it), in both arithmetic modes."""
+    from cumind_b200 import Config
+    from cumind_b200 import params as P
+    from cumind_b200.agent import Agent
+    from oracle import network_np as nn
+
+    A, H, L, Cc, S = 4, 32, 1, 32, 12
+    blob = nn.flatten_params(nn.random_params(shape, A, H, L, Cc, 3, bias_scale=0.05, bn_random=True), shape)
+    ag = Agent(Config(hidden_dim=H, num_blocks=L, num_simulations=S, action_space_size=A, observation_shape=shape, conv_channels=Cc,
+                      model_dtype=dtype))
+    ag.network.load_state(P.unflatten(blob, shape, A, H, L, Cc))
+    frames = np.random.default_rng(11).integers(0, 256, size=(B,) + shape, dtype=np.uint8)
+    frames[0], frames[-1] = 0, 255
+    noise = np.random.default_rng(12).dirichlet([0.3] * A, size=B)
+    a_f, p_f = ag.select_actions(frames.astype(np.float32) / np.float32(255), training=False, noise=noise)
+    d_f = ag.mcts.dump_trees()
+    a_u, p_u = ag.select_actions(frames, training=False, noise=noise)
+    d_u = ag.mcts.dump_trees()
+    assert np.array_equal(a_f, a_u) and hp.bits_equal(p_f, p_u)
+    for k in ("visit", "value_sum", "hidden", "prior"):
+        assert hp.bits_equal(d_f[k], d_u[k]), k
+    # frames written in place into the pinned buffer take the same path
+    hb = ag.host_buffers(B)
+    hb["obs_u8"][...] = frames
+    a_p, p_p = ag.select_actions(hb["obs_u8"], training=False, noise=noise)
+    assert np.array_equal(a_p, a_u) and hp.bits_equal(p_p, p_u)
+
+
 @pytest.mark.parametrize("shape", [((84, 84, 3), 32, 2, 64, 4), ((10, 10, 4), 16, 2, 16, 4), ((3, 84, 84), 32, 2, 64, 4), ((21, 13, 5), 32, 1, 32, 3)],
                          ids=lambda s: "x".join(map(str, s[0])))
 def test_tensor_core_conv_encoder_within_tolerance(shape):
