@@ -19,7 +19,8 @@ EXPORTS = [
     "cumind_net_destroy", "cumind_initial_inference", "cumind_recurrent_inference", "cumind_prediction", "cumind_softmax",
     "cumind_tree_bytes", "cumind_tree_create", "cumind_tree_destroy", "cumind_tree_get_view", "cumind_search",
     "cumind_search_plan", "cumind_search_phase_clocks", "cumind_search_stepwise", "cumind_select_actions_work_bytes", "cumind_select_actions_host",
-    "cumind_select_actions_host_u8",
+    "cumind_select_actions_host_u8", "cumind_replay_create", "cumind_replay_destroy", "cumind_replay_record_bytes", "cumind_replay_write",
+    "cumind_replay_gather", "cumind_replay_values",
     "cumind_tree_init_root", "cumind_select", "cumind_expand", "cumind_backup", "cumind_finalize", "cumind_dirichlet",
     "cumind_launch_count", "cumind_selftest_division", "cumind_adamw_step", "cumind_adamw_step_dev", "cumind_net_update_params_device",
     "cumind_sumtree_create", "cumind_sumtree_destroy", "cumind_sumtree_tree_size", "cumind_sumtree_clear", "cumind_sumtree_update",
@@ -140,6 +141,14 @@ def load():
     lib.cumind_sumtree_update.argtypes = [vp, vp, vp, i64, vp]
     lib.cumind_sumtree_sample.argtypes = [vp, vp, i64, vp, vp, vp]
     lib.cumind_sumtree_read.argtypes = [vp, vp, vp]
+    lib.cumind_replay_create.argtypes = [i64, i64, C.c_int32, C.c_int32, C.POINTER(vp)]
+    lib.cumind_replay_destroy.argtypes = [vp]
+    lib.cumind_replay_destroy.restype = None
+    lib.cumind_replay_record_bytes.argtypes = [vp]
+    lib.cumind_replay_record_bytes.restype = i64
+    lib.cumind_replay_write.argtypes = [vp, i64, vp, i64, vp]
+    lib.cumind_replay_gather.argtypes = [vp, vp, i64, i64, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.cumind_replay_values.argtypes = [vp, vp, vp, C.c_double, C.c_int32, vp, vp]
     _lib = lib
     return lib
 

@@ -1260,6 +1260,68 @@ extern "C" int cumind_sumtree_read(const cumind_sumtree* t, double* d_out, void*
 }
 
 // ------------------------------------------------------------------------------------------------
+// Trajectory records of the replay buffers in device memory (memory.py:13-85 holds them in a deque; trainer.py:118-170 reads them)
+// ------------------------------------------------------------------------------------------------
+struct cumind_replay {
+    unsigned char* d_ring;
+    long long capacity, obs_size, rec_bytes;
+    int A, K;
+};
+static long long replay_record_bytes(long long obs_size, int A, int K) {
+    const long long b = 16 + 4 * (2 * obs_size + A + 2 * (long long)K);
+    return (b + 15) / 16 * 16;
+}
+extern "C" int cumind_replay_create(int64_t capacity, int64_t obs_size, int32_t n_actions, int32_t unroll_steps, cumind_replay** out) {
+    if (!out || capacity < 1 || obs_size < 1 || n_actions < 1 || unroll_steps < 1) return fail("cumind_replay_create: bad argument");
+    cumind_replay* r = new cumind_replay();
+    r->capacity = capacity;
+    r->obs_size = obs_size;
+    r->A = n_actions;
+    r->K = unroll_steps;
+    r->rec_bytes = replay_record_bytes(obs_size, n_actions, unroll_steps);
+    cudaError_t e = cudaMalloc(&r->d_ring, (size_t)(r->rec_bytes * capacity));
+    if (e == cudaSuccess) e = cudaMemset(r->d_ring, 0, (size_t)(r->rec_bytes * capacity));
+    if (e != cudaSuccess) { delete r; return fail_cuda("cumind_replay_create", e); }
+    *out = r;
+    return 0;
+}
+extern "C" void cumind_replay_destroy(cumind_replay* r) {
+    if (!r) return;
+    cudaFree(r->d_ring);
+    delete r;
+}
+extern "C" int64_t cumind_replay_record_bytes(const cumind_replay* r) { return r ? r->rec_bytes : 0; }
+extern "C" int cumind_replay_write(cumind_replay* r, int64_t slot0, const void* records, int64_t n, void* stream) {
+    if (!r || !records || n < 0 || n > r->capacity || slot0 < 0 || slot0 >= r->capacity) return fail("cumind_replay_write: bad argument");
+    const long long first = std::min<long long>(n, r->capacity - slot0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (first > 0)
+        CM_CUDA(cudaMemcpyAsync(r->d_ring + (size_t)(slot0 * r->rec_bytes), records, (size_t)(first * r->rec_bytes), cudaMemcpyDefault, st));
+    if (n > first)   // the ring wraps
+        CM_CUDA(cudaMemcpyAsync(r->d_ring, (const unsigned char*)records + (size_t)(first * r->rec_bytes), (size_t)((n - first) * r->rec_bytes),
+                                cudaMemcpyDefault, st));
+    return 0;
+}
+extern "C" int cumind_replay_gather(const cumind_replay* r, const int64_t* d_index, int64_t head, int64_t n_valid, int32_t B, float* d_obs,
+                                    float* d_boot_obs, float* d_policy, float* d_rewards, int32_t* d_actions, double* d_partial,
+                                    int32_t* d_has_boot, int32_t* d_flags, void* stream) {
+    if (!r || !d_index || !d_obs || !d_boot_obs || !d_policy || !d_rewards || !d_actions || !d_partial || !d_has_boot || !d_flags || B < 1 ||
+        head < 0 || head >= r->capacity || n_valid < 0 || n_valid > r->capacity)
+        return fail("cumind_replay_gather: bad argument");
+    CM_CUDA(launch_replay_gather(r->d_ring, r->capacity, r->rec_bytes, r->obs_size, r->A, r->K, (const long long*)d_index, head, n_valid, B, d_obs,
+                                 d_boot_obs, d_policy, d_rewards, d_actions, d_partial, d_has_boot, d_flags, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+extern "C" int cumind_replay_values(const double* d_partial, const int32_t* d_has_boot, const float* d_boot_value, double discount_pow_n,
+                                    int32_t B, float* d_values, void* stream) {
+    if (!d_partial || !d_has_boot || !d_boot_value || !d_values || B < 1) return fail("cumind_replay_values: bad argument");
+    CM_CUDA(launch_replay_values(d_partial, d_has_boot, d_boot_value, discount_pow_n, B, d_values, (cudaStream_t)stream));
+    g_launches += 1;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Agent.select_action for a batch, host buffers in / out (agent.py:61-89)
 // ------------------------------------------------------------------------------------------------
 struct WorkOffsets { size_t obs, hidden, noise, visits, probs, actions, obs_u8, total; };

@@ -185,6 +185,11 @@ cudaError_t launch_p2p_allreduce_adamw(const P2PArgs& a, float* p, float* m, flo
 // replay.cu — TreeBuffer's sum tree on the device (memory.py:190-299)
 cudaError_t launch_sumtree_update(double* tree, long long n_nodes, int depth, const long long* idx, const double* pri, long long n,
                                   cudaStream_t st);
+cudaError_t launch_replay_gather(const unsigned char* ring, long long capacity, long long rec_bytes, long long obs_size, int A, int K,
+                                 const long long* index, long long head, long long n_valid, int B, float* obs, float* boot_obs, float* policy,
+                                 float* rewards, int* actions, double* partial, int* has_boot, int* flags, cudaStream_t st);
+cudaError_t launch_replay_values(const double* partial, const int* has_boot, const float* boot_value, double discount_pow_n, int B, float* values,
+                                 cudaStream_t st);
 cudaError_t launch_sumtree_sample(const double* tree, long long n_nodes, long long tree_size, const double* uniform, long long batch,
                                   long long* tree_idx, long long* data_idx, cudaStream_t st);
 

@@ -280,6 +280,22 @@ class Trainer:
                 actions[b, s], rewards[b, s] = step["action"], step["reward"]
         return obs, actions, {"values": values.astype(np.float32), "rewards": rewards, "policies": policies}
 
+    def _device_batch(self):
+        """_prepare_batch for a buffer with a DeviceTrajectoryStore: indices drawn as `memory.sample` draws them, rows
+        gathered from the records in HBM, bootstrap values from ONE target-network call over the batch, n-step targets
+        by cumind_replay_values.  The only host read is the two error counters (the reference's IndexError for a deque
+        index past the end, memory.py:272-273, and its RuntimeError for an empty trajectory, trainer.py:123-125)."""
+        store = self.memory.device_store
+        g = self.memory.sample_batch_device(self.config.batch_size)
+        oob, empty = g["flags"].tolist()
+        if oob:
+            raise IndexError("deque index out of range")
+        if empty:
+            raise RuntimeError("Encountered empty item in batch.")
+        _, _, boot_value = self.agent.target_network.initial_inference(g["boot_observations"])
+        values = store.n_step_values(g, boot_value)
+        return g["observations"], g["actions"], {"values": values, "rewards": g["rewards"], "policies": g["policies"]}
+
     # ---- the step -----------------------------------------------------------------------------------
     def compute_losses(self, observations, actions, targets) -> Dict[str, torch.Tensor]:
         dev = self._flat.device
@@ -440,11 +456,15 @@ class Trainer:
         if batch is None:
             if not self.memory.is_ready(self.config.min_memory_size, self.config.min_memory_pct):
                 return {}
-            batch = self._prepare_batch(self.memory.sample(self.config.batch_size))
+            if getattr(self.memory, "device_store", None) is not None:
+                batch = self._device_batch()      # sampled, gathered and targeted on the GPU
+            else:
+                batch = self._prepare_batch(self.memory.sample(self.config.batch_size))
         dev = self._flat.device
-        observations = torch.as_tensor(np.asarray(batch[0], np.float32)).to(dev)
-        actions = torch.as_tensor(np.asarray(batch[1])).to(dev)
-        targets = {k: torch.as_tensor(np.asarray(v)).to(dev) for k, v in batch[2].items()}
+        to_dev = lambda x, dt=None: x.to(dev) if torch.is_tensor(x) else torch.as_tensor(np.asarray(x, dt)).to(dev)
+        observations = to_dev(batch[0], np.float32)
+        actions = to_dev(batch[1])
+        targets = {k: to_dev(v) for k, v in batch[2].items()}
         distributed = torch.distributed.is_available() and torch.distributed.is_initialized()
         if self.use_cuda_graph and (not distributed or self._p2p_active()):
             out = self._graph_step(observations, actions, targets)      # ONE graph, the fused peer-memory all-reduce included

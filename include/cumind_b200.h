@@ -358,6 +358,36 @@ int cumind_sumtree_sample(const cumind_sumtree* tree, const double* d_uniform, i
                           int64_t* d_data_idx, void* stream);
 int cumind_sumtree_read(const cumind_sumtree* tree, double* d_out, void* stream);
 
+/* ---- trajectory records of the replay buffers in device memory ------------------------------------------------------
+ * The reference keeps trajectories (lists of step dicts) in a deque (memory.py:13-85) and Trainer._prepare_batch
+ * (trainer.py:118-170) reads, of every sampled trajectory: step 0's observation and policy, the first K =
+ * num_unroll_steps actions and rewards (zero padded), the discounted sum of its first td_steps rewards and — if it is
+ * longer than td_steps — the observation at td_steps for the bootstrap value.  A record is exactly that, fixed when
+ * the trajectory is stored; `capacity` records form a ring (slot = number of earlier adds mod capacity).
+ * Record layout (cumind_replay_record_bytes, a multiple of 16):
+ *     [0,8)   float64  sum_{i < min(len, td_steps)} reward_i * discount**i     (computed by the caller, in its arithmetic)
+ *     [8,12)  int32    trajectory length (0 = empty: flagged by the gather)
+ *     [12,16) int32    1 if the trajectory is longer than td_steps (the bootstrap observation is valid)
+ *     float32 observation_0[obs_size] | float32 bootstrap observation[obs_size] | float32 policy_0[A]
+ *     float32 rewards[K] | int32 actions[K]
+ * cumind_replay_write copies n packed records (host or device memory) to slots (slot0 + i) mod capacity.
+ * cumind_replay_gather builds a batch: row b comes from slot (head + d_index[b]) mod capacity, i.e. element d_index[b]
+ * of the reference's deque when `head` is the slot of its oldest element; an index outside [0, n_valid) counts in
+ * d_flags[0] (the reference's IndexError) and reads slot `head`; an empty trajectory counts in d_flags[1] (the
+ * reference's RuntimeError).  d_flags is int32[2], accumulated (the caller zeroes it).
+ * cumind_replay_values: values[b] = float32(partial[b] + discount_pow_n * float64(boot_value[b])) where has_boot[b],
+ * else float32(partial[b]) — the n-step return target of trainer.py:172-205. */
+typedef struct cumind_replay cumind_replay;
+int cumind_replay_create(int64_t capacity, int64_t obs_size, int32_t n_actions, int32_t unroll_steps, cumind_replay** out);
+void cumind_replay_destroy(cumind_replay* ring);
+int64_t cumind_replay_record_bytes(const cumind_replay* ring);
+int cumind_replay_write(cumind_replay* ring, int64_t slot0, const void* records, int64_t n, void* stream);
+int cumind_replay_gather(const cumind_replay* ring, const int64_t* d_index, int64_t head, int64_t n_valid, int32_t B,
+                         float* d_obs, float* d_boot_obs, float* d_policy, float* d_rewards, int32_t* d_actions,
+                         double* d_partial, int32_t* d_has_boot, int32_t* d_flags, void* stream);
+int cumind_replay_values(const double* d_partial, const int32_t* d_has_boot, const float* d_boot_value,
+                         double discount_pow_n, int32_t B, float* d_values, void* stream);
+
 /* Diagnostic: checks the table-driven small-divisor division used by the fused select kernel
  * (a/d from RN(1/d) with two FMA residual corrections) against the IEEE division on the device,
  * bitwise, over 148*4*256*n_per_thread random and structured numerators and divisors 1..max_divisor.

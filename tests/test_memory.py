@@ -204,3 +204,170 @@ def test_device_sum_tree_matches_host_tree_on_random_batches(cap):
         dev._dev.update([dev._dev.n_nodes], [1.0])
     host.clear(), dev.clear()
     assert not dev.sum_tree.any() and len(dev) == 0
+
+
+# ---- batched add / index draws (host) --------------------------------------------------------------------
+@pytest.mark.parametrize("cls", BUFFERS)
+def test_batch_indices_are_the_picks_of_sample(cls):
+    """_batch_indices draws from the same RNG stream as sample() and names the same elements."""
+    b = _create(cls, 40, Config())
+    for i in range(55):
+        b.add({"id": i})
+    if hasattr(b, "update_priorities"):
+        off = b.tree_size - 1 if cls is TreeBuffer else 0
+        b.update_priorities([off + 3, off + 9, off + 3], [2.0, 0.25, 5.0])
+    for k in (7, 40, 41):
+        random.seed(5), np.random.seed(5)
+        want = b.sample(k)
+        random.seed(5), np.random.seed(5)
+        idx = b._batch_indices(k)
+        assert [b.buffer[int(i)] for i in idx] == want
+
+
+@pytest.mark.parametrize("cls", BUFFERS)
+def test_add_batch_equals_adds_in_order(cls):
+    one, many = _create(cls, 13, Config()), _create(cls, 13, Config())
+    items = [{"id": i} for i in range(31)]
+    for lo, hi in ((0, 5), (5, 6), (6, 24), (24, 31)):
+        for it in items[lo:hi]:
+            one.add(it)
+        many.add_batch(items[lo:hi])
+        assert list(one.buffer) == list(many.buffer) and one._added == many._added
+        if cls is TreeBuffer:
+            assert np.array_equal(_bits(one.sum_tree), _bits(many.sum_tree))
+            assert (one.data_pointer, one.n_entries) == (many.data_pointer, many.n_entries)
+        if cls is PrioritizedMemoryBuffer:
+            assert list(one.priorities) == list(many.priorities)
+
+
+# ---- device sum tree: the parallel batched update -----------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("cap", [5, 64, 1000, 5000, 30000])
+def test_device_sum_tree_parallel_update_large_batches(cap):
+    """Batches longer than one chunk (1024), heavy duplication, and chunks that fall back to the ordered path (an
+    internal node or the last node among the indices): the tree equals the host tree bit for bit."""
+    import torch
+
+    rng = np.random.default_rng(cap + 1)
+    host = TreeBuffer(cap, 0.6, 1e-6)
+    dev = TreeBuffer(cap, 0.6, 1e-6, device=torch.device("cuda", 0))
+    items = list(range(min(cap, 2500)))
+    for it in items:
+        host.add(it)
+    dev.add_batch(items)
+    assert np.array_equal(_bits(host.sum_tree), _bits(dev.sum_tree))
+    for rnd, n in enumerate((1, 1024, 1025, 2600, 3333)):
+        span = min(len(items), [len(items), 7, len(items), 40, len(items)][rnd])
+        idx = [int(x) + host.tree_size - 1 for x in rng.integers(0, span, size=n)]
+        if rnd == 3:
+            idx[1700] = 0                        # an internal node in the second chunk
+        if rnd == 4:
+            idx[5] = 2 * host.tree_size - 2     # the last node in the first chunk
+        pri = [float(x) for x in np.abs(rng.standard_normal(n)) * 3.0]
+        host.update_priorities(idx, pri), dev.update_priorities(idx, pri)
+        assert np.array_equal(_bits(host.sum_tree), _bits(dev.sum_tree)), (cap, rnd)
+    u = rng.random(64)
+    assert np.array_equal(host.sample_indices(64, uniforms=u), dev.sample_indices(64, uniforms=u))
+
+
+# ---- trajectory records on the device ---------------------------------------------------------------------
+def _trajectories(rng, n, obs_shape, A, max_len):
+    out = []
+    for _ in range(n):
+        T = int(rng.integers(1, max_len + 1))
+        out.append([{"observation": rng.standard_normal(obs_shape).astype(np.float32), "action": int(rng.integers(0, A)),
+                     "reward": float(rng.standard_normal()), "policy": rng.dirichlet([1.0] * A).astype(np.float32)} for _ in range(T)])
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["uniform", "prioritized", "tree_host", "tree_device"])
+@pytest.mark.parametrize("obs_shape,cap,n_add", [((4,), 64, 40), ((4,), 32, 75), ((6, 5, 2), 16, 16)], ids=["filling", "wrapped", "image"])
+def test_device_batch_equals_prepare_batch(kind, obs_shape, cap, n_add):
+    """Trainer._device_batch (indices drawn like sample(), rows gathered from the records in HBM, n-step targets on the
+    device) == Trainer._prepare_batch(memory.sample(...)) under the same RNG seeds, bit for bit — including the
+    reference's quirk that a wrapped TreeBuffer indexes the deque with tree slots."""
+    import torch
+
+    from cumind_b200 import Agent
+    from cumind_b200.memory import DeviceTrajectoryStore
+    from cumind_b200.trainer import Trainer
+
+    A, K, n = 3, 4, 5
+    cfg = Config(hidden_dim=16, num_blocks=1, action_space_size=A, observation_shape=obs_shape, conv_channels=8, num_unroll_steps=K, td_steps=n,
+                 batch_size=12, num_simulations=2, discount=0.97, min_memory_size=1)
+    agent = Agent(cfg)
+    dev = torch.device("cuda", 0)
+    mk = {"uniform": lambda: MemoryBuffer(cap), "prioritized": lambda: PrioritizedMemoryBuffer(cap, 0.6, 1e-6, 0.4),
+          "tree_host": lambda: TreeBuffer(cap, 0.6, 1e-6), "tree_device": lambda: TreeBuffer(cap, 0.6, 1e-6, device=dev)}[kind]
+    host_buf, dev_buf = mk(), mk()
+    dev_buf.attach_device_store(DeviceTrajectoryStore(cap, obs_shape, A, K, n, cfg.discount, device=dev))
+    trajs = _trajectories(np.random.default_rng(3), n_add, obs_shape, A, 9)
+    for t in trajs[:7]:
+        host_buf.add(t), dev_buf.add(t)
+    for t in trajs[7:]:
+        host_buf.add(t)
+    dev_buf.add_batch(trajs[7:])
+    assert list(map(id, host_buf.buffer)) == list(map(id, dev_buf.buffer))
+    if hasattr(host_buf, "update_priorities"):
+        off = host_buf.tree_size - 1 if isinstance(host_buf, TreeBuffer) else 0
+        idx, pri = [off + 1, off + 5, off + 2], [3.0, 0.5, 1.5]
+        host_buf.update_priorities(idx, pri), dev_buf.update_priorities(idx, pri)
+    t_host, t_dev = Trainer(agent, host_buf, cfg), Trainer(agent, dev_buf, cfg)
+    for rnd in range(3):
+        random.seed(rnd), np.random.seed(rnd)
+        try:
+            want = t_host._prepare_batch(host_buf.sample(cfg.batch_size))
+        except IndexError:
+            want = IndexError
+        random.seed(rnd), np.random.seed(rnd)
+        if want is IndexError:
+            with pytest.raises(IndexError):
+                t_dev._device_batch()
+            continue
+        obs, act, tg = t_dev._device_batch()
+        assert np.array_equal(obs.cpu().numpy().view(np.uint32), want[0].view(np.uint32))
+        assert np.array_equal(act.cpu().numpy(), want[1])
+        for k in ("values", "rewards", "policies"):
+            assert np.array_equal(tg[k].cpu().numpy().view(np.uint32), want[2][k].view(np.uint32)), k
+
+
+@pytest.mark.gpu
+def test_device_store_flags_and_train_step():
+    """An empty trajectory raises the reference's RuntimeError when sampled; a train step from the device store equals
+    the step from the host deque under the same seeds."""
+    import torch
+
+    from cumind_b200 import Agent
+    from cumind_b200.memory import DeviceTrajectoryStore
+    from cumind_b200.trainer import Trainer
+
+    A, K, n, cap = 2, 3, 4, 50
+    cfg = Config(hidden_dim=32, num_blocks=2, action_space_size=A, observation_shape=(4,), num_unroll_steps=K, td_steps=n, batch_size=16,
+                 num_simulations=2, min_memory_size=1)
+    dev = torch.device("cuda", 0)
+    trajs = _trajectories(np.random.default_rng(8), 30, (4,), A, 12)
+    losses, blobs = [], []
+    for use_store in (False, True):
+        agent = Agent(cfg)                       # seeded by cfg.seed: the same initial parameters both times
+        buf = MemoryBuffer(cap)
+        if use_store:
+            buf.attach_device_store(DeviceTrajectoryStore(cap, (4,), A, K, n, cfg.discount, device=dev))
+        buf.add_batch(trajs)
+        tr = Trainer(agent, buf, cfg)
+        random.seed(1)
+        losses.append([tr.train_step()["total_loss"] for _ in range(3)])
+        blobs.append(agent.network.blob.copy())
+    assert losses[0] == losses[1] and np.isfinite(losses[0]).all()
+    assert np.array_equal(blobs[0].view(np.uint32), blobs[1].view(np.uint32))
+    bad = MemoryBuffer(4)
+    bad.attach_device_store(DeviceTrajectoryStore(4, (4,), A, K, n, cfg.discount, device=dev))
+    bad.add_batch([trajs[0], [], trajs[1]])
+    with pytest.raises(RuntimeError, match="empty item"):
+        Trainer(Agent(cfg), bad, cfg)._device_batch()
+    with pytest.raises(RuntimeError):
+        MemoryBuffer(4).sample_batch_device(2)
+    full = MemoryBuffer(4)
+    full.add([1])
+    with pytest.raises(RuntimeError):
+        full.attach_device_store(DeviceTrajectoryStore(4, (4,), A, K, n, cfg.discount, device=dev))
