@@ -448,7 +448,8 @@ def measure_search(args, rank: int, world: int, local_rank: int, dist, sampler, 
     if os.path.exists(tpath) and WORKLOAD == "cartpole" and B == 4096:
         traffic = json.load(open(tpath)).get("search_fused_dram_bytes_per_launch")
     plan = mcts.plan(B)
-    kernel_name = {"team": "search_team_kernel", "warp": "search_fused_kernel", "tensor-core": "search_tc_kernel"}.get(plan["schedule"], "stepwise")
+    kernel_name = {"team": "search_team_lw_kernel" if plan.get("layer_warpgroup_resident_k") else "search_team_kernel", "warp": "search_fused_kernel",
+                   "tensor-core": "search_tc_kernel"}.get(plan["schedule"], "stepwise")
     # SM-side view of the same kernel: the fp32 fused multiply-adds of the in-search network against the FFMA peak of the part
     # (148 SMs x 128 lanes x 2 flop x SM clock; MEASURED_PEAKS.json has no fp32 entry)
     fma_peak = 148 * 128 * 2 * (peaks.get("sm_max_mhz", 1965.0) * 1e6) / 1e12
