@@ -42,6 +42,28 @@ def test_oracle_backward_matches_finite_differences():
         assert abs(fd - gflat[idx]) <= 1e-6 + 1e-4 * abs(fd), (idx, fd, gflat[idx])
 
 
+def test_oracle_adamw_equals_an_independent_implementation():
+    """The optimiser semantics are pinned to something not written here: torch.optim.AdamW (decoupled weight decay,
+    bias-corrected moments, eps outside the square root) is the update optax.adamw documents (agent.py:48:
+    optax.adamw(learning_rate, weight_decay)); the oracle's adamw must follow it step for step in float64."""
+    import torch
+
+    from oracle import train_np as tn
+
+    rng = np.random.default_rng(0)
+    p0 = rng.standard_normal(257)
+    lr, wd = 3e-3, 1e-2
+    tp = torch.tensor(p0, dtype=torch.float64, requires_grad=True)
+    opt = torch.optim.AdamW([tp], lr=lr, weight_decay=wd, betas=(0.9, 0.999), eps=1e-8)
+    p, m, v = p0.copy(), np.zeros_like(p0), np.zeros_like(p0)
+    for step in range(1, 40):
+        g = rng.standard_normal(257) * (10.0 ** rng.integers(-3, 2))
+        tp.grad = torch.tensor(g, dtype=torch.float64)
+        opt.step()
+        p, m, v = tn.adamw(p, g, m, v, step, lr, wd)
+        assert np.allclose(p, tp.detach().numpy(), rtol=1e-12, atol=1e-14), step
+
+
 def _leaves(tree, obs_shape):
     from cumind_b200 import params as P
 
