@@ -21,17 +21,25 @@ class Trajectory(Sequence):
     dicts, iteration.  run_batch stores the steps of all environments step-major and hands out episodes as strided
     views, so the per-step host work does not grow with the number of environments."""
 
-    __slots__ = ("observation", "action", "reward", "policy", "done")
+    __slots__ = ("_bufs", "_s0", "_s1", "_env")
 
-    def __init__(self, observation, action, reward, policy, done):
-        self.observation, self.action, self.reward, self.policy, self.done = observation, action, reward, policy, done
+    def __init__(self, bufs, s0: int, s1: int, env: int):
+        # bufs = the step-major arrays (observation, action, reward, policy, done) of the whole run; the views are cut on
+        # access, so ending an episode costs one small object (hundreds of episodes end per lock-step early in training)
+        self._bufs, self._s0, self._s1, self._env = bufs, s0, s1, env
+
+    observation = property(lambda self: self._bufs[0][self._s0:self._s1, self._env])
+    action = property(lambda self: self._bufs[1][self._s0:self._s1, self._env])
+    reward = property(lambda self: self._bufs[2][self._s0:self._s1, self._env])
+    policy = property(lambda self: self._bufs[3][self._s0:self._s1, self._env])
+    done = property(lambda self: self._bufs[4][self._s0:self._s1, self._env])
 
     def __len__(self) -> int:
-        return len(self.action)
+        return self._s1 - self._s0
 
     def _step(self, i: int) -> Dict[str, Any]:
-        return {"observation": self.observation[i], "action": int(self.action[i]), "reward": float(self.reward[i]),
-                "policy": self.policy[i], "done": bool(self.done[i])}
+        b, t, e = self._bufs, self._s0 + i, self._env
+        return {"observation": b[0][t, e], "action": int(b[1][t, e]), "reward": float(b[2][t, e]), "policy": b[3][t, e], "done": bool(b[4][t, e])}
 
     def __getitem__(self, i):
         if isinstance(i, slice):
@@ -107,8 +115,8 @@ class SelfPlay:
         start = np.zeros(B, dtype=np.int64)
         finished: List[List[Trajectory]] = [[] for _ in range(B)]
 
-        def episode(i: int, s0: int, s1: int) -> Trajectory:
-            return Trajectory(obs_buf[s0:s1, i], act_buf[s0:s1, i], rew_buf[s0:s1, i], pol_buf[s0:s1, i], done_buf[s0:s1, i])
+        bufs = (obs_buf, act_buf, rew_buf, pol_buf, done_buf)
+        add_batch = getattr(self.memory, "add_batch", None) if self.memory is not None else None
 
         for step in range(num_steps):
             seed = None if philox_seed is None else philox_seed + step
@@ -116,11 +124,17 @@ class SelfPlay:
             next_observation, reward, terminated, truncated, _ = vec_env.step(actions)
             done = np.logical_or(terminated, truncated)
             obs_buf[step], act_buf[step], rew_buf[step], pol_buf[step], done_buf[step] = observation, actions, reward, policies, done
-            for i in np.nonzero(done)[0]:                      # only the environments whose episode just ended
-                ep = episode(int(i), int(start[i]), step + 1)
-                if self.memory is not None:
-                    self.memory.add(ep)
-                finished[i].append(ep)
-                start[i] = step + 1
+            ended = np.nonzero(done)[0]                        # only the environments whose episode just ended
+            if ended.size:
+                envs = ended.tolist()
+                eps = [Trajectory(bufs, s0, step + 1, i) for i, s0 in zip(envs, start[ended].tolist())]
+                if add_batch is not None:
+                    add_batch(eps)                             # one call (one device copy / sum-tree launch where those exist)
+                elif self.memory is not None:
+                    for ep in eps:
+                        self.memory.add(ep)
+                for i, ep in zip(envs, eps):
+                    finished[i].append(ep)
+                start[ended] = step + 1
             observation = np.asarray(next_observation)
-        return [finished[i] + ([episode(i, int(start[i]), num_steps)] if start[i] < num_steps else []) for i in range(B)]
+        return [finished[i] + ([Trajectory(bufs, int(start[i]), num_steps, i)] if start[i] < num_steps else []) for i in range(B)]
