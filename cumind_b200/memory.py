@@ -219,12 +219,13 @@ class DeviceSumTree:
         with self._torch.cuda.device(self.device):
             self._native.check(self._lib.cumind_sumtree_clear(self._handle, self._stream()))
 
-    def update(self, tree_idx, priority) -> None:
-        """`_update(tree_idx[k], priority[k])` for k = 0..n-1 IN ORDER (memory.py:249-253)."""
+    def update(self, tree_idx, priority, check: bool = True) -> None:
+        """`_update(tree_idx[k], priority[k])` for k = 0..n-1 IN ORDER (memory.py:249-253).  `check=False` skips the range check
+        of indices that are already on the device (it costs a device synchronisation)."""
         torch = self._torch
         if torch.is_tensor(tree_idx):
             idx = tree_idx.to(self.device, torch.int64)
-            lo, hi = (int(idx.min()), int(idx.max())) if idx.numel() else (0, 0)   # device indices: checked on the device (a sync)
+            lo, hi = (int(idx.min()), int(idx.max())) if idx.numel() and check else (0, 0)   # device indices: checked on the device (a sync)
         else:
             host_idx = np.asarray(tree_idx, dtype=np.int64)
             lo, hi = (int(host_idx.min()), int(host_idx.max())) if host_idx.size else (0, 0)

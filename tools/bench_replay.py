@@ -34,7 +34,7 @@ for cap, batch in [(1000, 1024), (100000, 1024), (1000000, 4096)]:
     s, m, e = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     s.record()
     for _ in range(20):
-        dev.update(d_idx, d_pri)
+        dev.update(d_idx, d_pri, check=False)
     m.record()
     for _ in range(20):
         dev.sample(d_u)
