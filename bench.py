@@ -282,7 +282,8 @@ def run_reference(args, rank: int, world: int):
 def workload_config(args, per_gpu: int, total_trees: int = 0):
     title = ("BASELINE configs[3]: large-batch search, %d CartPole-shaped trees sharded over the GPUs" % total_trees if total_trees == 65536 and WORKLOAD == "cartpole" else
              "CartPole-shaped trees, %d in total sharded over the GPUs (strong scaling)" % total_trees if total_trees > 0 and WORKLOAD == "cartpole" else
-             "BASELINE configs[1]: CartPole-shaped synthetic self-play" if WORKLOAD == "cartpole" else
+             "BASELINE configs[1]: CartPole-shaped synthetic self-play" if WORKLOAD == "cartpole" and per_gpu == 4096 else
+             "CartPole-shaped synthetic self-play (the configs[1] network at another batch size)" if WORKLOAD == "cartpole" else
              "CartPole-shaped, shipped-checkpoint width" if WORKLOAD == "cartpole-h128" else f"BASELINE configs[2] ({WORKLOAD}): image observations")
     mode = "fp32-exact network" if MODEL_DTYPE == "float32" else "bf16 tensor-core (tcgen05) network mode (search kernel: see plan)"
     return {"workload": f"{title}, B={per_gpu} trees per GPU, S={args.sims} simulations, "
