@@ -884,7 +884,7 @@ static int search_impl(cumind_tree* t, const cumind_net* n, const float* d_root_
         q.seed = c->seed;
         q.tree_base = c->tree_index_base;
         q.n_sqrt = 2 * t->tv.S_max + 4;
-        q.pdl = pdl ? 1 : 0;
+        q.pdl = 0;   // as for the warp schedule below: measured 0.08 ms slower per step at 32 768 trees with the dependent launch
         CM_CUDA(launch_search_tc(q, n->sm_count, (cudaStream_t)stream));
         g_launches += 1;
         return 0;

@@ -23,4 +23,4 @@ for f in sorted(glob.glob('gpurun_out/${tag}_bench_*.json')):
         print(f.split('/')[-1], 'ms/step', round(d['ms_per_step'],4), 'value %.3e'%d['value'], d['plan']['schedule'], 'kernel_ms', round(d['roofline']['kernel_ms'],4), 'e2e', round(d['e2e']['ms_per_step'],4))
     except Exception as e: print(f,'ERR',e)
 PY
-tail -2 gpurun_out/${tag}_selfplay.log gpurun_out/${tag}_replay.log gpurun_out/${tag}_train.log
+for f in selfplay replay train; do tail -n 3 gpurun_out/${tag}_$f.log; done
