@@ -29,12 +29,8 @@ namespace cm {
 // chase of one shared-memory load per level instead of one L2 round trip per level, and the backup re-scores the
 // children of every parent on the path with the record loads of several levels in flight together.
 // Without CACHE (trees whose node count does not fit) every walk scores its way down from HBM / L2.
-// CACHE: 0 = none, 1 = 16-bit node indices, 2 = 8-bit node indices (trees of fewer than 255 nodes: half the shared memory,
-// one more CTA per SM)
-template <int H, int CACHE>
-__global__ void __launch_bounds__(128, CACHE == 2 ? 3 : 1) search_tc_kernel(const SearchTcParams p) {
-    using CT = typename std::conditional<CACHE == 2, uint8_t, uint16_t>::type;
-    constexpr int kNone = CACHE == 2 ? 0xFF : 0xFFFF;
+template <int H, bool CACHE>
+__global__ void __launch_bounds__(128) search_tc_kernel(const SearchTcParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const TcPackLayout& pk = p.pk;
     unsigned char* w_s = smem;                        // the whole pack (bf16 tiles, fp32 biases, fp32 embedding)
@@ -44,8 +40,8 @@ __global__ void __launch_bounds__(128, CACHE == 2 ? 3 : 1) search_tc_kernel(cons
     uint64_t* bar_w = reinterpret_cast<uint64_t*>(rc_s + p.n_sqrt);
     uint64_t* bar_mma = bar_w + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 2);
-    CT* nxt_s = reinterpret_cast<CT*>(bar_w + 4);                        // CACHE: [N][128]
-    CT* path_s = nxt_s + (size_t)p.tv.N * 128;                            // CACHE: [S_max + 2][128]
+    uint16_t* nxt_s = reinterpret_cast<uint16_t*>(bar_w + 4);            // CACHE: [N][128]
+    uint16_t* path_s = nxt_s + (size_t)p.tv.N * 128;                      // CACHE: [S_max + 2][128]
     constexpr int NP = 16;
     constexpr uint32_t TMEM_COLS = (H + NP <= 32) ? 32 : (H + NP <= 64) ? 64 : (H + NP <= 128) ? 128 : 256;
 
@@ -201,7 +197,7 @@ __global__ void __launch_bounds__(128, CACHE == 2 ? 3 : 1) search_tc_kernel(cons
             exp_node[0] = 0;
             if constexpr (CACHE) {
                 nxt_s[tid] = 1;   // every root child unvisited: the first one
-                for (int a = 0; a < A; ++a) nxt_s[(1 + a) * 128 + tid] = (CT)kNone;
+                for (int a = 0; a < A; ++a) nxt_s[(1 + a) * 128 + tid] = 0xFFFF;
             }
         }
 
@@ -213,8 +209,8 @@ __global__ void __launch_bounds__(128, CACHE == 2 ? 3 : 1) search_tc_kernel(cons
                 // selection: follow the cached choices from the root to the first unexpanded node
                 if (live) {
                     int c = nxt_s[tid];
-                    while (c != kNone) {
-                        path_s[plen * 128 + tid] = (CT)node;
+                    while (c != 0xFFFF) {
+                        path_s[plen * 128 + tid] = (uint16_t)node;
                         ++plen;
                         node = c;
                         c = nxt_s[node * 128 + tid];
@@ -306,8 +302,8 @@ __global__ void __launch_bounds__(128, CACHE == 2 ? 3 : 1) search_tc_kernel(cons
                 const double v = (double)val;
                 if constexpr (CACHE) {
                     // Node.expand: the leaf's next visit takes its first child (all scores +inf, max() keeps the first)
-                    nxt_s[node * 128 + tid] = (CT)cbase;
-                    for (int a = 0; a < A; ++a) nxt_s[(cbase + a) * 128 + tid] = (CT)kNone;
+                    nxt_s[node * 128 + tid] = (uint16_t)cbase;
+                    for (int a = 0; a < A; ++a) nxt_s[(cbase + a) * 128 + tid] = 0xFFFF;
                     // backup (mcts.py:199-203) from the root down to the leaf's parent, and for every parent P the choice its
                     // next visit will make (Node.select_child, 67-76).  The only records read are the children blocks of
                     // the parents: P's own old record sits in the block of ITS parent (the root's is loaded once), and the
@@ -358,7 +354,7 @@ __global__ void __launch_bounds__(128, CACHE == 2 ? 3 : 1) search_tc_kernel(cons
                                             if (a == 0 || sc > best_sc) { best = a; best_sc = sc; }
                                         }
                                     }
-                                    nxt_s[P * 128 + tid] = (CT)(base[d] + best);
+                                    nxt_s[P * 128 + tid] = (uint16_t)(base[d] + best);
                                 }
                             }
                         }
@@ -404,7 +400,7 @@ __global__ void __launch_bounds__(128, CACHE == 2 ? 3 : 1) search_tc_kernel(cons
     if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int H, int CACHE>
+template <int H, bool CACHE>
 static cudaError_t launch_hc(const SearchTcParams& p, int sm_count, size_t smem, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(search_tc_kernel<H, CACHE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -424,9 +420,8 @@ template <int H>
 static cudaError_t launch_h(const SearchTcParams& p, int sm_count, cudaStream_t st) {
     const size_t base = p.pk.total_bytes + (size_t)128 * H * 2 + (size_t)2 * p.n_sqrt * sizeof(double) + 64;
     const size_t cache = ((size_t)p.tv.N + (size_t)p.tv.S_max + 2) * 128 * sizeof(uint16_t);
-    if (p.tv.N < 0xFF && !getenv("CUMIND_TC_CACHE16")) return launch_hc<H, 2>(p, sm_count, base + cache / 2, st);
-    if (p.tv.N < 0xFFFF && base + cache <= 200 * 1024) return launch_hc<H, 1>(p, sm_count, base + cache, st);
-    return launch_hc<H, 0>(p, sm_count, base, st);
+    if (p.tv.N < 0xFFFF && base + cache <= 200 * 1024) return launch_hc<H, true>(p, sm_count, base + cache, st);
+    return launch_hc<H, false>(p, sm_count, base, st);
 }
 
 cudaError_t launch_search_tc(const SearchTcParams& p, int sm_count, cudaStream_t st) {
