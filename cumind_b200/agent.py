@@ -33,6 +33,9 @@ class AdamW:
         return {"count": 0, "mu": np.zeros_like(blob), "nu": np.zeros_like(blob)}
 
 
+_current_device = getattr(torch._C, "_cuda_getDevice", torch.cuda.current_device)
+
+
 class Agent:
     def __init__(self, config: Config, existing_state: Optional[Dict[str, Any]] = None):
         self.config = config
@@ -107,10 +110,13 @@ class Agent:
         samples the actions on the host from the returned probabilities."""
         net, lib = self.network, self.mcts._lib
         # uint8 image frames go to the device as bytes (a quarter of the PCIe traffic) and are scaled there: float32(u8) / 255
-        as_u8 = isinstance(observations, np.ndarray) and observations.dtype == np.uint8 and len(net.observation_shape) == 3
-        obs = np.ascontiguousarray(observations) if as_u8 else np.ascontiguousarray(observations, dtype=np.float32)
+        obs = observations
+        as_u8 = False
+        if type(obs) is not np.ndarray or obs.dtype != np.float32 or not obs.flags.c_contiguous:   # (the common case skips all of this)
+            as_u8 = isinstance(obs, np.ndarray) and obs.dtype == np.uint8 and len(net.observation_shape) == 3
+            obs = np.ascontiguousarray(obs) if as_u8 else np.ascontiguousarray(obs, dtype=np.float32)
         B = obs.shape[0]
-        if tuple(obs.shape[1:]) != tuple(net.observation_shape):
+        if obs.shape[1:] != tuple(net.observation_shape):
             raise ValueError(f"expected observations of shape (B, {net.observation_shape}), got {obs.shape}")
         A_cfg = int(self.config.action_space_size)
         A = min(A_cfg, net.action_space_size)
@@ -127,16 +133,19 @@ class Agent:
         views, ptr = plan["np"], plan["ptr"]
         # inputs written in place into host_buffers() are already in the pinned memory the GPU reads
         okey = "obs_u8" if as_u8 else "obs"
-        if obs.ctypes.data != views[okey].ctypes.data:
-            views[okey][...] = obs
-        if noise is not None and not (isinstance(noise, np.ndarray) and noise.ctypes.data == views["noise"].ctypes.data):
-            views["noise"][...] = noise
+        dst = views[okey]
+        if obs is not dst and obs.ctypes.data != dst.ctypes.data:
+            dst[...] = obs
+        if noise is not None:
+            dst = views["noise"]
+            if noise is not dst and not (isinstance(noise, np.ndarray) and noise.ctypes.data == dst.ctypes.data):
+                dst[...] = noise
         def call():
             fn = lib.cumind_select_actions_host_u8 if as_u8 else lib.cumind_select_actions_host
             _native.check(fn(tree.handle, net._handle, ptr[okey], C.byref(cfg), ptr["noise"] if noise is not None else plan["null"],
                              ptr["actions"], ptr["probs"], plan["wbase"], plan["need"], _stream_ptr()))
 
-        if torch.cuda.current_device() == self._device_index:
+        if _current_device() == self._device_index:
             call()
         else:
             with torch.cuda.device(self.device):

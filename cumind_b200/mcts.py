@@ -140,6 +140,14 @@ class MCTS:
 
     def _cfg(self, noise_mode: int, seed: int = 0, tree_index_base: int = 0) -> _native.SearchCfg:
         c = self.config
+        # the configuration is read at call time (tests mutate it after construction, tests/test_mcts.py:274); the struct of
+        # the previous call is reused when nothing it is built from has changed
+        key = (c.num_simulations, c.action_space_size, c.c_puct, c.exploration_fraction, c.dirichlet_alpha, noise_mode, self.network.net_mode,
+               self.tree_mode, getattr(c, "discount", 1.0), self.lanes_per_tree, self.schedule, self.teams_per_cta, self.net_warps_per_team,
+               self.trees_per_team, seed, tree_index_base)
+        last = getattr(self, "_cfg_cache", None)
+        if last is not None and last[0] == key:
+            return _native.SearchCfg.from_buffer_copy(last[1])   # a copy: callers may edit their struct
         cfg = _native.SearchCfg()
         cfg.num_simulations = int(c.num_simulations)
         cfg.action_space_size = int(c.action_space_size)
@@ -159,6 +167,7 @@ class MCTS:
         cfg.trees_per_team = int(self.trees_per_team)
         cfg.seed = int(seed) & (2**64 - 1)
         cfg.tree_index_base = int(tree_index_base)
+        self._cfg_cache = (key, _native.SearchCfg.from_buffer_copy(cfg))
         return cfg
 
     # ---- reference API -------------------------------------------------------------------------

@@ -22,7 +22,13 @@ from . import _native, params as P
 from .prng import Rngs
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream_ptr() -> C.c_void_p:
+    """The current CUDA stream of the current device as a pointer (the raw accessor skips building a Stream object)."""
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
