@@ -695,7 +695,9 @@ static int plan_team(const cumind_tree* t, const cumind_net* n, const cumind_sea
     // layer-warpgroup mode prefers up to four small teams (8 tree slots each) over two large ones: the chain of one
     // simulation is mostly latency, so more teams in flight overlap more of it and a team's layers are two short jobs
     const bool lw_wanted = H == 64 && n->desc.num_blocks == 2 && c->schedule != CUMIND_SCHED_TEAM_CLASSIC && G <= 8;
-    if (lw_wanted && c->trees_per_team <= 0 && c->teams_per_cta <= 0 && tps <= 32 && G <= 4) TT = 8;
+    // (also beyond one round per SM: shared memory holds ~28 trees per CTA whatever the slot count, and with 16 slots per team the
+    // layer warps would compute 16 rows for 7 trees — measured 1.51 ms instead of 0.52 ms at 8192 trees)
+    if (lw_wanted && c->trees_per_team <= 0 && c->teams_per_cta <= 0 && G <= 4) TT = 8;
     if (!team_variant_ok(G, TT)) { why = "no team kernel for this lane mapping"; return 1; }
     const int ntw = (TT + TPW - 1) / TPW;
     int nmw = c->net_warps_per_team > 0 ? c->net_warps_per_team : 4;
@@ -801,9 +803,12 @@ static int plan_team(const cumind_tree* t, const cumind_net* n, const cumind_sea
 // CUMIND_SCHED_AUTO: the team schedule wins while every tree of an SM is in flight at once (its trees live in
 // shared memory, so it holds a few dozen per SM; measured 0.33 vs 0.39 ms at 28 trees per SM); beyond one
 // round per CTA the warp schedule, which keeps its trees in HBM/L2 and runs 100+ per SM, is faster.
+// With the layer warpgroup two nearly full rounds still win: 8192 trees (BASELINE configs[3] on 8 GPUs) take 0.518 ms per
+// step in two rounds of 4736 against 0.545 ms on the warp schedule, while 6144 trees take the same 0.508 ms against 0.472 ms.
 static bool team_is_preferred(const TeamPlan& tp, int sm_count) {
     const long long in_flight = (long long)tp.p.n_team * tp.p.tpt * (tp.grid < sm_count ? tp.grid : sm_count);
-    return in_flight >= tp.p.tv.B;
+    if (in_flight >= tp.p.tv.B) return true;
+    return tp.p.lw > 0 && tp.p.tv.B <= 2 * in_flight && 100LL * tp.p.tv.B >= 77LL * 2 * in_flight;
 }
 
 extern "C" int cumind_search_stepwise(cumind_tree* t, const cumind_net* n, const float* d_root_hidden, const cumind_search_cfg* c,

@@ -340,6 +340,38 @@ def test_baseline_config4_full_size_schedules_agree_and_invariants_hold():
     assert np.array_equal(visits[lo_:hi_].cpu().numpy(), o["out_visits"]) and np.array_equal(probs[lo_:hi_].cpu().numpy(), o["out_probs"])
 
 
+def test_two_round_batches_take_the_team_kernel_and_match_the_oracle():
+    """BASELINE configs[3] on 8 GPUs is 8192 trees per GPU: two nearly full rounds of the layer-warpgroup team kernel, which
+    AUTO prefers there (0.52 ms against 0.54 ms on the warp schedule); 7000 and 9600 trees stay on the warp schedule.
+    Every tree of the 8192 against the C oracle, bit for bit."""
+    from cumind_b200 import _native
+    from cumind_b200.mcts import MCTS
+    from oracle import network_np as nn
+
+    A, H, S = 2, 64, 12
+    blob = nn.flatten_params(nn.random_params((4,), A, H, 2, 32, 9), (4,))
+    net = _network((4,), A, H, 2, 32, blob)
+    mcts = MCTS(net, _Cfg(S, A))
+    sm = torch_sm_count()
+    if sm == 148:
+        assert [mcts.plan(b)["schedule"] for b in (4096, 7000, 8192, 9600)] == ["team", "warp", "team", "warp"]
+    B = 8192
+    obs = np.random.default_rng(3).standard_normal((B, 4)).astype(np.float32)
+    noise = np.random.default_rng(4).dirichlet([0.3] * A, size=B)
+    desc = lo.make_desc((4,), A, H, 2)
+    h, _, _ = lo.initial_inference(desc, blob, obs)
+    o = lo.search(desc, blob, h, S, A, 1.25, 0.25, noise)
+    probs, visits = mcts.search_batch(net.representation_network(obs), noise=noise)
+    _assert_trees_equal(mcts, o, S, A)
+    assert np.array_equal(visits, o["out_visits"]) and np.array_equal(probs, o["out_probs"])
+
+
+def torch_sm_count() -> int:
+    import torch
+
+    return torch.cuda.get_device_properties(0).multi_processor_count
+
+
 def test_select_actions_host_path_matches_oracle():
     """Agent.select_actions -> cumind_select_actions_host (host buffers in/out) == oracle actions."""
     from cumind_b200 import Config
