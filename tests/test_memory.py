@@ -371,3 +371,37 @@ def test_device_store_flags_and_train_step():
     full.add([1])
     with pytest.raises(RuntimeError):
         full.attach_device_store(DeviceTrajectoryStore(4, (4,), A, K, n, cfg.discount, device=dev))
+
+
+@pytest.mark.gpu
+def test_self_play_feeds_the_device_store_and_the_trainer_reads_it():
+    """The whole loop on the device side: SelfPlay.run_batch ends episodes into memory.add_batch (lazy Trajectory views packed
+    into HBM records), Trainer.train_step samples / gathers / targets on the GPU; the device batch equals the host batch of
+    the same draw."""
+    import torch
+
+    from cumind_b200 import Agent
+    from cumind_b200.envs import CartPoleVec
+    from cumind_b200.memory import DeviceTrajectoryStore
+    from cumind_b200.self_play import SelfPlay
+    from cumind_b200.trainer import Trainer
+
+    cfg = Config(hidden_dim=32, num_simulations=6, batch_size=16, td_steps=3, num_unroll_steps=3, min_memory_size=4)
+    agent = Agent(cfg)
+    dev = torch.device("cuda", 0)
+    memory = TreeBuffer(256, cfg.per_alpha, cfg.per_epsilon, device=dev)
+    memory.attach_device_store(DeviceTrajectoryStore(256, cfg.observation_shape, cfg.action_space_size, cfg.num_unroll_steps, cfg.td_steps,
+                                                     cfg.discount, device=dev))
+    SelfPlay(agent, memory).run_batch(CartPoleVec(64, seed=3), num_steps=30, philox_seed=5)
+    assert len(memory) > 16
+    trainer = Trainer(agent, memory, cfg)
+    random.seed(7)
+    obs, act, tg = trainer._device_batch()
+    random.seed(7)
+    idx = memory._batch_indices(cfg.batch_size).cpu().numpy()
+    want = trainer._prepare_batch([memory.buffer[int(i)] for i in idx])
+    assert np.array_equal(obs.cpu().numpy().view(np.uint32), want[0].view(np.uint32)) and np.array_equal(act.cpu().numpy(), want[1])
+    for k in ("values", "rewards", "policies"):
+        assert np.array_equal(tg[k].cpu().numpy().view(np.uint32), want[2][k].view(np.uint32)), k
+    info = trainer.train_step()
+    assert np.isfinite(info["total_loss"])
