@@ -267,7 +267,9 @@ int cumind_select_actions_host(cumind_tree* tree, const cumind_net* net, const f
 
 /* The same call for uint8 observations (image frames): h_obs_u8 [B,*obs_shape] uint8; the device computes
  * float32(u8) / 255 correctly rounded — what `frames.astype(np.float32) / 255` gives on the host — so the results equal
- * cumind_select_actions_host on those floats, with a quarter of the bytes crossing PCIe. */
+ * cumind_select_actions_host on those floats, with a quarter of the bytes crossing PCIe.  Batches of 512 or more frames are
+ * copied in two slices on an internal second stream (one per device, created on first use) while the encoder already works
+ * on the first; the call still returns with every result in place.  One call per device at a time. */
 int cumind_select_actions_host_u8(cumind_tree* tree, const cumind_net* net, const uint8_t* h_obs_u8,
                                   const cumind_search_cfg* cfg, const double* h_noise,
                                   int32_t* h_actions, double* h_probs, void* d_work, size_t work_bytes,
