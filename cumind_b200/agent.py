@@ -120,6 +120,8 @@ class Agent:
             raise ValueError(f"expected observations of shape (B, {net.observation_shape}), got {obs.shape}")
         A_cfg = int(self.config.action_space_size)
         A = min(A_cfg, net.action_space_size)
+        if B == 0:   # an empty batch is an empty result, not an error
+            return np.zeros(0, dtype=np.int32), np.zeros((0, A_cfg), dtype=np.float64)
         tree = self.mcts._tree(B, int(self.config.num_simulations), A)
         mode = 0
         if noise is not None:

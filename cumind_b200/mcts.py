@@ -200,6 +200,11 @@ class MCTS:
         S = int(self.config.num_simulations)
         if S <= 0:
             raise ValueError(f"num_simulations must be positive, got {S}")
+        if B == 0:   # an empty batch is an empty result, not an error (no launch)
+            self.last_root_value = torch.empty((0,), dtype=torch.float64, device=net.device)
+            visits = torch.empty((0, A_cfg), dtype=torch.int32, device=net.device)
+            probs = torch.empty((0, A_cfg), dtype=torch.float64, device=net.device)
+            return (probs, visits) if return_device else (probs.cpu().numpy(), visits.cpu().numpy())
         tree = self._tree(B, S, A)
         d_noise = None
         mode = 0

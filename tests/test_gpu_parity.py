@@ -796,6 +796,22 @@ def test_odd_hidden_sizes_take_a_valid_path_and_stay_bit_exact(shape):
     assert tuple(nx.shape) == (B, H)
 
 
+def test_empty_and_single_tree_batches():
+    """Edge sizes of the batched entry points: an empty batch returns empty arrays without a launch; a batch of one equals
+    the reference-style single call."""
+    from cumind_b200 import Agent, Config
+
+    agent = Agent(Config(hidden_dim=32, num_simulations=7, action_space_size=3, observation_shape=(4,)))
+    a, p = agent.select_actions(np.zeros((0, 4), dtype=np.float32))
+    assert a.shape == (0,) and p.shape == (0, 3) and a.dtype == np.int32 and p.dtype == np.float64
+    probs, visits = agent.mcts.search_batch(np.zeros((0, 32), dtype=np.float32))
+    assert probs.shape == (0, 3) and visits.shape == (0, 3)
+    obs = np.random.default_rng(0).standard_normal(4).astype(np.float32)
+    a1, p1 = agent.select_actions(obs[None], training=False)
+    a0, p0 = agent.select_action(obs, training=False)
+    assert int(a1[0]) == a0 and hp.bits_equal(p1[0], p0)
+
+
 def test_error_paths_raise_python_exceptions():
     import torch
 
