@@ -754,11 +754,23 @@ __global__ void __launch_bounds__(256) pool_dense_bf16_kernel(const __nv_bfloat1
         for (int job = warp; job < NJ * slices; job += nwarps) {     // (chunk j, slice sl): rows y = sl, sl + slices, ...
             const int j = job % NJ, sl = job / NJ;
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int yy = sl; yy < Ho; yy += slices) {
-                const uint4* row = reinterpret_cast<const uint4*>(xi + ((size_t)yy * NJ + j) * Wo * 8);
-                for (int xx = lane; xx < Wo; xx += 32) {
-                    const uint4 v = row[xx];
-                    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+            // the (row, pixel) pairs of this slice as one index space, eight 16-byte loads of a lane in flight before the first
+            // is used (a row of 42 pixels leaves a third of the lanes idle on its second pass otherwise)
+            const int rows = (Ho - sl + slices - 1) / slices, items = rows * Wo;
+            for (int i0 = lane; i0 < items; i0 += 32 * 8) {
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + 32 * u;
+                    v[u] = make_uint4(0, 0, 0, 0);
+                    if (i < items) {
+                        const int r = i / Wo, xx = i - r * Wo;
+                        v[u] = *reinterpret_cast<const uint4*>(xi + (((size_t)(sl + r * slices) * NJ + j) * Wo + xx) * 8);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[q]));
